@@ -1,0 +1,139 @@
+/* kzgpu.h -- C ABI of the B200 (sm_100a) KZG-MSM / NTT library (libkzgpu.so).
+ *
+ * The reference (swusjask/kzg-snark) is pure Python and has no FFI of its own; its
+ * drop-in boundary is the Python surface of kzg.py and fft_ff.py.
+ * The functions below are what a ctypes/cffi binding under those modules calls; each
+ * cites the reference code it replaces.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative KZGPU_E* code; it never throws and
+ *    never calls back into Python.  kzgpu_last_error() gives the message of the last
+ *    failure on the calling thread's library context.
+ *  - field elements cross the boundary as little-endian uint64 limbs of the CANONICAL
+ *    residue in [0, modulus): 4 limbs for both scalar fields and the BN254 base field,
+ *    6 limbs for the BLS12-381 base field.  Montgomery form never leaves the device.
+ *  - G1 points cross as affine (x, y) = 2 * fp_limbs64 limbs; the point at infinity is
+ *    (0, 0) (py_ecc's Z1 = (1, 1, 0), kzg.py:42, is mapped to it by the host shim).
+ *  - pointers are caller-owned host buffers unless the name starts with d_ (device
+ *    pointers obtained from kzgpu_alloc).
+ *  - one caller thread at a time; one CUDA device per process (the multi-GPU layout is
+ *    one process per GPU).
+ */
+#ifndef KZGPU_H
+#define KZGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KZGPU_OK            0
+#define KZGPU_EINVAL       -1   /* bad argument (size, curve id, non power of two ...) */
+#define KZGPU_ECUDA        -2   /* CUDA runtime failure (no device, OOM, launch error) */
+#define KZGPU_ENOTINIT     -3   /* kzgpu_init not called */
+#define KZGPU_ERANGE       -4   /* operand not reduced / degree exceeds the SRS (kzg.py:103-106) */
+#define KZGPU_EHANDLE      -5   /* unknown SRS handle */
+
+/* curve ids: the two curve_type strings of KZG.__init__ (kzg.py:26-37) */
+#define KZGPU_BN254         0
+#define KZGPU_BLS12_381     1
+
+/* ---- context ----------------------------------------------------------------------- */
+int kzgpu_init(int device);                  /* cudaSetDevice + streams; idempotent */
+int kzgpu_shutdown(void);                    /* frees SRS handles, NTT plans, workspaces */
+int kzgpu_last_error(char* buf, size_t cap);
+int kzgpu_device_info(char* name, size_t cap, int* sm_count, size_t* total_mem);
+int kzgpu_fp_limbs64(int curve);             /* 4 (BN254) or 6 (BLS12-381); <0 on bad id */
+
+/* ---- device memory (bench / multi-GPU plumbing; lets callers keep data resident) ---- */
+int kzgpu_alloc(void** d_ptr, size_t bytes);
+int kzgpu_free(void* d_ptr);
+int kzgpu_h2d(void* d_dst, const void* src, size_t bytes);
+int kzgpu_d2h(void* dst, const void* d_src, size_t bytes);
+int kzgpu_sync(void);
+/* CUDA-event timing on the library's stream (bench.py: device time of a bracketed region) */
+int kzgpu_timer_start(void);
+int kzgpu_timer_stop(float* ms);
+
+/* ---- SRS: the commitment key ck = [tau^i * G1] (kzg.py:69-72, consumed at :99,:115) -- */
+/* Upload n affine points (canonical limbs); converted to Montgomery form on the device and
+ * kept resident (ck is passed on every commit/open call, SURVEY.md section 7 hard part 4). */
+int kzgpu_srs_create(int curve, const uint64_t* affine_xy, size_t n, uint64_t* handle);
+/* Device-side replacement of the setup loop kzg.py:69-72 for a given secret tau
+ * (canonical, 4 limbs): points[i] = tau^i * G1, i < n. */
+int kzgpu_srs_generate(int curve, const uint64_t* tau, size_t n, uint64_t* handle);
+int kzgpu_srs_destroy(uint64_t handle);
+int kzgpu_srs_size(uint64_t handle, size_t* n);
+/* read back `count` points starting at `first` as canonical affine limbs */
+int kzgpu_srs_read(uint64_t handle, size_t first, size_t count, uint64_t* affine_xy);
+
+/* ---- MSM: KZG.commit's inner loop, sum_i scalars[i] * ck[first + i]  (kzg.py:108-116) -- */
+/* scalars: n * 4 limbs, canonical mod r.  out_affine_xy: 2 * fp_limbs64 limbs; *is_inf = 1
+ * and out = (0,0) when the sum is the identity (zero polynomial -> Z1, kzg.py:109).
+ * KZGPU_ERANGE if first + n exceeds the SRS (the degree check kzg.py:103-106). */
+int kzgpu_msm(uint64_t handle, size_t first, const uint64_t* scalars, size_t n,
+              uint64_t* out_affine_xy, int* is_inf);
+/* same with scalars already on the device */
+int kzgpu_msm_dev(uint64_t handle, size_t first, const uint64_t* d_scalars, size_t n,
+                  uint64_t* out_affine_xy, int* is_inf);
+/* k polynomials of one commit() call (kzg.py:102): scalars concatenated, lens[j] limbs-of-4 counts */
+int kzgpu_msm_batch(uint64_t handle, const uint64_t* scalars, const size_t* lens, size_t k,
+                    uint64_t* out_affine_xy, int* is_inf);
+/* Partial sum for point-sharded multi-GPU MSM: result left un-normalised as XYZZ in
+ * Montgomery form (4 * fp_limbs64 limbs), to be all-gathered and folded by kzgpu_g1_fold. */
+int kzgpu_msm_partial_dev(uint64_t handle, size_t first, const uint64_t* d_scalars, size_t n,
+                          uint64_t* d_out_xyzz);
+/* sum of `count` XYZZ partials (device) -> canonical affine on the host */
+int kzgpu_g1_fold(int curve, const uint64_t* d_xyzz, size_t count,
+                  uint64_t* out_affine_xy, int* is_inf);
+
+/* ---- NTT: fft_ff / ifft_ff (fft_ff.py:3-58) and the coset variant ---------------------- */
+/* In place, natural order in and out:  out[k] = sum_j data[j] * (shift^j) * w^(j k)
+ * inverse != 0: uses w^-1 and scales by n^-1 (fft_ff.py:53-58); with a shift, output j is
+ * additionally multiplied by shift^-j (inverse of the forward coset transform).
+ * n must be a power of two (fft_ff.py:74) and w a canonical element (4 limbs) whose order
+ * is caller-guaranteed (fft_ff.py:77-78 is checked by the host shim).  field = curve id
+ * (the scalar field of that curve).  coset_shift may be NULL. */
+int kzgpu_ntt(int field, uint64_t* data, size_t n, const uint64_t* w, int inverse,
+              const uint64_t* coset_shift);
+int kzgpu_ntt_dev(int field, uint64_t* d_data, size_t n, const uint64_t* w, int inverse,
+                  const uint64_t* coset_shift);
+/* `batch` independent vectors of the same length n, contiguous */
+int kzgpu_ntt_batch(int field, uint64_t* data, size_t n, size_t batch, const uint64_t* w,
+                    int inverse, const uint64_t* coset_shift);
+int kzgpu_ntt_batch_dev(int field, uint64_t* d_data, size_t n, size_t batch, const uint64_t* w,
+                        int inverse, const uint64_t* coset_shift);
+
+/* ---- open: KZG.open (kzg.py:122-159) ---------------------------------------------------- */
+/* polys: k coefficient vectors concatenated (low -> high, 4 limbs each), lens[j] coefficients.
+ * Computes P = sum_j xi^(j+1) * poly_j (kzg.py:148-150), W = (P - P(z)) / (X - z)
+ * (kzg.py:153-154) and returns commit(W) (kzg.py:157).  eval_out (4 limbs, may be NULL)
+ * receives P(z). */
+int kzgpu_open(uint64_t handle, const uint64_t* polys, const size_t* lens, size_t k,
+               const uint64_t* z, const uint64_t* xi, uint64_t* out_affine_xy, int* is_inf,
+               uint64_t* eval_out);
+/* the polynomial half alone: combination + synthetic division, quotient returned to the host
+ * (max(lens) - 1 coefficients; *quot_len receives the count) */
+int kzgpu_open_quotient(int field, const uint64_t* polys, const size_t* lens, size_t k,
+                        const uint64_t* z, const uint64_t* xi, uint64_t* quotient,
+                        size_t* quot_len, uint64_t* eval_out);
+
+/* ---- diagnostics used by the parity tests and bench.py ---------------------------------- */
+/* elementwise Montgomery-core check: out[i] = a[i] op b[i] in the chosen field.
+ * which: 0 = Fp(curve), 1 = Fr(curve); op: 0 mul, 1 add, 2 sub, 3 inverse(a). */
+int kzgpu_field_op(int curve, int which, int op, const uint64_t* a, const uint64_t* b,
+                   uint64_t* out, size_t n);
+/* throughput microbenchmarks (DESIGN.md "integer roofline"): runs `iters` dependent
+ * operations per thread on blocks*threads threads and returns the elapsed device ms.
+ * kind: 0 = IMAD.WIDE.U32 carry chain (raw pipe), 1 = Fp(BN254) Montgomery mul,
+ *       2 = Fp(BLS12-381) Montgomery mul, 3 = XYZZ mixed add BN254, 4 = XYZZ mixed add BLS */
+int kzgpu_microbench(int kind, int blocks, int threads, int iters, float* ms, double* ops);
+/* number of kernel launches issued by the library since init (bench.py "gpu_launches") */
+int kzgpu_launch_count(uint64_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KZGPU_H */

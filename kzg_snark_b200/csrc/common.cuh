@@ -1,0 +1,62 @@
+// Library context shared by the translation units of libkzgpu.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <string>
+#include "../../include/kzgpu.h"
+#include "params_gen.cuh"
+#include "curve.cuh"
+
+struct KzgpuCtx {
+  bool inited = false;
+  int device = -1;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  uint64_t launches = 0;
+  char err[512] = {0};
+};
+
+KzgpuCtx& kz_ctx();
+int kz_fail(int code, const char* fmt, ...);
+
+#define KZ_REQUIRE_INIT() \
+  do { if (!kz_ctx().inited) return kz_fail(KZGPU_ENOTINIT, "kzgpu_init has not been called"); } while (0)
+
+#define KZ_CUDA(expr) \
+  do { cudaError_t e__ = (expr); \
+       if (e__ != cudaSuccess) return kz_fail(KZGPU_ECUDA, "%s failed: %s (%s:%d)", #expr, \
+                                              cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
+
+// after a kernel launch: count it and surface launch-configuration errors
+#define KZ_LAUNCHED() \
+  do { kz_ctx().launches++; KZ_CUDA(cudaGetLastError()); } while (0)
+
+// device scratch that grows on demand and is reused between calls
+struct KzScratch {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes);
+  void release();
+};
+
+static inline size_t kz_div_up(size_t a, size_t b) { return (a + b - 1) / b; }
+
+// 64-bit-limb canonical <-> 32-bit-limb Fe (little endian: identical byte layout)
+template <class P> static inline Fe<P> kz_fe_from_u64(const uint64_t* w) {
+  Fe<P> r;
+  for (int i = 0; i < P::N; i++) r.v[i] = (uint32_t)(w[i / 2] >> (32 * (i & 1)));
+  return r;
+}
+template <class P> static inline void kz_fe_to_u64(const Fe<P>& a, uint64_t* w) {
+  for (int i = 0; i < P::N / 2; i++) w[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
+}
+template <class P> static inline bool kz_fe_reduced(const Fe<P>& a) {
+  for (int i = P::N - 1; i >= 0; i--) {
+    if (a.v[i] < P::mod(i)) return true;
+    if (a.v[i] > P::mod(i)) return false;
+  }
+  return false;   // equal to the modulus
+}

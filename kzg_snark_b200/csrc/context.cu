@@ -1,0 +1,286 @@
+// Library context, device-memory plumbing, field self-test and throughput microbenchmarks.
+#include "common.cuh"
+#include <cstring>
+
+void kz_ntt_release();
+void kz_msm_release();
+void kz_poly_release();
+
+KzgpuCtx& kz_ctx() {
+  static KzgpuCtx ctx;
+  return ctx;
+}
+
+int kz_fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(kz_ctx().err, sizeof(kz_ctx().err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int KzScratch::ensure(size_t bytes) {
+  if (bytes <= cap) return 0;
+  if (p) { cudaFree(p); p = nullptr; cap = 0; }
+  size_t want = bytes + bytes / 8;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    e = cudaMalloc(&p, bytes);
+    want = bytes;
+  }
+  if (e != cudaSuccess) { p = nullptr; return kz_fail(KZGPU_ECUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
+  cap = want;
+  return 0;
+}
+
+void KzScratch::release() {
+  if (p) cudaFree(p);
+  p = nullptr; cap = 0;
+}
+
+namespace {
+
+template <class P>
+__global__ void field_op_kernel(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fe<P> x, y, r;
+  for (int k = 0; k < P::N; k++) { x.v[k] = a[i * P::N + k]; y.v[k] = b ? b[i * P::N + k] : 0; }
+  x = fe_to_mont<P>(x);
+  y = fe_to_mont<P>(y);
+  if (op == 0) r = fe_mul<P>(x, y);
+  else if (op == 1) r = fe_add<P>(x, y);
+  else if (op == 2) r = fe_sub<P>(x, y);
+  else r = fe_inv<P>(x);
+  r = fe_from_mont<P>(r);
+  for (int k = 0; k < P::N; k++) out[i * P::N + k] = r.v[k];
+}
+
+template <class P>
+int field_op_impl(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  KzgpuCtx& cx = kz_ctx();
+  size_t bytes = n * P::N * 4;
+  uint32_t *da = nullptr, *db = nullptr, *dout = nullptr;
+  KZ_CUDA(cudaMalloc(&da, bytes));
+  KZ_CUDA(cudaMalloc(&dout, bytes));
+  KZ_CUDA(cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, cx.stream));
+  if (b) {
+    KZ_CUDA(cudaMalloc(&db, bytes));
+    KZ_CUDA(cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, cx.stream));
+  }
+  field_op_kernel<P><<<(unsigned)kz_div_up(n, 128), 128, 0, cx.stream>>>(op, da, db, dout, n);
+  KZ_LAUNCHED();
+  KZ_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, cx.stream));
+  KZ_CUDA(cudaStreamSynchronize(cx.stream));
+  cudaFree(da); cudaFree(db); cudaFree(dout);
+  return 0;
+}
+
+// --- microbenchmarks ---------------------------------------------------------------------
+// raw IMAD.WIDE.U32(.X) issue rate: 4 independent 8-limb carry chains per thread
+__global__ void mb_imad_kernel(uint32_t* sink, int iters, uint32_t seed) {
+  uint32_t acc[4][8], a[8];
+  for (int i = 0; i < 8; i++) a[i] = seed * (i + 3) + threadIdx.x;
+  for (int c = 0; c < 4; c++)
+    for (int i = 0; i < 8; i++) acc[c][i] = seed + c * 17 + i;
+  uint32_t top = 0;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      MpPrims<8>::mad_even(acc[c], a, acc[(c + 1) & 3][0], top);       // 4 IMAD.WIDE each
+      MpPrims<8>::mad_even(acc[c], a + 1, acc[(c + 2) & 3][1], top);
+    }
+  }
+  uint32_t s = top;
+  for (int c = 0; c < 4; c++)
+    for (int i = 0; i < 8; i++) s ^= acc[c][i];
+  if (s == 0x12345678u) sink[0] = s;
+}
+
+template <class P> __global__ void mb_mul_kernel(uint32_t* sink, int iters, uint32_t seed) {
+  Fe<P> x[4];
+  for (int c = 0; c < 4; c++)
+    for (int i = 0; i < P::N; i++) x[c].v[i] = (seed * (c + 1) + i * 7 + threadIdx.x) & 0x0fffffffu;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) x[c] = fe_mul<P>(x[c], x[(c + 1) & 3]);
+  }
+  uint32_t s = 0;
+  for (int c = 0; c < 4; c++)
+    for (int i = 0; i < P::N; i++) s ^= x[c].v[i];
+  if (s == 0x12345678u) sink[0] = s;
+}
+
+template <class P> __global__ void mb_madd_kernel(uint32_t* sink, int iters, uint32_t seed) {
+  XYZZ<P> acc;
+  Affine<P> pt;
+  for (int i = 0; i < P::N; i++) {
+    uint32_t v = (seed + i * 13 + threadIdx.x) & 0x0fffffffu;
+    acc.x.v[i] = v; acc.y.v[i] = v ^ 0x55; acc.zz.v[i] = v + 9; acc.zzz.v[i] = v + 11;
+    pt.x.v[i] = v + 3; pt.y.v[i] = v + 5;
+  }
+  for (int it = 0; it < iters; it++) {
+    xyzz_madd<P>(acc, pt);
+    pt.x.v[0] ^= acc.x.v[0] & 1;     // keep the operand live and varying
+  }
+  uint32_t s = 0;
+  for (int i = 0; i < P::N; i++) s ^= acc.x.v[i] ^ acc.y.v[i] ^ acc.zz.v[i] ^ acc.zzz.v[i];
+  if (s == 0x12345678u) sink[0] = s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kzgpu_init(int device) {
+  KzgpuCtx& cx = kz_ctx();
+  if (cx.inited) {
+    if (device == cx.device) return 0;
+    return kz_fail(KZGPU_EINVAL, "already initialised on device %d", cx.device);
+  }
+  int count = 0;
+  KZ_CUDA(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return kz_fail(KZGPU_EINVAL, "device %d out of range (%d devices)", device, count);
+  KZ_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  KZ_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return kz_fail(KZGPU_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  cx.sm_count = prop.multiProcessorCount;
+  KZ_CUDA(cudaStreamCreateWithFlags(&cx.stream, cudaStreamNonBlocking));
+  KZ_CUDA(cudaEventCreate(&cx.ev0));
+  KZ_CUDA(cudaEventCreate(&cx.ev1));
+  cx.device = device;
+  cx.inited = true;
+  cx.launches = 0;
+  return 0;
+}
+
+int kzgpu_shutdown(void) {
+  KzgpuCtx& cx = kz_ctx();
+  if (!cx.inited) return 0;
+  cudaStreamSynchronize(cx.stream);
+  kz_ntt_release();
+  kz_msm_release();
+  kz_poly_release();
+  cudaEventDestroy(cx.ev0);
+  cudaEventDestroy(cx.ev1);
+  cudaStreamDestroy(cx.stream);
+  cx.inited = false;
+  cx.device = -1;
+  return 0;
+}
+
+int kzgpu_last_error(char* buf, size_t cap) {
+  if (!buf || cap == 0) return KZGPU_EINVAL;
+  strncpy(buf, kz_ctx().err, cap - 1);
+  buf[cap - 1] = 0;
+  return 0;
+}
+
+int kzgpu_device_info(char* name, size_t cap, int* sm_count, size_t* total_mem) {
+  KZ_REQUIRE_INIT();
+  cudaDeviceProp prop;
+  KZ_CUDA(cudaGetDeviceProperties(&prop, kz_ctx().device));
+  if (name && cap) { strncpy(name, prop.name, cap - 1); name[cap - 1] = 0; }
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (total_mem) *total_mem = prop.totalGlobalMem;
+  return 0;
+}
+
+int kzgpu_fp_limbs64(int curve) {
+  if (curve == KZGPU_BN254) return 4;
+  if (curve == KZGPU_BLS12_381) return 6;
+  return KZGPU_EINVAL;
+}
+
+int kzgpu_alloc(void** d_ptr, size_t bytes) {
+  KZ_REQUIRE_INIT();
+  if (!d_ptr) return kz_fail(KZGPU_EINVAL, "null pointer");
+  KZ_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 1));
+  return 0;
+}
+
+int kzgpu_free(void* d_ptr) {
+  KZ_REQUIRE_INIT();
+  KZ_CUDA(cudaFree(d_ptr));
+  return 0;
+}
+
+int kzgpu_h2d(void* d_dst, const void* src, size_t bytes) {
+  KZ_REQUIRE_INIT();
+  KZ_CUDA(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, kz_ctx().stream));
+  KZ_CUDA(cudaStreamSynchronize(kz_ctx().stream));
+  return 0;
+}
+
+int kzgpu_d2h(void* dst, const void* d_src, size_t bytes) {
+  KZ_REQUIRE_INIT();
+  KZ_CUDA(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, kz_ctx().stream));
+  KZ_CUDA(cudaStreamSynchronize(kz_ctx().stream));
+  return 0;
+}
+
+int kzgpu_sync(void) {
+  KZ_REQUIRE_INIT();
+  KZ_CUDA(cudaStreamSynchronize(kz_ctx().stream));
+  return 0;
+}
+
+int kzgpu_timer_start(void) {
+  KZ_REQUIRE_INIT();
+  KZ_CUDA(cudaEventRecord(kz_ctx().ev0, kz_ctx().stream));
+  return 0;
+}
+
+int kzgpu_timer_stop(float* ms) {
+  KZ_REQUIRE_INIT();
+  KZ_CUDA(cudaEventRecord(kz_ctx().ev1, kz_ctx().stream));
+  KZ_CUDA(cudaEventSynchronize(kz_ctx().ev1));
+  KZ_CUDA(cudaEventElapsedTime(ms, kz_ctx().ev0, kz_ctx().ev1));
+  return 0;
+}
+
+int kzgpu_launch_count(uint64_t* count) {
+  if (!count) return KZGPU_EINVAL;
+  *count = kz_ctx().launches;
+  return 0;
+}
+
+int kzgpu_field_op(int curve, int which, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  KZ_REQUIRE_INIT();
+  if (!a || !out || (op != 3 && !b) || op < 0 || op > 3) return kz_fail(KZGPU_EINVAL, "bad argument");
+  if (n == 0) return 0;
+  if (curve == KZGPU_BN254) return which == 0 ? field_op_impl<FpBN254>(op, a, b, out, n) : field_op_impl<FrBN254>(op, a, b, out, n);
+  if (curve == KZGPU_BLS12_381) return which == 0 ? field_op_impl<FpBLS381>(op, a, b, out, n) : field_op_impl<FrBLS381>(op, a, b, out, n);
+  return kz_fail(KZGPU_EINVAL, "unknown curve id %d", curve);
+}
+
+int kzgpu_microbench(int kind, int blocks, int threads, int iters, float* ms, double* ops) {
+  KZ_REQUIRE_INIT();
+  if (blocks <= 0 || threads <= 0 || threads > 1024 || iters <= 0 || !ms) return kz_fail(KZGPU_EINVAL, "bad argument");
+  KzgpuCtx& cx = kz_ctx();
+  uint32_t* sink = nullptr;
+  KZ_CUDA(cudaMalloc(&sink, 4));
+  double per_thread = 0;
+  for (int rep = 0; rep < 2; rep++) {       // rep 0 = warm-up
+    KZ_CUDA(cudaEventRecord(cx.ev0, cx.stream));
+    switch (kind) {
+      case 0: mb_imad_kernel<<<blocks, threads, 0, cx.stream>>>(sink, iters, 12345u); per_thread = 32.0 * iters; break;
+      case 1: mb_mul_kernel<FpBN254><<<blocks, threads, 0, cx.stream>>>(sink, iters, 12345u); per_thread = 4.0 * iters; break;
+      case 2: mb_mul_kernel<FpBLS381><<<blocks, threads, 0, cx.stream>>>(sink, iters, 12345u); per_thread = 4.0 * iters; break;
+      case 3: mb_madd_kernel<FpBN254><<<blocks, threads, 0, cx.stream>>>(sink, iters, 12345u); per_thread = 1.0 * iters; break;
+      case 4: mb_madd_kernel<FpBLS381><<<blocks, threads, 0, cx.stream>>>(sink, iters, 12345u); per_thread = 1.0 * iters; break;
+      default: cudaFree(sink); return kz_fail(KZGPU_EINVAL, "unknown microbench kind %d", kind);
+    }
+    KZ_LAUNCHED();
+    KZ_CUDA(cudaEventRecord(cx.ev1, cx.stream));
+    KZ_CUDA(cudaEventSynchronize(cx.ev1));
+    KZ_CUDA(cudaEventElapsedTime(ms, cx.ev0, cx.ev1));
+  }
+  if (ops) *ops = per_thread * (double)blocks * (double)threads;
+  cudaFree(sink);
+  return 0;
+}
+
+}  // extern "C"

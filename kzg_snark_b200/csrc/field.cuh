@@ -1,0 +1,190 @@
+// Montgomery prime-field arithmetic on 32-bit limbs (8 limbs: BN254 p/r, BLS12-381 r;
+// 12 limbs: BLS12-381 p).  Replaces, for the hot path, the arithmetic the reference
+// delegates to py_ecc's pure-Python FQ (kzg.py:27-35) and Sage's GF(r) (kzg.py:52).
+//
+// Representation: little-endian uint32 limbs, value < p.  "Montgomery form" of x is
+// x * 2^(32N) mod p.  mont_mul(a, b) = a * b * 2^(-32N) mod p for a, b < p.
+//
+// mont_mul keeps two accumulators E ("even-aligned", limb k at bit 32k) and O
+// ("odd-aligned", limb k at bit 32(k+1)) so that every 32x32->64 product of a row lands
+// on a (lo,hi) register pair of one accumulator and the whole row is one carry chain of
+// IMAD.WIDE.U32.X.  After each row the Montgomery step makes E[0] zero; dividing by 2^32
+// then simply swaps the roles of E and O (E>>32 is odd-aligned again after dropping E[0]
+// and folding E[1] into the new even accumulator).  Bound: the running value stays < 2p
+// after each division and < 2p * 2^32 before it, so it fits positions 0..N as long as
+// p <= 2^(32N-1) -- true for all four moduli (254/255/254/381 bits in 256/256/256/384).
+#pragma once
+#include <cstdint>
+#include "mp_prims.cuh"
+
+#ifdef __CUDACC__
+#define HD __host__ __device__ __forceinline__
+#else
+#define HD inline
+#endif
+
+template <class P> struct Fe {
+  static constexpr int N = P::N;
+  uint32_t v[P::N];
+};
+
+template <class P> HD void fe_load_mod(uint32_t* m) {
+#pragma unroll
+  for (int i = 0; i < P::N; i++) m[i] = P::mod(i);
+}
+
+template <class P> HD bool fe_is_zero(const Fe<P>& a) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < P::N; i++) o |= a.v[i];
+  return o == 0;
+}
+
+template <class P> HD bool fe_eq(const Fe<P>& a, const Fe<P>& b) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < P::N; i++) o |= a.v[i] ^ b.v[i];
+  return o == 0;
+}
+
+template <class P> HD Fe<P> fe_zero() {
+  Fe<P> r;
+#pragma unroll
+  for (int i = 0; i < P::N; i++) r.v[i] = 0;
+  return r;
+}
+
+// 1 in Montgomery form (2^(32N) mod p)
+template <class P> HD Fe<P> fe_one() {
+  Fe<P> r;
+#pragma unroll
+  for (int i = 0; i < P::N; i++) r.v[i] = P::one(i);
+  return r;
+}
+
+// r = (x >= p) ? x - p : x   for x < 2p
+template <class P> HD void fe_final_sub(uint32_t* r, const uint32_t* x) {
+  constexpr int N = P::N;
+  uint32_t m[N], t[N];
+  fe_load_mod<P>(m);
+  uint32_t borrow = Mp<N>::sub_cc(t, x, m);
+#pragma unroll
+  for (int i = 0; i < N; i++) r[i] = borrow ? x[i] : t[i];
+}
+
+template <class P> HD Fe<P> fe_add(const Fe<P>& a, const Fe<P>& b) {
+  constexpr int N = P::N;
+  uint32_t s[N];
+  Mp<N>::add_cc(s, a.v, b.v);          // a + b < 2p < 2^(32N): no carry out
+  Fe<P> r;
+  fe_final_sub<P>(r.v, s);
+  return r;
+}
+
+template <class P> HD Fe<P> fe_sub(const Fe<P>& a, const Fe<P>& b) {
+  constexpr int N = P::N;
+  uint32_t d[N], m[N];
+  uint32_t borrow = Mp<N>::sub_cc(d, a.v, b.v);
+#pragma unroll
+  for (int i = 0; i < N; i++) m[i] = P::mod(i) & borrow;
+  Fe<P> r;
+  Mp<N>::add_cc(r.v, d, m);
+  return r;
+}
+
+template <class P> HD Fe<P> fe_neg(const Fe<P>& a) {
+  constexpr int N = P::N;
+  uint32_t m[N];
+  fe_load_mod<P>(m);
+  Fe<P> r;
+  Mp<N>::sub_cc(r.v, m, a.v);
+  uint32_t nz = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) nz |= a.v[i];
+#pragma unroll
+  for (int i = 0; i < N; i++) r.v[i] = nz ? r.v[i] : 0u;
+  return r;
+}
+
+template <class P> HD Fe<P> fe_dbl(const Fe<P>& a) { return fe_add<P>(a, a); }
+
+// One Montgomery row-reduction: make E[0] zero by adding m*p, m = E[0] * (-p^-1 mod 2^32).
+template <class P> HD void fe_redc_row(uint32_t* E, uint32_t* O, const uint32_t* mod) {
+  constexpr int N = P::N;
+  uint32_t m = E[0] * P::INV32;
+  Mp<N>::mad_even_nc(O, mod + 1, m);
+  Mp<N>::mad_even(E, mod, m, O[N - 1]);
+}
+
+template <class P> HD Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
+  constexpr int N = P::N;
+  uint32_t mod[N], E[N], O[N];
+  fe_load_mod<P>(mod);
+  // row 0
+  Mp<N>::mul_even(E, a.v, b.v[0]);
+  Mp<N>::mul_even(O, a.v + 1, b.v[0]);
+  fe_redc_row<P>(E, O, mod);
+#pragma unroll
+  for (int i = 1; i < N; i += 2) {
+    // odd row: roles swapped (O is even-aligned now, E is shifted into odd alignment)
+    Mp<N>::shift_mad(E, O[0], a.v + 1, b.v[i]);
+    Mp<N>::mad_even(O, a.v, b.v[i], E[N - 1]);
+    fe_redc_row<P>(O, E, mod);
+    if (i + 1 < N) {
+      Mp<N>::shift_mad(O, E[0], a.v + 1, b.v[i + 1]);
+      Mp<N>::mad_even(E, a.v, b.v[i + 1], O[N - 1]);
+      fe_redc_row<P>(E, O, mod);
+    }
+  }
+  // N is even: after the last (odd) row the even-aligned accumulator is O, with O[0] == 0
+  uint32_t t[N];
+  Mp<N>::merge(t, E, O);
+  Fe<P> r;
+  fe_final_sub<P>(r.v, t);
+  return r;
+}
+
+template <class P> HD Fe<P> fe_sqr(const Fe<P>& a) { return fe_mul<P>(a, a); }
+
+template <class P> HD Fe<P> fe_to_mont(const Fe<P>& a) {
+  Fe<P> r2;
+#pragma unroll
+  for (int i = 0; i < P::N; i++) r2.v[i] = P::r2(i);
+  return fe_mul<P>(a, r2);
+}
+
+template <class P> HD Fe<P> fe_from_mont(const Fe<P>& a) {
+  Fe<P> one = fe_zero<P>();
+  one.v[0] = 1;
+  return fe_mul<P>(a, one);
+}
+
+// a^e for a in Montgomery form, e given as limbs (not secret; square-and-multiply MSB first)
+template <class P> HD Fe<P> fe_pow(const Fe<P>& a, const uint32_t* e, int nlimbs) {
+  Fe<P> r = fe_one<P>();
+  bool started = false;
+  for (int i = nlimbs - 1; i >= 0; i--) {
+    for (int b = 31; b >= 0; b--) {
+      if (started) r = fe_sqr<P>(r);
+      if ((e[i] >> b) & 1) {
+        r = started ? fe_mul<P>(r, a) : a;
+        started = true;
+      }
+    }
+  }
+  return r;
+}
+
+// a^(p-2): inverse for a != 0 (returns 0 for 0)
+template <class P> HD Fe<P> fe_inv(const Fe<P>& a) {
+  uint32_t e[P::N];
+#pragma unroll
+  for (int i = 0; i < P::N; i++) e[i] = P::mod(i);
+  uint32_t borrow = 2;                 // e = p - 2 (r_bls has low limb 1: the borrow ripples)
+  for (int i = 0; i < P::N && borrow; i++) {
+    uint32_t old = e[i];
+    e[i] = old - borrow;
+    borrow = old < borrow ? 1u : 0u;
+  }
+  return fe_pow<P>(a, e, P::N);
+}

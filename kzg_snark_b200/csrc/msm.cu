@@ -1,0 +1,639 @@
+// G1 multi-scalar multiplication: the device replacement of KZG.commit's inner loop
+// (reference kzg.py:108-116:  commitment = sum_i coeff_i * ck[i], zero coefficients skipped),
+// plus the SRS store behind `ck` (kzg.py:69-72).
+//
+// Pippenger bucket method:
+//   1. every scalar is recoded into W signed c-bit digits d_w in [-2^(c-1), 2^(c-1)]
+//      (zero digits are skipped, as the reference skips zero coefficients, kzg.py:113);
+//   2. counting sort of (window, |d|-1) -> per-bucket lists of point indices (sign in bit 31):
+//      histogram with L2 atomics, exclusive scan, scatter;
+//   3. one thread per bucket accumulates its points with XYZZ mixed additions (8M+2S);
+//   4. per window, sum_b (b+1) * B_b by chunked running sums, then a block reduction;
+//   5. Horner over the windows (c doublings each), normalisation to affine, canonical limbs.
+// Only step 3 is O(n * W); it is integer-pipe (IMAD) bound, see DESIGN.md.
+#include "common.cuh"
+#include <map>
+#include <vector>
+#include <cstdlib>
+#include <cstring>
+
+namespace {
+
+struct BN254Cfg { using Fp = FpBN254; using Fr = FrBN254; static constexpr int id = KZGPU_BN254; };
+struct BLS381Cfg { using Fp = FpBLS381; using Fr = FrBLS381; static constexpr int id = KZGPU_BLS12_381; };
+
+struct Srs {
+  int curve;
+  size_t n;
+  uint32_t* d_points;     // affine, Montgomery form, [x | y] per point
+};
+
+std::map<uint64_t, Srs> g_srs;
+uint64_t g_next_handle = 1;
+
+struct MsmWs {
+  KzScratch counts, offsets, cursor, entries, buckets, partials, winsums, blocksums, result, flag, scal;
+};
+MsmWs g_ws;
+
+// ---------------------------------------------------------------- device helpers
+template <class P> __device__ __forceinline__ void ld_words(uint32_t* dst, const uint32_t* src) {
+  const uint4* q = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int i = 0; i < P::N / 4; i++) {
+    uint4 t = __ldg(q + i);
+    dst[4 * i] = t.x; dst[4 * i + 1] = t.y; dst[4 * i + 2] = t.z; dst[4 * i + 3] = t.w;
+  }
+}
+template <class P> __device__ __forceinline__ Affine<P> ld_affine(const uint32_t* pts, size_t idx) {
+  Affine<P> a;
+  const uint32_t* p = pts + idx * (2 * P::N);
+  ld_words<P>(a.x.v, p);
+  ld_words<P>(a.y.v, p + P::N);
+  return a;
+}
+template <class P> __device__ __forceinline__ XYZZ<P> ld_xyzz(const uint32_t* buf, size_t idx) {
+  XYZZ<P> a;
+  const uint4* q = reinterpret_cast<const uint4*>(buf + idx * (4 * P::N));
+  uint32_t* d = a.x.v;     // XYZZ is 4 contiguous Fe
+#pragma unroll
+  for (int i = 0; i < P::N; i++) {
+    uint4 t = q[i];
+    d[4 * i] = t.x; d[4 * i + 1] = t.y; d[4 * i + 2] = t.z; d[4 * i + 3] = t.w;
+  }
+  return a;
+}
+template <class P> __device__ __forceinline__ void st_xyzz(uint32_t* buf, size_t idx, const XYZZ<P>& a) {
+  uint4* q = reinterpret_cast<uint4*>(buf + idx * (4 * P::N));
+  const uint32_t* d = a.x.v;
+#pragma unroll
+  for (int i = 0; i < P::N; i++) q[i] = make_uint4(d[4 * i], d[4 * i + 1], d[4 * i + 2], d[4 * i + 3]);
+}
+
+// signed digit of window w (c bits) of the 256-bit scalar s, with the running carry
+__device__ __forceinline__ int signed_digit(const uint32_t* s, uint32_t w, uint32_t c, uint32_t& carry) {
+  uint32_t bit = w * c;
+  uint32_t word = bit >> 5, sh = bit & 31;
+  uint64_t lo = word < 8 ? s[word] : 0u;
+  uint64_t hi = word + 1 < 8 ? s[word + 1] : 0u;
+  uint32_t raw = (uint32_t)(((lo | (hi << 32)) >> sh) & ((1ull << c) - 1));
+  uint32_t d = raw + carry;
+  if (d > (1u << (c - 1))) { carry = 1; return (int)d - (int)(1u << c); }
+  carry = 0;
+  return (int)d;
+}
+
+// ---------------------------------------------------------------- kernels
+// pass = 0: histogram;  pass = 1: scatter (cursor pre-loaded with the bucket offsets)
+template <int PASS>
+__global__ void msm_sort_kernel(const uint32_t* __restrict__ scalars, size_t n, uint32_t c, uint32_t W, uint32_t top_bits,
+                                uint32_t* __restrict__ counts_or_cursor, uint32_t* __restrict__ entries, uint32_t* __restrict__ flag) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s[8];
+  const uint4* q = reinterpret_cast<const uint4*>(scalars + i * 8);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+  if (PASS == 0 && top_bits < 32 && (s[7] >> top_bits)) atomicOr(flag, 1u);   // scalar >= 2^bits: not canonical
+  const uint32_t B = 1u << (c - 1);
+  uint32_t carry = 0;
+  for (uint32_t w = 0; w < W; w++) {
+    int d = signed_digit(s, w, c, carry);
+    if (d == 0) continue;
+    uint32_t neg = d < 0 ? 1u : 0u;
+    uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
+    uint32_t bucket = w * B + (mag - 1);
+    if (PASS == 0) {
+      atomicAdd(counts_or_cursor + bucket, 1u);
+    } else {
+      uint32_t pos = atomicAdd(counts_or_cursor + bucket, 1u);
+      entries[pos] = (uint32_t)i | (neg << 31);
+    }
+  }
+}
+
+// exclusive scan, 3 kernels: (1) per-block scan of 1024 items + block totals, (2) scan of totals,
+// (3) add block offsets.  `out` gets len + 1 entries (out[len] = total).
+__global__ void scan_block_kernel(const uint32_t* in, uint32_t* out, uint32_t* blocksums, size_t len) {
+  __shared__ uint32_t sh[256];
+  size_t base = (size_t)blockIdx.x * 1024 + threadIdx.x * 4;
+  uint32_t v[4], s = 0;
+  for (int k = 0; k < 4; k++) { v[k] = base + k < len ? in[base + k] : 0; s += v[k]; }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 1; off < 256; off <<= 1) {
+    uint32_t t = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += t;
+    __syncthreads();
+  }
+  uint32_t excl = sh[threadIdx.x] - s;
+  for (int k = 0; k < 4; k++) { if (base + k < len) out[base + k] = excl; excl += v[k]; }
+  if (threadIdx.x == 255) blocksums[blockIdx.x] = sh[255];
+}
+__global__ void scan_sums_kernel(uint32_t* blocksums, size_t nblocks, uint32_t* total_out) {
+  // single block, sequential over chunks of 256
+  __shared__ uint32_t sh[256];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (size_t base = 0; base < nblocks; base += 256) {
+    size_t i = base + threadIdx.x;
+    uint32_t v = i < nblocks ? blocksums[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) {
+      uint32_t t = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < nblocks) blocksums[i] = carry + sh[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 255) carry += sh[255];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_out = carry;
+}
+__global__ void scan_add_kernel(uint32_t* out, const uint32_t* blocksums, size_t len, uint32_t* cursor) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  uint32_t v = out[i] + blocksums[i >> 10];
+  out[i] = v;
+  cursor[i] = v;
+}
+
+// one thread per bucket: XYZZ accumulator in registers, points gathered through the sorted index
+template <class Cfg>
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __restrict__ points, size_t first,
+                                                            const uint32_t* __restrict__ offsets,
+                                                            const uint32_t* __restrict__ entries, uint32_t nbuckets,
+                                                            uint32_t* __restrict__ buckets) {
+  using P = typename Cfg::Fp;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nbuckets) return;
+  uint32_t start = offsets[t], end = offsets[t + 1];
+  XYZZ<P> acc = xyzz_inf<P>();
+  for (uint32_t e = start; e < end; e++) {
+    uint32_t ent = __ldg(entries + e);
+    Affine<P> pt = ld_affine<P>(points, first + (ent & 0x7fffffffu));
+    if (ent >> 31) pt.y = fe_neg<P>(pt.y);
+    xyzz_madd<P>(acc, pt);
+  }
+  st_xyzz<P>(buckets, t, acc);
+}
+
+// chunked running sum: thread (w, chunk) reduces CH consecutive buckets of window w to
+//   sum_b (b + 1) * B_b  over its chunk  =  acc + lo * running
+template <class Cfg>
+__global__ void __launch_bounds__(128) msm_reduce_kernel(const uint32_t* __restrict__ buckets, uint32_t B, uint32_t CH,
+                                                        uint32_t chunks_per_window, uint32_t W, uint32_t* __restrict__ partials) {
+  using P = typename Cfg::Fp;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= chunks_per_window * W) return;
+  uint32_t w = t / chunks_per_window, ch = t % chunks_per_window;
+  uint32_t lo = ch * CH, hi = lo + CH < B ? lo + CH : B;
+  XYZZ<P> running = xyzz_inf<P>(), acc = xyzz_inf<P>();
+  for (uint32_t b = hi; b-- > lo;) {
+    XYZZ<P> bk = ld_xyzz<P>(buckets, (size_t)w * B + b);
+    running = xyzz_add<P>(running, bk);
+    acc = xyzz_add<P>(acc, running);
+  }
+  if (lo) acc = xyzz_add<P>(acc, xyzz_mul_u32<P>(running, lo));
+  st_xyzz<P>(partials, t, acc);
+}
+
+// block per window: sum the window's chunk partials (strided serial + shared-memory tree)
+template <class Cfg>
+__global__ void __launch_bounds__(128) msm_window_kernel(const uint32_t* __restrict__ partials, uint32_t chunks_per_window,
+                                                        uint32_t* __restrict__ winsums) {
+  using P = typename Cfg::Fp;
+  extern __shared__ uint32_t shw[];
+  uint32_t w = blockIdx.x;
+  XYZZ<P> acc = xyzz_inf<P>();
+  for (uint32_t ch = threadIdx.x; ch < chunks_per_window; ch += blockDim.x)
+    acc = xyzz_add<P>(acc, ld_xyzz<P>(partials, (size_t)w * chunks_per_window + ch));
+  st_xyzz<P>(shw, threadIdx.x, acc);
+  __syncthreads();
+  for (uint32_t off = blockDim.x / 2; off > 0; off >>= 1) {
+    if (threadIdx.x < off) {
+      XYZZ<P> a = ld_xyzz<P>(shw, threadIdx.x), b = ld_xyzz<P>(shw, threadIdx.x + off);
+      st_xyzz<P>(shw, threadIdx.x, xyzz_add<P>(a, b));
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) st_xyzz<P>(winsums, w, ld_xyzz<P>(shw, 0));
+}
+
+// Horner over windows (top first), optional normalisation.
+// out layout: mode 0 -> XYZZ Montgomery (4N words); mode 1 -> [x | y] canonical (2N words) + inf flag word
+template <class Cfg>
+__global__ void msm_final_kernel(const uint32_t* __restrict__ winsums, uint32_t W, uint32_t c, int mode, uint32_t* __restrict__ out) {
+  using P = typename Cfg::Fp;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  XYZZ<P> acc = xyzz_inf<P>();
+  for (uint32_t w = W; w-- > 0;) {
+    for (uint32_t k = 0; k < c; k++) acc = xyzz_dbl<P>(acc);
+    acc = xyzz_add<P>(acc, ld_xyzz<P>(winsums, w));
+  }
+  if (mode == 0) { st_xyzz<P>(out, 0, acc); return; }
+  Affine<P> a = xyzz_to_affine<P>(acc);
+  Fe<P> x = fe_from_mont<P>(a.x), y = fe_from_mont<P>(a.y);
+  for (int i = 0; i < P::N; i++) { out[i] = x.v[i]; out[P::N + i] = y.v[i]; }
+  out[2 * P::N] = xyzz_is_inf<P>(acc) ? 1u : 0u;
+}
+
+// sum `count` XYZZ points (one block), normalise -> canonical affine + inf flag
+template <class Cfg>
+__global__ void __launch_bounds__(128) g1_fold_kernel(const uint32_t* __restrict__ pts, uint32_t count, uint32_t* __restrict__ out) {
+  using P = typename Cfg::Fp;
+  extern __shared__ uint32_t shw[];
+  XYZZ<P> acc = xyzz_inf<P>();
+  for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) acc = xyzz_add<P>(acc, ld_xyzz<P>(pts, i));
+  st_xyzz<P>(shw, threadIdx.x, acc);
+  __syncthreads();
+  for (uint32_t off = blockDim.x / 2; off > 0; off >>= 1) {
+    if (threadIdx.x < off) {
+      XYZZ<P> a = ld_xyzz<P>(shw, threadIdx.x), b = ld_xyzz<P>(shw, threadIdx.x + off);
+      st_xyzz<P>(shw, threadIdx.x, xyzz_add<P>(a, b));
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    XYZZ<P> r = ld_xyzz<P>(shw, 0);
+    Affine<P> a = xyzz_to_affine<P>(r);
+    Fe<P> x = fe_from_mont<P>(a.x), y = fe_from_mont<P>(a.y);
+    for (int i = 0; i < P::N; i++) { out[i] = x.v[i]; out[P::N + i] = y.v[i]; }
+    out[2 * P::N] = xyzz_is_inf<P>(r) ? 1u : 0u;
+  }
+}
+
+// canonical affine -> Montgomery affine (in place); (0,0) stays (0,0)
+template <class Cfg> __global__ void srs_to_mont_kernel(uint32_t* pts, size_t n) {
+  using P = typename Cfg::Fp;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * n) return;
+  Fe<P> v;
+  for (int k = 0; k < P::N; k++) v.v[k] = pts[i * P::N + k];
+  v = fe_to_mont<P>(v);
+  for (int k = 0; k < P::N; k++) pts[i * P::N + k] = v.v[k];
+}
+template <class Cfg> __global__ void srs_from_mont_kernel(const uint32_t* pts, size_t first, size_t count, uint32_t* out) {
+  using P = typename Cfg::Fp;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * count) return;
+  Fe<P> v;
+  for (int k = 0; k < P::N; k++) v.v[k] = pts[(2 * first + i) * P::N + k];
+  v = fe_from_mont<P>(v);
+  for (int k = 0; k < P::N; k++) out[i * P::N + k] = v.v[k];
+}
+
+// SRS generation (kzg.py:69-72): point i = tau^i * G1.  dbl_table[j] = 2^j * G1 (affine, Montgomery).
+template <class Cfg>
+__global__ void __launch_bounds__(128) srs_generate_kernel(uint32_t* pts, size_t n, Fe<typename Cfg::Fr> tau_mont,
+                                                          const uint32_t* __restrict__ dbl_table) {
+  using P = typename Cfg::Fp;
+  using R = typename Cfg::Fr;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // tau^i in the scalar field
+  Fe<R> base = tau_mont, e = fe_one<R>();
+  for (size_t k = i; k; k >>= 1) {
+    if (k & 1) e = fe_mul<R>(e, base);
+    if (k >> 1) base = fe_sqr<R>(base);
+  }
+  e = fe_from_mont<R>(e);
+  XYZZ<P> acc = xyzz_inf<P>();
+  for (int bit = 0; bit < R::BITS; bit++) {
+    if ((e.v[bit >> 5] >> (bit & 31)) & 1) {
+      Affine<P> t = ld_affine<P>(dbl_table, bit);
+      xyzz_madd<P>(acc, t);
+    }
+  }
+  Affine<P> a = xyzz_to_affine<P>(acc);
+  uint32_t* o = pts + i * (2 * P::N);
+  for (int k = 0; k < P::N; k++) { o[k] = a.x.v[k]; o[P::N + k] = a.y.v[k]; }
+}
+
+// ---------------------------------------------------------------- host side
+uint32_t choose_c(size_t n) {
+  const char* env = getenv("KZGPU_MSM_C");
+  if (env) {
+    int v = atoi(env);
+    if (v >= 2 && v <= 24) return (uint32_t)v;
+  }
+  uint32_t logn = 0;
+  while ((1ull << (logn + 1)) <= n) logn++;
+  int c = (int)logn - 4;
+  if (c < 3) c = 3;
+  if (c > 20) c = 20;
+  return (uint32_t)c;
+}
+
+template <class Cfg>
+int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, int mode, uint32_t* d_out) {
+  using P = typename Cfg::Fp;
+  using R = typename Cfg::Fr;
+  KzgpuCtx& cx = kz_ctx();
+  cudaStream_t st = cx.stream;
+  const uint32_t c = choose_c(n);
+  const uint32_t W = (R::BITS + 1 + c - 1) / c;
+  const uint32_t B = 1u << (c - 1);
+  const size_t nb = (size_t)W * B;
+  int rc;
+  if ((rc = g_ws.counts.ensure(nb * 4))) return rc;
+  if ((rc = g_ws.offsets.ensure((nb + 1) * 4))) return rc;
+  if ((rc = g_ws.cursor.ensure(nb * 4))) return rc;
+  if ((rc = g_ws.entries.ensure((size_t)n * W * 4 + 4))) return rc;
+  if ((rc = g_ws.buckets.ensure(nb * 4 * P::N * 4))) return rc;
+  if ((rc = g_ws.flag.ensure(4))) return rc;
+  const size_t nblk = kz_div_up(nb, 1024);
+  if ((rc = g_ws.blocksums.ensure(nblk * 4))) return rc;
+  uint32_t CH = 64;
+  if (CH > B) CH = B;
+  const uint32_t cpw = (B + CH - 1) / CH;
+  if ((rc = g_ws.partials.ensure((size_t)cpw * W * 4 * P::N * 4))) return rc;
+  if ((rc = g_ws.winsums.ensure((size_t)W * 4 * P::N * 4))) return rc;
+
+  uint32_t* counts = (uint32_t*)g_ws.counts.p;
+  uint32_t* offsets = (uint32_t*)g_ws.offsets.p;
+  uint32_t* cursor = (uint32_t*)g_ws.cursor.p;
+  uint32_t* entries = (uint32_t*)g_ws.entries.p;
+  uint32_t* flag = (uint32_t*)g_ws.flag.p;
+
+  KZ_CUDA(cudaMemsetAsync(counts, 0, nb * 4, st));
+  KZ_CUDA(cudaMemsetAsync(flag, 0, 4, st));
+  const uint32_t top_bits = R::BITS - 224;       // bits allowed in the top 32-bit word
+  if (n) {
+    msm_sort_kernel<0><<<(unsigned)kz_div_up(n, 256), 256, 0, st>>>(d_scalars, n, c, W, top_bits, counts, nullptr, flag);
+    KZ_LAUNCHED();
+  }
+  scan_block_kernel<<<(unsigned)nblk, 256, 0, st>>>(counts, offsets, (uint32_t*)g_ws.blocksums.p, nb);
+  KZ_LAUNCHED();
+  scan_sums_kernel<<<1, 256, 0, st>>>((uint32_t*)g_ws.blocksums.p, nblk, offsets + nb);
+  KZ_LAUNCHED();
+  scan_add_kernel<<<(unsigned)kz_div_up(nb, 256), 256, 0, st>>>(offsets, (uint32_t*)g_ws.blocksums.p, nb, cursor);
+  KZ_LAUNCHED();
+  if (n) {
+    msm_sort_kernel<1><<<(unsigned)kz_div_up(n, 256), 256, 0, st>>>(d_scalars, n, c, W, top_bits, cursor, entries, flag);
+    KZ_LAUNCHED();
+  }
+  msm_accumulate_kernel<Cfg><<<(unsigned)kz_div_up(nb, 128), 128, 0, st>>>(srs.d_points, first, offsets, entries, (uint32_t)nb,
+                                                                          (uint32_t*)g_ws.buckets.p);
+  KZ_LAUNCHED();
+  msm_reduce_kernel<Cfg><<<(unsigned)kz_div_up((size_t)cpw * W, 128), 128, 0, st>>>((uint32_t*)g_ws.buckets.p, B, CH, cpw, W,
+                                                                                   (uint32_t*)g_ws.partials.p);
+  KZ_LAUNCHED();
+  msm_window_kernel<Cfg><<<W, 128, 128 * 4 * P::N * 4, st>>>((uint32_t*)g_ws.partials.p, cpw, (uint32_t*)g_ws.winsums.p);
+  KZ_LAUNCHED();
+  msm_final_kernel<Cfg><<<1, 32, 0, st>>>((uint32_t*)g_ws.winsums.p, W, c, mode, d_out);
+  KZ_LAUNCHED();
+  uint32_t hflag = 0;
+  KZ_CUDA(cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, st));
+  KZ_CUDA(cudaStreamSynchronize(st));
+  if (hflag) return kz_fail(KZGPU_ERANGE, "a scalar is not a canonical residue (>= 2^%d)", R::BITS);
+  return 0;
+}
+
+template <class Cfg>
+int msm_affine(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, uint64_t* out_xy, int* is_inf) {
+  using P = typename Cfg::Fp;
+  int rc;
+  if ((rc = g_ws.result.ensure((2 * P::N + 1) * 4))) return rc;
+  if ((rc = msm_core<Cfg>(srs, first, d_scalars, n, 1, (uint32_t*)g_ws.result.p))) return rc;
+  uint32_t h[2 * 12 + 1];
+  KZ_CUDA(cudaMemcpy(h, g_ws.result.p, (2 * P::N + 1) * 4, cudaMemcpyDeviceToHost));
+  memcpy(out_xy, h, 2 * P::N * 4);
+  if (is_inf) *is_inf = (int)h[2 * P::N];
+  return 0;
+}
+
+int set_smem_attrs() {
+  static bool done = false;
+  if (done) return 0;
+  KZ_CUDA(cudaFuncSetAttribute(msm_window_kernel<BLS381Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 4 * 12 * 4));
+  KZ_CUDA(cudaFuncSetAttribute(g1_fold_kernel<BLS381Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 4 * 12 * 4));
+  done = true;
+  return 0;
+}
+
+const Srs* find_srs(uint64_t handle) {
+  auto it = g_srs.find(handle);
+  return it == g_srs.end() ? nullptr : &it->second;
+}
+
+template <class Cfg>
+int srs_create_impl(const uint64_t* affine_xy, size_t n, uint64_t* handle) {
+  using P = typename Cfg::Fp;
+  KzgpuCtx& cx = kz_ctx();
+  Srs s;
+  s.curve = Cfg::id; s.n = n; s.d_points = nullptr;
+  size_t bytes = n * 2 * P::N * 4;
+  KZ_CUDA(cudaMalloc((void**)&s.d_points, bytes ? bytes : 16));
+  if (n) {
+    KZ_CUDA(cudaMemcpyAsync(s.d_points, affine_xy, bytes, cudaMemcpyHostToDevice, cx.stream));
+    srs_to_mont_kernel<Cfg><<<(unsigned)kz_div_up(2 * n, 128), 128, 0, cx.stream>>>(s.d_points, n);
+    KZ_LAUNCHED();
+    KZ_CUDA(cudaStreamSynchronize(cx.stream));
+  }
+  *handle = g_next_handle++;
+  g_srs[*handle] = s;
+  return 0;
+}
+
+template <class Cfg>
+int srs_generate_impl(const uint64_t* tau, size_t n, uint64_t* handle) {
+  using P = typename Cfg::Fp;
+  using R = typename Cfg::Fr;
+  KzgpuCtx& cx = kz_ctx();
+  Fe<R> t = kz_fe_from_u64<R>(tau);
+  if (!kz_fe_reduced<R>(t)) return kz_fail(KZGPU_ERANGE, "tau is not a canonical scalar");
+  // host: table of 2^j * G1 in affine Montgomery form (O(bits) work, done once per call)
+  std::vector<uint32_t> table((size_t)R::BITS * 2 * P::N);
+  Affine<P> g;
+  for (int i = 0; i < P::N; i++) { g.x.v[i] = P::gx_mont(i); g.y.v[i] = P::gy_mont(i); }
+  for (int j = 0; j < R::BITS; j++) {
+    memcpy(&table[(size_t)j * 2 * P::N], g.x.v, P::N * 4);
+    memcpy(&table[(size_t)j * 2 * P::N + P::N], g.y.v, P::N * 4);
+    g = xyzz_to_affine<P>(xyzz_dbl_affine<P>(g));
+  }
+  uint32_t* d_table = nullptr;
+  KZ_CUDA(cudaMalloc((void**)&d_table, table.size() * 4));
+  KZ_CUDA(cudaMemcpyAsync(d_table, table.data(), table.size() * 4, cudaMemcpyHostToDevice, cx.stream));
+  Srs s;
+  s.curve = Cfg::id; s.n = n; s.d_points = nullptr;
+  size_t bytes = n * 2 * P::N * 4;
+  KZ_CUDA(cudaMalloc((void**)&s.d_points, bytes ? bytes : 16));
+  if (n) {
+    srs_generate_kernel<Cfg><<<(unsigned)kz_div_up(n, 128), 128, 0, cx.stream>>>(s.d_points, n, fe_to_mont<R>(t), d_table);
+    KZ_LAUNCHED();
+  }
+  KZ_CUDA(cudaStreamSynchronize(cx.stream));
+  cudaFree(d_table);
+  *handle = g_next_handle++;
+  g_srs[*handle] = s;
+  return 0;
+}
+
+int upload_scalars(const uint64_t* scalars, size_t n, uint32_t** d) {
+  int rc = g_ws.scal.ensure(n * 32 + 32);
+  if (rc) return rc;
+  if (n) KZ_CUDA(cudaMemcpyAsync(g_ws.scal.p, scalars, n * 32, cudaMemcpyHostToDevice, kz_ctx().stream));
+  *d = (uint32_t*)g_ws.scal.p;
+  return 0;
+}
+
+}  // namespace
+
+void kz_msm_release() {
+  for (auto& kv : g_srs) cudaFree(kv.second.d_points);
+  g_srs.clear();
+  KzScratch* all[] = {&g_ws.counts, &g_ws.offsets, &g_ws.cursor, &g_ws.entries, &g_ws.buckets, &g_ws.partials,
+                      &g_ws.winsums, &g_ws.blocksums, &g_ws.result, &g_ws.flag, &g_ws.scal};
+  for (auto* s : all) s->release();
+}
+
+// used by poly.cu (open): MSM of device-resident scalars against a handle
+int kz_msm_dev_internal(uint64_t handle, size_t first, const uint32_t* d_scalars, size_t n, uint64_t* out_xy, int* is_inf) {
+  const Srs* s = find_srs(handle);
+  if (!s) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle %llu", (unsigned long long)handle);
+  if (first + n > s->n)
+    return kz_fail(KZGPU_ERANGE, "Polynomial degree %zu exceeds maximum allowed degree %zu", first + n - 1, s->n - 1);
+  int rc = set_smem_attrs();
+  if (rc) return rc;
+  if (s->curve == KZGPU_BN254) return msm_affine<BN254Cfg>(*s, first, d_scalars, n, out_xy, is_inf);
+  return msm_affine<BLS381Cfg>(*s, first, d_scalars, n, out_xy, is_inf);
+}
+
+int kz_srs_curve(uint64_t handle) {
+  const Srs* s = find_srs(handle);
+  return s ? s->curve : -1;
+}
+
+extern "C" {
+
+int kzgpu_srs_create(int curve, const uint64_t* affine_xy, size_t n, uint64_t* handle) {
+  KZ_REQUIRE_INIT();
+  if (!handle || (n && !affine_xy)) return kz_fail(KZGPU_EINVAL, "null pointer");
+  if (curve == KZGPU_BN254) return srs_create_impl<BN254Cfg>(affine_xy, n, handle);
+  if (curve == KZGPU_BLS12_381) return srs_create_impl<BLS381Cfg>(affine_xy, n, handle);
+  return kz_fail(KZGPU_EINVAL, "Unsupported curve type: %d", curve);
+}
+
+int kzgpu_srs_generate(int curve, const uint64_t* tau, size_t n, uint64_t* handle) {
+  KZ_REQUIRE_INIT();
+  if (!handle || !tau) return kz_fail(KZGPU_EINVAL, "null pointer");
+  if (curve == KZGPU_BN254) return srs_generate_impl<BN254Cfg>(tau, n, handle);
+  if (curve == KZGPU_BLS12_381) return srs_generate_impl<BLS381Cfg>(tau, n, handle);
+  return kz_fail(KZGPU_EINVAL, "Unsupported curve type: %d", curve);
+}
+
+int kzgpu_srs_destroy(uint64_t handle) {
+  KZ_REQUIRE_INIT();
+  auto it = g_srs.find(handle);
+  if (it == g_srs.end()) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle %llu", (unsigned long long)handle);
+  cudaFree(it->second.d_points);
+  g_srs.erase(it);
+  return 0;
+}
+
+int kzgpu_srs_size(uint64_t handle, size_t* n) {
+  KZ_REQUIRE_INIT();
+  const Srs* s = find_srs(handle);
+  if (!s || !n) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle");
+  *n = s->n;
+  return 0;
+}
+
+int kzgpu_srs_read(uint64_t handle, size_t first, size_t count, uint64_t* affine_xy) {
+  KZ_REQUIRE_INIT();
+  const Srs* s = find_srs(handle);
+  if (!s) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle");
+  if (first + count > s->n || !affine_xy) return kz_fail(KZGPU_EINVAL, "range outside the SRS");
+  if (!count) return 0;
+  KzgpuCtx& cx = kz_ctx();
+  const int N = s->curve == KZGPU_BN254 ? 8 : 12;
+  size_t bytes = count * 2 * N * 4;
+  uint32_t* tmp = nullptr;
+  KZ_CUDA(cudaMalloc((void**)&tmp, bytes));
+  if (s->curve == KZGPU_BN254)
+    srs_from_mont_kernel<BN254Cfg><<<(unsigned)kz_div_up(2 * count, 128), 128, 0, cx.stream>>>(s->d_points, first, count, tmp);
+  else
+    srs_from_mont_kernel<BLS381Cfg><<<(unsigned)kz_div_up(2 * count, 128), 128, 0, cx.stream>>>(s->d_points, first, count, tmp);
+  KZ_LAUNCHED();
+  KZ_CUDA(cudaMemcpyAsync(affine_xy, tmp, bytes, cudaMemcpyDeviceToHost, cx.stream));
+  KZ_CUDA(cudaStreamSynchronize(cx.stream));
+  cudaFree(tmp);
+  return 0;
+}
+
+int kzgpu_msm_dev(uint64_t handle, size_t first, const uint64_t* d_scalars, size_t n, uint64_t* out_affine_xy, int* is_inf) {
+  KZ_REQUIRE_INIT();
+  if (!out_affine_xy || (n && !d_scalars)) return kz_fail(KZGPU_EINVAL, "null pointer");
+  return kz_msm_dev_internal(handle, first, (const uint32_t*)d_scalars, n, out_affine_xy, is_inf);
+}
+
+int kzgpu_msm(uint64_t handle, size_t first, const uint64_t* scalars, size_t n, uint64_t* out_affine_xy, int* is_inf) {
+  KZ_REQUIRE_INIT();
+  if (!out_affine_xy || (n && !scalars)) return kz_fail(KZGPU_EINVAL, "null pointer");
+  uint32_t* d = nullptr;
+  int rc = upload_scalars(scalars, n, &d);
+  if (rc) return rc;
+  return kz_msm_dev_internal(handle, first, d, n, out_affine_xy, is_inf);
+}
+
+int kzgpu_msm_batch(uint64_t handle, const uint64_t* scalars, const size_t* lens, size_t k, uint64_t* out_affine_xy, int* is_inf) {
+  KZ_REQUIRE_INIT();
+  if (k && (!lens || !out_affine_xy)) return kz_fail(KZGPU_EINVAL, "null pointer");
+  int curve = kz_srs_curve(handle);
+  if (curve < 0) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle %llu", (unsigned long long)handle);
+  const int L = kzgpu_fp_limbs64(curve);
+  size_t total = 0;
+  for (size_t j = 0; j < k; j++) total += lens[j];
+  uint32_t* d = nullptr;
+  int rc = upload_scalars(scalars, total, &d);
+  if (rc) return rc;
+  size_t off = 0;
+  for (size_t j = 0; j < k; j++) {
+    rc = kz_msm_dev_internal(handle, 0, d + off * 8, lens[j], out_affine_xy + j * 2 * L, is_inf ? is_inf + j : nullptr);
+    if (rc) return rc;
+    off += lens[j];
+  }
+  return 0;
+}
+
+int kzgpu_msm_partial_dev(uint64_t handle, size_t first, const uint64_t* d_scalars, size_t n, uint64_t* d_out_xyzz) {
+  KZ_REQUIRE_INIT();
+  const Srs* s = find_srs(handle);
+  if (!s) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle %llu", (unsigned long long)handle);
+  if (first + n > s->n) return kz_fail(KZGPU_ERANGE, "scalar range exceeds the SRS shard");
+  if (!d_out_xyzz || (n && !d_scalars)) return kz_fail(KZGPU_EINVAL, "null pointer");
+  int rc = set_smem_attrs();
+  if (rc) return rc;
+  if (s->curve == KZGPU_BN254) return msm_core<BN254Cfg>(*s, first, (const uint32_t*)d_scalars, n, 0, (uint32_t*)d_out_xyzz);
+  return msm_core<BLS381Cfg>(*s, first, (const uint32_t*)d_scalars, n, 0, (uint32_t*)d_out_xyzz);
+}
+
+int kzgpu_g1_fold(int curve, const uint64_t* d_xyzz, size_t count, uint64_t* out_affine_xy, int* is_inf) {
+  KZ_REQUIRE_INIT();
+  if (!d_xyzz || !out_affine_xy) return kz_fail(KZGPU_EINVAL, "null pointer");
+  if (curve != KZGPU_BN254 && curve != KZGPU_BLS12_381) return kz_fail(KZGPU_EINVAL, "Unsupported curve type: %d", curve);
+  KzgpuCtx& cx = kz_ctx();
+  int rc = set_smem_attrs();
+  if (rc) return rc;
+  const int N = curve == KZGPU_BN254 ? 8 : 12;
+  if ((rc = g_ws.result.ensure((2 * N + 1) * 4))) return rc;
+  if (curve == KZGPU_BN254)
+    g1_fold_kernel<BN254Cfg><<<1, 128, 128 * 4 * N * 4, cx.stream>>>((const uint32_t*)d_xyzz, (uint32_t)count, (uint32_t*)g_ws.result.p);
+  else
+    g1_fold_kernel<BLS381Cfg><<<1, 128, 128 * 4 * N * 4, cx.stream>>>((const uint32_t*)d_xyzz, (uint32_t)count, (uint32_t*)g_ws.result.p);
+  KZ_LAUNCHED();
+  uint32_t h[2 * 12 + 1];
+  KZ_CUDA(cudaMemcpyAsync(h, g_ws.result.p, (2 * N + 1) * 4, cudaMemcpyDeviceToHost, cx.stream));
+  KZ_CUDA(cudaStreamSynchronize(cx.stream));
+  memcpy(out_affine_xy, h, 2 * N * 4);
+  if (is_inf) *is_inf = (int)h[2 * N];
+  return 0;
+}
+
+}  // extern "C"

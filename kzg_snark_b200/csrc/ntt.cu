@@ -1,0 +1,486 @@
+// NTT / iNTT / coset NTT over the scalar field: the device replacement of the reference's
+// fft_ff / ifft_ff (fft_ff.py:3-58).  Contract (fft_ff.py:32-35 unrolled):
+//     out[k] = sum_j in[j] * w^(j k),  natural order in and out, caller-supplied w.
+//
+// Algorithm: mixed-radix Stockham decomposition n = R_1 * ... * R_m (R_t = 2^b_t, b_t <= 9).
+// Pass t (executed t = m .. 1) views its input as a [R_t][Q] matrix (Q = n / R_t), transforms
+// each column with an R_t-point DFT held in shared memory, and writes the result so that the
+// NEXT pass again reads contiguous runs and the last pass lands in natural order:
+//     in [j_t][jlo][kk]  ->  out[jlo][k_t][kk],   jlo < J = R_1..R_{t-1},  kk < K = R_{t+1}..R_m.
+// The inter-pass twiddle w^(J * j_t * kk) (and, folded into it, the 1/n scale of the inverse
+// and the coset powers) comes from a per-pass 2-D table indexed exactly like the data tile, so
+// it is read with the same coalesced pattern.  Inside a block the R_t-point DFT is again
+// decomposed into radix-8/4/2 layers done in registers (5 constant multiplications per 8
+// points) with one shared-memory exchange per layer.
+//
+// Data stays in canonical form end to end: every table entry is in Montgomery form, and
+// mont_mul(canonical, montgomery) is canonical.  HBM traffic per pass: 32 B read + 32 B
+// written per element (+32 B of table for t < m).
+#include "common.cuh"
+#include <vector>
+#include <list>
+#include <cstring>
+
+namespace {
+
+constexpr int kLogTile = 11;        // 2048 elements (64 KB of shared memory) per block
+constexpr int kMaxB = 9;            // R_t <= 512
+constexpr int kThreads = 256;
+
+template <class P> struct NttConsts { Fe<P> w8, w4, w8_3; };   // omega_8, omega_8^2, omega_8^3
+
+struct NttPassArgs {
+  const uint32_t* in;
+  uint32_t* out;
+  const uint32_t* bnd;    // [R][K] boundary table or nullptr
+  const uint32_t* post;   // [R] multiplier applied at the final store or nullptr
+  const uint32_t* wR;     // omega_R^e, e < R
+  uint64_t n;
+  uint32_t b, logC, logK, logQ;
+  uint32_t nd;
+  uint32_t d[3];
+};
+
+template <class P> __device__ __forceinline__ Fe<P> ld_fe(const uint32_t* p) {
+  Fe<P> r;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < P::N / 4; i++) {
+    uint4 t = q[i];
+    r.v[4 * i] = t.x; r.v[4 * i + 1] = t.y; r.v[4 * i + 2] = t.z; r.v[4 * i + 3] = t.w;
+  }
+  return r;
+}
+template <class P> __device__ __forceinline__ Fe<P> ldg_fe(const uint32_t* p) {
+  Fe<P> r;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < P::N / 4; i++) {
+    uint4 t = __ldg(q + i);
+    r.v[4 * i] = t.x; r.v[4 * i + 1] = t.y; r.v[4 * i + 2] = t.z; r.v[4 * i + 3] = t.w;
+  }
+  return r;
+}
+template <class P> __device__ __forceinline__ void st_fe(uint32_t* p, const Fe<P>& a) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < P::N / 4; i++) q[i] = make_uint4(a.v[4 * i], a.v[4 * i + 1], a.v[4 * i + 2], a.v[4 * i + 3]);
+}
+
+// shared memory: 8 word-planes of `tile` words; XOR swizzle so that both the "consecutive
+// columns" and the "stride 8C" access patterns of the layers fall on distinct banks
+__device__ __forceinline__ uint32_t swz(uint32_t pos, uint32_t logC) {
+  return pos ^ (((pos >> (logC + 3)) & 7u) << logC);
+}
+template <class P> __device__ __forceinline__ Fe<P> sm_ld(const uint32_t* sm, uint32_t tile, uint32_t p) {
+  Fe<P> r;
+#pragma unroll
+  for (int w = 0; w < P::N; w++) r.v[w] = sm[w * tile + p];
+  return r;
+}
+template <class P> __device__ __forceinline__ void sm_st(uint32_t* sm, uint32_t tile, uint32_t p, const Fe<P>& a) {
+#pragma unroll
+  for (int w = 0; w < P::N; w++) sm[w * tile + p] = a.v[w];
+}
+
+template <class P> __device__ __forceinline__ void bfly(Fe<P>& a, Fe<P>& b) {
+  Fe<P> s = fe_add<P>(a, b);
+  b = fe_sub<P>(a, b);
+  a = s;
+}
+
+// y[v] = sum_u x[u] * root^(u v), root = omega_{2^D}; in place, natural order
+template <class P, int D> __device__ __forceinline__ void dft_small(Fe<P>* x, const NttConsts<P>& c) {
+  if constexpr (D == 1) {
+    bfly<P>(x[0], x[1]);
+  } else if constexpr (D == 2) {
+    bfly<P>(x[0], x[2]);                 // s0, s1
+    bfly<P>(x[1], x[3]);                 // s2, (a1 - a3)
+    x[3] = fe_mul<P>(x[3], c.w4);
+    Fe<P> y0 = fe_add<P>(x[0], x[1]), y2 = fe_sub<P>(x[0], x[1]);
+    Fe<P> y1 = fe_add<P>(x[2], x[3]), y3 = fe_sub<P>(x[2], x[3]);
+    x[0] = y0; x[1] = y1; x[2] = y2; x[3] = y3;
+  } else {
+    Fe<P> e[4] = {x[0], x[2], x[4], x[6]};
+    Fe<P> o[4] = {x[1], x[3], x[5], x[7]};
+    dft_small<P, 2>(e, c);
+    dft_small<P, 2>(o, c);
+    o[1] = fe_mul<P>(o[1], c.w8);
+    o[2] = fe_mul<P>(o[2], c.w4);
+    o[3] = fe_mul<P>(o[3], c.w8_3);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      x[i] = fe_add<P>(e[i], o[i]);
+      x[i + 4] = fe_sub<P>(e[i], o[i]);
+    }
+  }
+}
+
+template <class P, int D>
+__device__ __forceinline__ void ntt_layer(uint32_t* sm, const NttPassArgs& a, const NttConsts<P>& c,
+                                          uint32_t li, uint32_t off, uint32_t done) {
+  const uint32_t tile_log = a.b + a.logC, tile = 1u << tile_log;
+  const uint32_t ngroups = tile >> D;
+  const uint32_t Cmask = (1u << a.logC) - 1;
+#pragma unroll 1
+  for (uint32_t gsub = 0; gsub < (8u >> D); gsub++) {
+    uint32_t G = threadIdx.x + blockDim.x * gsub;
+    if (G >= ngroups) break;
+    uint32_t cc = G & Cmask, rest = G >> a.logC;
+    uint32_t low = rest & ((1u << off) - 1), high = rest >> off;
+    // V = number formed by the output digits of the previous layers (first layer = least significant)
+    uint32_t V = 0, hb = high, sh = done;
+    for (int s = (int)li - 1; s >= 0; s--) {
+      uint32_t dd = a.d[s];
+      sh -= dd;
+      V |= (hb & ((1u << dd) - 1)) << sh;
+      hb >>= dd;
+    }
+    Fe<P> x[1 << D];
+    uint32_t base_l = (high << (off + D)) | low;
+#pragma unroll
+    for (int u = 0; u < (1 << D); u++) {
+      uint32_t l = base_l | ((uint32_t)u << off);
+      x[u] = sm_ld<P>(sm, tile, swz((l << a.logC) | cc, a.logC));
+    }
+    if (li > 0) {
+#pragma unroll
+      for (int u = 1; u < (1 << D); u++) {
+        uint32_t e = ((uint32_t)u << off) * V;
+        x[u] = fe_mul<P>(x[u], ldg_fe<P>(a.wR + (size_t)e * P::N));
+      }
+    }
+    dft_small<P, D>(x, c);
+#pragma unroll
+    for (int u = 0; u < (1 << D); u++) {
+      uint32_t l = base_l | ((uint32_t)u << off);
+      sm_st<P>(sm, tile, swz((l << a.logC) | cc, a.logC), x[u]);
+    }
+  }
+}
+
+template <class P>
+__global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(NttPassArgs a, NttConsts<P> c) {
+  extern __shared__ uint32_t sm[];
+  const uint32_t tile_log = a.b + a.logC, tile = 1u << tile_log;
+  const uint32_t Cmask = (1u << a.logC) - 1, Kmask = (1u << a.logK) - 1, Rmask = (1u << a.b) - 1;
+  const size_t boff = (size_t)blockIdx.y * a.n;
+  const size_t q0 = (size_t)blockIdx.x << a.logC;
+
+  for (uint32_t o = threadIdx.x; o < tile; o += blockDim.x) {
+    uint32_t l = o >> a.logC, cc = o & Cmask;
+    size_t qq = q0 + cc;
+    Fe<P> v = ld_fe<P>(a.in + (boff + ((size_t)l << a.logQ) + qq) * P::N);
+    if (a.bnd) {
+      size_t kk = qq & Kmask;
+      v = fe_mul<P>(v, ldg_fe<P>(a.bnd + (((size_t)l << a.logK) + kk) * P::N));
+    }
+    sm_st<P>(sm, tile, swz(o, a.logC), v);
+  }
+  __syncthreads();
+
+  uint32_t off = a.b, done = 0;
+  for (uint32_t li = 0; li < a.nd; li++) {
+    uint32_t d = a.d[li];
+    off -= d;
+    if (d == 3) ntt_layer<P, 3>(sm, a, c, li, off, done);
+    else if (d == 2) ntt_layer<P, 2>(sm, a, c, li, off, done);
+    else ntt_layer<P, 1>(sm, a, c, li, off, done);
+    done += d;
+    __syncthreads();
+  }
+
+  const uint32_t logCm = a.logC < a.logK ? a.logC : a.logK;
+  for (uint32_t o = threadIdx.x; o < tile; o += blockDim.x) {
+    uint32_t cc_lo = o & ((1u << logCm) - 1);
+    uint32_t kt = (o >> logCm) & Rmask;
+    uint32_t cc_hi = o >> (logCm + a.b);
+    uint32_t cc = (cc_hi << logCm) | cc_lo;
+    size_t qq = q0 + cc;
+    size_t jlo = qq >> a.logK, kk = qq & Kmask;
+    // X[kt] sits at the digit-reversed row
+    uint32_t l = 0, ob = a.b, kr = kt;
+    for (uint32_t s = 0; s < a.nd; s++) {
+      uint32_t dd = a.d[s];
+      ob -= dd;
+      l |= (kr & ((1u << dd) - 1)) << ob;
+      kr >>= dd;
+    }
+    Fe<P> v = sm_ld<P>(sm, tile, swz((l << a.logC) | cc, a.logC));
+    if (a.post) v = fe_mul<P>(v, ldg_fe<P>(a.post + (size_t)kt * P::N));
+    st_fe<P>(a.out + (boff + (((jlo << a.b) + kt) << a.logK) + kk) * P::N, v);
+  }
+}
+
+template <class P> __device__ Fe<P> fe_pow_u64(Fe<P> base, uint64_t e) {
+  Fe<P> r = fe_one<P>();
+  while (e) {
+    if (e & 1) r = fe_mul<P>(r, base);
+    e >>= 1;
+    if (e) base = fe_sqr<P>(base);
+  }
+  return r;
+}
+
+// out[l*K + kk] = a0 * a1^l * (h * g^l)^kk   (all Montgomery form); one thread per 64 kk's
+template <class P>
+__global__ void ntt_gen_table_kernel(uint32_t* out, uint32_t R, uint64_t K, Fe<P> a0, Fe<P> a1, Fe<P> h, Fe<P> g) {
+  constexpr uint64_t CH = 64;
+  uint64_t chunks_per_row = (K + CH - 1) / CH;
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= chunks_per_row * R) return;
+  uint32_t l = (uint32_t)(t / chunks_per_row);
+  uint64_t kk0 = (t % chunks_per_row) * CH;
+  Fe<P> A = fe_mul<P>(a0, fe_pow_u64<P>(a1, l));
+  Fe<P> B = fe_mul<P>(h, fe_pow_u64<P>(g, l));
+  Fe<P> cur = fe_mul<P>(A, fe_pow_u64<P>(B, kk0));
+  uint64_t end = kk0 + CH < K ? kk0 + CH : K;
+  for (uint64_t kk = kk0; kk < end; kk++) {
+    st_fe<P>(out + ((uint64_t)l * K + kk) * P::N, cur);
+    cur = fe_mul<P>(cur, B);
+  }
+}
+
+// ------------------------------------------------------------------ host-side plan
+struct PassPlan {
+  uint32_t b, logC, logK, logQ, nd, d[3];
+  uint32_t* bnd = nullptr;
+  uint32_t* post = nullptr;
+  uint32_t* wR = nullptr;
+};
+
+struct NttPlan {
+  int field;
+  uint32_t logn;
+  int inverse;
+  bool has_shift;
+  uint32_t w[8], shift[8];
+  std::vector<PassPlan> passes;      // in execution order (t = m .. 1)
+  uint32_t consts[3 * 8];            // w8, w4, w8^3 (Montgomery)
+  size_t bytes = 0;
+  void free_tables() {
+    for (auto& p : passes) { cudaFree(p.bnd); cudaFree(p.post); cudaFree(p.wR); }
+    passes.clear();
+  }
+};
+
+std::list<NttPlan> g_plans;                 // most recently used first
+constexpr size_t kMaxPlans = 8;
+KzScratch g_ntt_scratch[2];
+
+template <class P> Fe<P> host_pow(Fe<P> base, uint64_t e) {
+  Fe<P> r = fe_one<P>();
+  while (e) {
+    if (e & 1) r = fe_mul<P>(r, base);
+    e >>= 1;
+    if (e) base = fe_sqr<P>(base);
+  }
+  return r;
+}
+
+template <class P>
+int gen_table(uint32_t** out, uint32_t R, uint64_t K, const Fe<P>& a0, const Fe<P>& a1, const Fe<P>& h, const Fe<P>& g) {
+  KzgpuCtx& cx = kz_ctx();
+  size_t bytes = (size_t)R * K * P::N * 4;
+  KZ_CUDA(cudaMalloc((void**)out, bytes));
+  uint64_t threads = (uint64_t)R * ((K + 63) / 64);
+  ntt_gen_table_kernel<P><<<(unsigned)kz_div_up(threads, 128), 128, 0, cx.stream>>>(*out, R, K, a0, a1, h, g);
+  KZ_LAUNCHED();
+  return 0;
+}
+
+template <class P>
+int build_plan(NttPlan& pl, uint32_t logn, const Fe<P>& w_canon, int inverse, const Fe<P>* shift_canon) {
+  const uint64_t n = 1ull << logn;
+  Fe<P> w = fe_to_mont<P>(w_canon);
+  if (inverse) w = fe_inv<P>(w);                                   // fft_ff.py:53
+  Fe<P> one = fe_one<P>();
+  Fe<P> ninv = one;
+  if (inverse) {                                                   // fft_ff.py:57
+    Fe<P> nn = fe_zero<P>();
+    nn.v[0] = (uint32_t)n; nn.v[1] = (uint32_t)(n >> 32);
+    ninv = fe_inv<P>(fe_to_mont<P>(nn));
+  }
+  Fe<P> s = one, sinv = one;
+  if (shift_canon) { s = fe_to_mont<P>(*shift_canon); sinv = fe_inv<P>(s); }
+
+  Fe<P> w4 = logn >= 2 ? host_pow<P>(w, n / 4) : one;
+  Fe<P> w8 = logn >= 3 ? host_pow<P>(w, n / 8) : one;
+  Fe<P> w83 = fe_mul<P>(w8, w4);
+  memcpy(pl.consts, w8.v, 32); memcpy(pl.consts + 8, w4.v, 32); memcpy(pl.consts + 16, w83.v, 32);
+
+  uint32_t m = (logn + kMaxB - 1) / kMaxB;
+  if (m == 0) m = 1;
+  std::vector<uint32_t> bs(m);
+  for (uint32_t i = 0; i < m; i++) bs[i] = logn / m + (i < logn % m ? 1 : 0);
+
+  for (int t = (int)m; t >= 1; t--) {
+    PassPlan pp;
+    pp.b = bs[t - 1];
+    uint32_t logJ = 0;
+    for (int u = 0; u < t - 1; u++) logJ += bs[u];
+    pp.logK = logn - logJ - pp.b;
+    pp.logQ = logn - pp.b;
+    uint32_t logC = kLogTile - pp.b;
+    if (logC > pp.logQ) logC = pp.logQ;
+    pp.logC = logC;
+    pp.nd = 0;
+    for (uint32_t rem = pp.b; rem > 0;) { uint32_t dd = rem >= 3 ? 3 : rem; pp.d[pp.nd++] = dd; rem -= dd; }
+    const uint32_t R = 1u << pp.b;
+    const uint64_t K = 1ull << pp.logK, J = 1ull << logJ;
+    int rc;
+    // omega_R^e
+    Fe<P> wR = host_pow<P>(w, n >> pp.b);
+    if ((rc = gen_table<P>(&pp.wR, 1, R, one, one, wR, one))) return rc;
+    pl.bytes += (size_t)R * 32;
+    // boundary table T[l][kk] = w^(J l kk) * [fwd coset: s^(J l)] * [inv, t==1, m>=2: 1/n] * [inv coset, t==1: s^-kk]
+    bool fwd_coset = shift_canon && !inverse, inv_coset = shift_canon && inverse;
+    bool need_bnd = (t < (int)m) || fwd_coset;
+    if (need_bnd) {
+      Fe<P> a0 = (inverse && t == 1 && m >= 2) ? ninv : one;
+      Fe<P> a1 = fwd_coset ? host_pow<P>(s, J) : one;
+      Fe<P> h = (inv_coset && t == 1) ? sinv : one;
+      Fe<P> g = (t < (int)m) ? host_pow<P>(w, J) : one;
+      if ((rc = gen_table<P>(&pp.bnd, R, K, a0, a1, h, g))) return rc;
+      pl.bytes += (size_t)R * K * 32;
+    }
+    // final-store multiplier: [m == 1 inverse: 1/n] * [inverse coset: s^-(kt K)]
+    if (t == 1 && ((inverse && m == 1) || inv_coset)) {
+      Fe<P> a0 = (inverse && m == 1) ? ninv : one;
+      Fe<P> a1 = inv_coset ? host_pow<P>(sinv, K) : one;
+      if ((rc = gen_table<P>(&pp.post, R, 1, a0, a1, one, one))) return rc;
+    }
+    pl.passes.push_back(pp);
+  }
+  return 0;
+}
+
+template <class P>
+int run_plan(const NttPlan& pl, uint32_t* d_data, size_t batch) {
+  KzgpuCtx& cx = kz_ctx();
+  const uint64_t n = 1ull << pl.logn;
+  const size_t bytes = n * batch * 32;
+  const size_t m = pl.passes.size();
+  // ping-pong so that the last pass writes d_data: data -> s0 [-> s1 -> ...] -> data
+  int rc;
+  if ((rc = g_ntt_scratch[0].ensure(bytes))) return rc;
+  if (m >= 3 && (rc = g_ntt_scratch[1].ensure(bytes))) return rc;
+  NttConsts<P> c;
+  memcpy(c.w8.v, pl.consts, 32); memcpy(c.w4.v, pl.consts + 8, 32); memcpy(c.w8_3.v, pl.consts + 16, 32);
+  static bool attr_set = false;
+  if (!attr_set) {
+    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<FrBN254>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4 << kLogTile));
+    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<FrBLS381>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4 << kLogTile));
+    attr_set = true;
+  }
+  const uint32_t* src = d_data;
+  for (size_t i = 0; i < m; i++) {
+    const PassPlan& pp = pl.passes[i];
+    uint32_t* dst;
+    if (i == m - 1) dst = (m == 1) ? (uint32_t*)g_ntt_scratch[0].p : d_data;
+    else dst = (uint32_t*)g_ntt_scratch[(i & 1)].p;
+    if (dst == src) dst = (uint32_t*)g_ntt_scratch[1].p;   // cannot happen with the scheme above; defensive
+    NttPassArgs a;
+    a.in = src; a.out = dst; a.bnd = pp.bnd; a.post = pp.post; a.wR = pp.wR;
+    a.n = n; a.b = pp.b; a.logC = pp.logC; a.logK = pp.logK; a.logQ = pp.logQ; a.nd = pp.nd;
+    for (int k = 0; k < 3; k++) a.d[k] = pp.d[k];
+    uint32_t tile = 1u << (pp.b + pp.logC);
+    uint32_t threads = tile / 8 < 32 ? 32 : (tile / 8 > (uint32_t)kThreads ? kThreads : tile / 8);
+    dim3 grid((unsigned)(1ull << (pp.logQ - pp.logC)), (unsigned)batch);
+    ntt_pass_kernel<P><<<grid, threads, (size_t)tile * 32, cx.stream>>>(a, c);
+    KZ_LAUNCHED();
+    src = dst;
+  }
+  if (m == 1) KZ_CUDA(cudaMemcpyAsync(d_data, src, bytes, cudaMemcpyDeviceToDevice, cx.stream));
+  return 0;
+}
+
+template <class P>
+int ntt_impl(int field, uint32_t* d_data, size_t n, size_t batch, const uint64_t* w, int inverse, const uint64_t* shift) {
+  if (n == 0 || (n & (n - 1))) return kz_fail(KZGPU_EINVAL, "NTT length %zu is not a power of two (fft_ff.py:74)", n);
+  if (batch == 0) return 0;
+  uint32_t logn = 0;
+  while ((1ull << logn) < n) logn++;
+  if (logn > 32) return kz_fail(KZGPU_EINVAL, "NTT length 2^%u too large", logn);
+  Fe<P> wc = kz_fe_from_u64<P>(w), sc;
+  if (!kz_fe_reduced<P>(wc)) return kz_fail(KZGPU_ERANGE, "w is not a canonical field element");
+  if (shift) {
+    sc = kz_fe_from_u64<P>(shift);
+    if (!kz_fe_reduced<P>(sc) || fe_is_zero<P>(sc)) return kz_fail(KZGPU_ERANGE, "coset shift must be a non-zero canonical element");
+  }
+  if (logn == 0) {
+    // n == 1: fft_ff returns its input (fft_ff.py:16-17); inverse scales by 1; coset shift^0 = 1
+    return 0;
+  }
+  if (fe_is_zero<P>(wc)) return kz_fail(KZGPU_ERANGE, "w must be non-zero");
+  // plan lookup
+  for (auto it = g_plans.begin(); it != g_plans.end(); ++it) {
+    if (it->field == field && it->logn == logn && it->inverse == (inverse ? 1 : 0) && it->has_shift == (shift != nullptr) &&
+        !memcmp(it->w, wc.v, 32) && (!shift || !memcmp(it->shift, sc.v, 32))) {
+      g_plans.splice(g_plans.begin(), g_plans, it);
+      return run_plan<P>(g_plans.front(), d_data, batch);
+    }
+  }
+  NttPlan pl;
+  pl.field = field; pl.logn = logn; pl.inverse = inverse ? 1 : 0; pl.has_shift = shift != nullptr;
+  memcpy(pl.w, wc.v, 32);
+  if (shift) memcpy(pl.shift, sc.v, 32); else memset(pl.shift, 0, 32);
+  int rc = build_plan<P>(pl, logn, wc, inverse, shift ? &sc : nullptr);
+  if (rc) { pl.free_tables(); return rc; }
+  g_plans.push_front(pl);
+  while (g_plans.size() > kMaxPlans) { g_plans.back().free_tables(); g_plans.pop_back(); }
+  return run_plan<P>(g_plans.front(), d_data, batch);
+}
+
+int ntt_dispatch(int field, uint32_t* d_data, size_t n, size_t batch, const uint64_t* w, int inverse, const uint64_t* shift) {
+  if (field == KZGPU_BN254) return ntt_impl<FrBN254>(field, d_data, n, batch, w, inverse, shift);
+  if (field == KZGPU_BLS12_381) return ntt_impl<FrBLS381>(field, d_data, n, batch, w, inverse, shift);
+  return kz_fail(KZGPU_EINVAL, "unknown field id %d", field);
+}
+
+KzScratch g_ntt_io;
+
+}  // namespace
+
+void kz_ntt_release() {
+  for (auto& p : g_plans) p.free_tables();
+  g_plans.clear();
+  g_ntt_scratch[0].release(); g_ntt_scratch[1].release(); g_ntt_io.release();
+}
+
+extern "C" {
+
+int kzgpu_ntt_batch_dev(int field, uint64_t* d_data, size_t n, size_t batch, const uint64_t* w, int inverse,
+                        const uint64_t* coset_shift) {
+  KZ_REQUIRE_INIT();
+  if (!d_data || !w) return kz_fail(KZGPU_EINVAL, "null pointer");
+  return ntt_dispatch(field, (uint32_t*)d_data, n, batch, w, inverse, coset_shift);
+}
+
+int kzgpu_ntt_dev(int field, uint64_t* d_data, size_t n, const uint64_t* w, int inverse, const uint64_t* coset_shift) {
+  return kzgpu_ntt_batch_dev(field, d_data, n, 1, w, inverse, coset_shift);
+}
+
+int kzgpu_ntt_batch(int field, uint64_t* data, size_t n, size_t batch, const uint64_t* w, int inverse,
+                    const uint64_t* coset_shift) {
+  KZ_REQUIRE_INIT();
+  if (!data || !w) return kz_fail(KZGPU_EINVAL, "null pointer");
+  if (n == 0 || (n & (n - 1))) return kz_fail(KZGPU_EINVAL, "NTT length %zu is not a power of two (fft_ff.py:74)", n);
+  KzgpuCtx& cx = kz_ctx();
+  size_t bytes = n * batch * 32;
+  if (bytes == 0) return 0;
+  int rc = g_ntt_io.ensure(bytes);
+  if (rc) return rc;
+  KZ_CUDA(cudaMemcpyAsync(g_ntt_io.p, data, bytes, cudaMemcpyHostToDevice, cx.stream));
+  rc = ntt_dispatch(field, (uint32_t*)g_ntt_io.p, n, batch, w, inverse, coset_shift);
+  if (rc) return rc;
+  KZ_CUDA(cudaMemcpyAsync(data, g_ntt_io.p, bytes, cudaMemcpyDeviceToHost, cx.stream));
+  KZ_CUDA(cudaStreamSynchronize(cx.stream));
+  return 0;
+}
+
+int kzgpu_ntt(int field, uint64_t* data, size_t n, const uint64_t* w, int inverse, const uint64_t* coset_shift) {
+  return kzgpu_ntt_batch(field, data, n, 1, w, inverse, coset_shift);
+}
+
+}  // extern "C"

@@ -1,0 +1,246 @@
+"""GPU parity tests proper: every check goes through the C ABI (libkzgpu.so) and compares
+with the CPU oracle (oracle/) on the same seeded inputs.  Bit-exact (integer arithmetic)."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle.params import CURVES, root_of_unity
+from oracle.curve import get_curve
+from oracle.kzg import KZGOracle, poly_eval, poly_div_linear
+from oracle import fft_ff as off
+
+pytestmark = pytest.mark.gpu
+
+CURVE_NAMES = ["bn254", "bls12_381"]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from kzg_snark_b200 import device, _ffi
+    _ffi.init()
+    return device
+
+
+def L(vals, mod, n=4):
+    from kzg_snark_b200.limbs import ints_to_limbs
+    return ints_to_limbs(vals, mod, n)
+
+
+def I(arr):
+    from kzg_snark_b200.limbs import limbs_to_ints
+    return limbs_to_ints(arr)
+
+
+def affine_arr(cv, pts, nl):
+    """oracle projective points -> (n, 2*nl) canonical limbs, infinity = (0,0)."""
+    flat = []
+    for p in pts:
+        a = cv.normalize(p)
+        flat += [0, 0] if a is None else [a[0], a[1]]
+    return L(flat, cv.p, nl).reshape(len(pts), 2 * nl)
+
+
+def point_of(cv, out, inf, nl):
+    if inf:
+        return None
+    v = I(out.reshape(2, nl))
+    return (v[0], v[1])
+
+
+# ------------------------------------------------------------------ field core
+@pytest.mark.parametrize("curve", CURVE_NAMES)
+@pytest.mark.parametrize("which", [0, 1])
+def test_field_ops(dev, curve, which):
+    cv = CURVES[curve]
+    mod = cv["p"] if which == 0 else cv["r"]
+    nl = (cv["fp_limbs32"] if which == 0 else cv["fr_limbs32"]) // 2
+    rng = random.Random(100 + which)
+    edge = [0, 1, 2, mod - 1, mod - 2, (mod - 1) // 2, (mod + 1) // 2, 1 << 32, (1 << 64) - 1]
+    a = edge + [rng.randrange(mod) for _ in range(3000)]
+    b = list(reversed(edge)) + [rng.randrange(mod) for _ in range(3000)]
+    A, Bm = L(a, mod, nl), L(b, mod, nl)
+    assert I(dev.field_op(curve, which, 0, A, Bm)) == [x * y % mod for x, y in zip(a, b)]
+    assert I(dev.field_op(curve, which, 1, A, Bm)) == [(x + y) % mod for x, y in zip(a, b)]
+    assert I(dev.field_op(curve, which, 2, A, Bm)) == [(x - y) % mod for x, y in zip(a, b)]
+    inv = I(dev.field_op(curve, which, 3, A[:64]))
+    assert inv == [pow(x, -1, mod) if x else 0 for x in a[:64]]
+
+
+# ------------------------------------------------------------------ NTT
+@pytest.mark.parametrize("curve", CURVE_NAMES)
+@pytest.mark.parametrize("logn", list(range(0, 15)))
+def test_ntt_matches_oracle(dev, curve, logn):
+    cv = CURVES[curve]
+    r = cv["r"]
+    n = 1 << logn
+    rng = random.Random(1000 + logn)
+    x = [rng.randrange(r) for _ in range(n)]
+    if n >= 4:
+        x[1] = 0; x[2] = r - 1
+    w = root_of_unity(cv, n)
+    wl = L([w], r)[0]
+    got = I(dev.ntt(curve, L(x, r), wl))
+    assert got == off.fft_ff_int(x, w, r)
+    got = I(dev.ntt(curve, L(x, r), wl, inverse=True))
+    assert got == off.ifft_ff_int(x, w, r)
+    sh = L([7], r)[0]
+    got = I(dev.ntt(curve, L(x, r), wl, coset_limbs=sh))
+    assert got == off.coset_fft_ff_int(x, w, 7, r)
+    got = I(dev.ntt(curve, L(x, r), wl, inverse=True, coset_limbs=sh))
+    assert got == off.coset_ifft_ff_int(x, w, 7, r)
+
+
+def test_ntt_batch_and_nonprimitive_root(dev):
+    cv = CURVES["bn254"]; r = cv["r"]
+    rng = random.Random(5)
+    n, batch = 32, 9                              # the Marlin prover's 9 forward FFTs of size m=32
+    w = root_of_unity(cv, n)
+    xs = [[rng.randrange(r) for _ in range(n)] for _ in range(batch)]
+    flat = [v for x in xs for v in x]
+    got = I(dev.ntt("bn254", L(flat, r), L([w], r)[0], batch=batch))
+    exp = [v for x in xs for v in off.fft_ff_int(x, w, r)]
+    assert got == exp
+    # fft_ff never validates w: any w gives sum_j c_j w^(jk)
+    w2 = rng.randrange(2, r)
+    x = xs[0][:16]
+    assert I(dev.ntt("bn254", L(x, r), L([w2], r)[0])) == off.fft_ff_int(x, w2, r)
+
+
+def test_ntt_rejects_non_power_of_two(dev):
+    from kzg_snark_b200._ffi import KzgpuError
+    cv = CURVES["bn254"]; r = cv["r"]
+    with pytest.raises(KzgpuError):
+        dev.ntt("bn254", L([1, 2, 3], r), L([5], r)[0])
+
+
+@pytest.mark.parametrize("logn", [16, 18, 20, 22])
+def test_ntt_large_properties(dev, logn):
+    """Full-size checks that need no O(n log n) CPU work: Horner spot checks, round trip, delta."""
+    from kzg_snark_b200.limbs import random_scalars
+    cv = CURVES["bn254"]; r = cv["r"]
+    n = 1 << logn
+    w = root_of_unity(cv, n); wl = L([w], r)[0]
+    x = random_scalars(n, r, seed=logn)
+    y = dev.ntt("bn254", x.copy(), wl)
+    xi = I(x) if logn <= 18 else None
+    if xi is not None:
+        ks = [0, 1, 2, n // 2, n - 1, 12345 % n]
+        yi = I(y[ks])
+        assert yi == off.dft_definition(xi, w, r, ks)
+    back = dev.ntt("bn254", y.copy(), wl, inverse=True)
+    assert np.array_equal(back, x)
+    d = np.zeros((n, 4), dtype=np.uint64); d[1, 0] = 1          # delta_1 -> [w^k]
+    yd = dev.ntt("bn254", d, wl)
+    ks = [0, 1, 2, 3, n // 2 + 1, n - 1]
+    assert I(yd[ks]) == [pow(w, k, r) for k in ks]
+    # linearity checksum: sum_k y[k] = n * x[0]
+    if xi is not None:
+        assert sum(I(y)) % r == n * xi[0] % r
+
+
+# ------------------------------------------------------------------ MSM / commit
+@pytest.mark.parametrize("curve", CURVE_NAMES)
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 22, 201, 1025])
+def test_msm_matches_oracle(dev, curve, n):
+    cv = get_curve(curve); k = KZGOracle(curve)
+    nl = CURVES[curve]["fp_limbs32"] // 2
+    rng = random.Random(n + 7)
+    tau = rng.randrange(1, cv.r)
+    ck = k.setup_fast(max(n - 1, 0), tau)[:max(n, 1)]
+    srs = dev.Srs.from_affine(curve, affine_arr(cv, ck, nl))
+    coeffs = [rng.randrange(cv.r) for _ in range(n)]
+    if n >= 3:
+        coeffs[0] = 0; coeffs[1] = 1; coeffs[2] = cv.r - 1
+    out, inf = dev.msm(srs, L(coeffs, cv.r) if n else np.zeros((0, 4), np.uint64))
+    exp = cv.normalize(cv.multiply(cv.G1, poly_eval(coeffs, tau, cv.r)))      # tau-identity, kzg.py:108
+    assert point_of(cv, out, inf, nl) == exp
+    if 0 < n <= 201:
+        exp2 = cv.normalize(k.commit(ck, [coeffs])[0])                       # the reference's own loop
+        assert point_of(cv, out, inf, nl) == exp2
+    srs.destroy()
+
+
+@pytest.mark.parametrize("curve", CURVE_NAMES)
+def test_msm_edge_points(dev, curve):
+    """duplicate points, P + (-P), infinity entries, all-equal scalars, zero polynomial."""
+    cv = get_curve(curve)
+    nl = CURVES[curve]["fp_limbs32"] // 2
+    rng = random.Random(3)
+    P = cv.multiply(cv.G1, 1234567)
+    Q = cv.multiply(cv.G1, 7654321)
+    pts = [P, P, cv.neg(P), cv.Z1, Q, Q, P, cv.G1]
+    srs = dev.Srs.from_affine(curve, affine_arr(cv, pts, nl))
+    cases = [
+        [1, 1, 1, 5, 0, 0, 0, 0],
+        [1, 0, 1, 0, 0, 0, 0, 0],          # P + (-P) = O
+        [0] * 8,                           # zero polynomial -> Z1 (kzg.py:109)
+        [3, 3, 3, 3, 3, 3, 3, 3],
+        [cv.r - 1] * 8,
+        [rng.randrange(cv.r) for _ in range(8)],
+        [2, cv.r - 2, 0, 9, 5, cv.r - 5, 0, 0],
+    ]
+    for sc in cases:
+        acc = cv.Z1
+        for p, s in zip(pts, sc):
+            acc = cv.add(acc, cv.multiply(p, s))
+        out, inf = dev.msm(srs, L(sc, cv.r))
+        assert point_of(cv, out, inf, nl) == cv.normalize(acc), sc
+    srs.destroy()
+
+
+def test_msm_degree_check(dev):
+    cv = get_curve("bn254")
+    srs = dev.Srs.from_affine("bn254", affine_arr(cv, [cv.G1] * 4, 4))
+    with pytest.raises(ValueError, match="exceeds maximum allowed degree 3"):   # kzg.py:103-106
+        dev.msm(srs, L([1] * 5, cv.r))
+    srs.destroy()
+
+
+@pytest.mark.parametrize("curve", CURVE_NAMES)
+def test_srs_generate_and_tau_identity(dev, curve):
+    from kzg_snark_b200.limbs import random_scalars
+    cv = get_curve(curve)
+    nl = CURVES[curve]["fp_limbs32"] // 2
+    tau = 0xC0FFEE1234567 % cv.r
+    n = 1 << 14
+    srs = dev.Srs.generate(curve, tau, n)
+    for i in (0, 1, 2, n - 1):
+        got = I(srs.read(i, 1).reshape(2, nl))
+        assert tuple(got) == cv.normalize(cv.multiply(cv.G1, pow(tau, i, cv.r)))
+    sc = random_scalars(n, cv.r, seed=11)
+    out, inf = dev.msm(srs, sc)
+    exp = cv.normalize(cv.multiply(cv.G1, poly_eval(I(sc), tau, cv.r)))
+    assert point_of(cv, out, inf, nl) == exp
+    # skewed, witness-like scalars: half zeros, a quarter small
+    s2 = sc.copy(); s2[::2] = 0; s2[1::4, 1:] = 0; s2[1::4, 0] &= np.uint64(0xFFFF)
+    out, inf = dev.msm(srs, s2)
+    exp = cv.normalize(cv.multiply(cv.G1, poly_eval(I(s2), tau, cv.r)))
+    assert point_of(cv, out, inf, nl) == exp
+    srs.destroy()
+
+
+# ------------------------------------------------------------------ open
+@pytest.mark.parametrize("curve", CURVE_NAMES)
+@pytest.mark.parametrize("lens", [[5], [1], [4, 9, 2], [70, 64, 65, 1, 130], [5000, 4097]])
+def test_open_matches_oracle(dev, curve, lens):
+    cv = get_curve(curve); k = KZGOracle(curve)
+    nl = CURVES[curve]["fp_limbs32"] // 2
+    rng = random.Random(sum(lens))
+    tau = rng.randrange(1, cv.r)
+    polys = [[rng.randrange(cv.r) for _ in range(m)] for m in lens]
+    z, xi = rng.randrange(cv.r), rng.randrange(cv.r)
+    wit = k.witness(polys, z, xi)
+    comb = k.combine(polys, xi)
+    quot, ev = dev.open_quotient(curve, [L(p, cv.r) for p in polys], L([z], cv.r)[0], L([xi], cv.r)[0])
+    q = I(quot) if len(quot) else []
+    while q and q[-1] == 0:
+        q.pop()
+    assert q == wit
+    assert I(ev)[0] == poly_eval(comb, z, cv.r)
+    n = max(lens)
+    srs = dev.Srs.generate(curve, tau, n)
+    out, inf = dev.open_proof(srs, [L(p, cv.r) for p in polys], L([z], cv.r)[0], L([xi], cv.r)[0])
+    exp = cv.normalize(cv.multiply(cv.G1, poly_eval(wit, tau, cv.r)))
+    assert point_of(cv, out, inf, nl) == exp
+    srs.destroy()
