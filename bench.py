@@ -1,0 +1,480 @@
+#!/usr/bin/env python3
+"""bench.py -- the driver's measurement contract for the KZG-MSM / NTT hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload msm|ntt] [--logn 24] [--scaling weak|strong]
+
+Default workload (`msm`): one step = one KZG commit of a 2^24-coefficient polynomial, i.e. one
+BN254 G1 MSM of 2^24 points against the device-resident SRS (BASELINE.json metric "G1 MSM
+points/s ... at 2^24"; configs[2]).  The same line also carries the NTT half of the metric
+(`"ntt"`: BN254 scalar-field NTT of 2^24 elements, configs[1]) with its own roofline.
+`--workload ntt` makes the NTT the primary metric instead.
+
+N > 1 (torchrun, one process per GPU, NCCL): the SRS points and the scalars are sharded by
+index range, every rank reduces its shard to one XYZZ partial sum, the partials are
+all-gathered over NCCL (128 B per rank) and folded.  Default scaling is "weak" (2^logn points
+per GPU); `--scaling strong` splits 2^logn points across the ranks.
+
+`--impl reference` times the reference algorithm's CPU restatement (oracle/: py_ecc-style
+double-and-add commit loop, kzg.py:112-116, recursive fft_ff, fft_ff.py:3-37) on all host
+cores, on a bounded sample of the same workload.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+R_BN254 = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+TAU = 0x2545F4914F6CDD1D9E3779B97F4A7C15F39CC0605CEDC834 % R_BN254      # fixed synthetic trapdoor
+
+# SURVEY.md section 8(d) work model: 16 windows x (8M+2S = 10 modmul) x 272 32-bit IMADs
+MODEL_IMAD_PER_POINT = 43520
+IMAD32_PER_MODMUL = 272
+MODMUL_PER_MADD = 10
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(device), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            return None
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- CPU arms
+def _cpu_commit_chunk(args):
+    """Worker: reference commit loop (kzg.py:112-116) over a slice of (scalar, index) pairs."""
+    seed, start, count, tau = args
+    import random
+    from oracle.kzg import KZGOracle
+    ko = KZGOracle("bn254")
+    rng = random.Random(seed)
+    # SRS slice via the oracle's shared-doubling setup (not timed by the caller? it is part of
+    # producing inputs) -- points tau^i * G1
+    ck = ko.setup_fast(count - 1, tau)
+    coeffs = [rng.randrange(ko.curve_order) for _ in range(count)]
+    t0 = time.perf_counter()
+    c = ko.commit(ck, [coeffs])[0]
+    dt = time.perf_counter() - t0
+    return dt, ko.cv.normalize(c)
+
+
+def cpu_msm_rate(points_per_core, cores):
+    """points/s of the restated reference commit loop using `cores` processes."""
+    jobs = [(1000 + i, 0, points_per_core, TAU) for i in range(cores)]
+    if cores == 1:
+        res = [_cpu_commit_chunk(jobs[0])]
+        wall = res[0][0]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(cores) as pool:
+            res = pool.map(_cpu_commit_chunk, jobs)
+        wall = max(r[0] for r in res)          # commit loop time only (inputs prepared before)
+    return points_per_core * cores / wall, wall
+
+
+def _cpu_ntt_chunk(args):
+    seed, logn = args
+    import random
+    from oracle.fft_ff import fft_ff_int
+    rng = random.Random(seed)
+    n = 1 << logn
+    x = [rng.randrange(R_BN254) for _ in range(n)]
+    w = pow(5, (R_BN254 - 1) // n, R_BN254)
+    t0 = time.perf_counter()
+    fft_ff_int(x, w, R_BN254)
+    return time.perf_counter() - t0
+
+
+def cpu_ntt_rate(logn, cores):
+    """elements/s of the restated recursive fft_ff; `cores` independent vectors in parallel
+    (the reference itself is single-threaded: batched vectors are its only parallelism)."""
+    jobs = [(2000 + i, logn) for i in range(cores)]
+    if cores == 1:
+        wall = _cpu_ntt_chunk(jobs[0])
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(cores) as pool:
+            wall = max(pool.map(_cpu_ntt_chunk, jobs))
+    return (1 << logn) * cores / wall, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    vals, t_all = [], 0.0
+    if args.workload == "msm":
+        per_core = 256
+        unit, metric = "points/s", "g1_msm_points_per_s"
+        for i in range(args.warmup + args.steps):
+            v, wall = cpu_msm_rate(per_core, cores)
+            if i >= args.warmup:
+                vals.append(v); t_all += wall
+        sample = f"{per_core * cores} random BN254 scalars x SRS points per step ({per_core}/core), commit loop kzg.py:112-116"
+        workload = f"BN254 G1 MSM (KZG commit) of 2^{args.logn} points"
+    else:
+        logn_s = 15
+        unit, metric = "elements/s", "ntt_elements_per_s"
+        for i in range(args.warmup + args.steps):
+            v, wall = cpu_ntt_rate(logn_s, cores)
+            if i >= args.warmup:
+                vals.append(v); t_all += wall
+        sample = f"{cores} vectors of 2^{logn_s} elements per step (one per core), recursive fft_ff.py:3-37"
+        workload = f"BN254 scalar-field NTT of 2^{args.logn} elements"
+    value = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "u32x8 (256-bit modular integers)", "data": "synthetic",
+        "config": {"workload": workload, "curve": "bn254", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample,
+                         "note": "restated reference algorithm on CPython ints (SageMath/py_ecc are not installable here)"},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------- GPU arm
+class RawPtr:
+    def __init__(self, p):
+        import ctypes
+        self.ptr = ctypes.c_void_p(p)
+
+
+def on_curve_bn254(out):
+    from kzg_snark_b200.limbs import limbs_to_ints
+    p = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+    x, y = limbs_to_ints(out.reshape(2, 4))
+    return (y * y - x * x * x - 3) % p == 0
+
+
+def run_gpu(args):
+    import numpy as np
+    from kzg_snark_b200 import _ffi, device
+    from kzg_snark_b200.limbs import random_scalars, ints_to_limbs, limbs_to_ints
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _ffi.init(local)
+    info = _ffi.device_info()
+    peaks, peak_src = load_peaks()
+    K, Wm = args.steps, args.warmup
+    n_total = 1 << args.logn
+    if world > 1 and args.scaling == "strong":
+        n = n_total // world
+    else:
+        n = n_total                           # weak: per-GPU work fixed
+    start = rank * n
+    if world > 1:
+        _ffi.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        _ffi.check(_ffi._lib.kzgpu_sync())
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    result = {}
+
+    # ------------------------------------------------------------------ integer roofline (live)
+    sm = info["sm_count"]
+    ms_i, ops_i = _ffi.microbench(0, sm * 4, 256, 2000)
+    imad_wide_peak = ops_i / ms_i * 1e3                   # IMAD.WIDE.U32 / s
+    imad32_peak = 2.0 * imad_wide_peak                    # one wide = two 32-bit multiply-add slots
+
+    # ------------------------------------------------------------------ MSM
+    def bench_msm():
+        srs = device.Srs.generate("bn254", TAU, n, start=start)
+        pinned = _ffi.PinnedArray((n, 4))
+        pinned.array[:] = random_scalars(n, R_BN254, seed=args.logn * 100 + rank)
+        dsc = _ffi.DeviceBuffer(n * 32).upload(pinned.array)
+        if world > 1:
+            partial = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            gathered = torch.zeros(128 * world, dtype=torch.uint8, device="cuda")
+
+        def step_resident():
+            if world == 1:
+                return device.msm_dev(srs, dsc, n)
+            device.msm_partial_dev(srs, dsc, n, RawPtr(partial.data_ptr()))
+            dist.all_gather_into_tensor(gathered, partial)
+            return device.g1_fold("bn254", RawPtr(gathered.data_ptr()), world)
+
+        def step_e2e():
+            if world == 1:
+                return device.msm(srs, pinned.array)       # H2D of the scalars inside the call
+            dsc.upload(pinned.array)
+            return step_resident()
+
+        for _ in range(Wm):
+            out, inf = step_resident()
+        assert not inf and on_curve_bn254(out), "MSM result is not a curve point"
+        # timed region: resident inputs, device clock
+        sampler = ClockSampler(local)
+        barrier()
+        l0 = _ffi.launch_count()
+        if world == 1:
+            _ffi.timer_start()
+            for _ in range(K):
+                step_resident()
+            ms = _ffi.timer_stop()
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(K):
+                step_resident()
+            e1.record(); e1.synchronize()
+            ms = e0.elapsed_time(e1)
+        barrier()
+        launches = _ffi.launch_count() - l0
+        clocks = sampler.stop()
+        ms = max_over_ranks(ms)
+        # per-kernel profile (second region, CUDA events around the kernels on the launching stream)
+        _ffi.profile_reset(); _ffi.profile_enable(True)
+        for _ in range(K):
+            step_resident()
+        _ffi.profile_enable(False)
+        prof = {k: _ffi.profile_get(i) for k, i in (("accumulate", 0), ("sort", 2), ("reduce", 3))}
+        # e2e: host (pinned) scalars in, affine point out, every step
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            step_e2e()
+        barrier()
+        ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        acc = prof["accumulate"]
+        acc_ms = acc["ms"] / max(acc["launches"], 1)
+        madds = acc["work"] / max(acc["launches"], 1)            # mixed additions per launch (n * windows upper bound)
+        pts_per_s = world * n * K / (ms * 1e-3)
+        res = {
+            "value": pts_per_s, "ms": ms, "launches": launches, "clocks": clocks,
+            "e2e": {"value": world * n * K / (ms_e2e * 1e-3), "unit": "points/s",
+                    "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": (64 + 4) * world,
+                    "ms_per_step": ms_e2e / K, "host_buffers": "pinned (cudaHostAlloc)"},
+            "roofline": {
+                "bound": "imad", "kernel": "msm_accumulate_kernel",
+                "achieved": (n / (acc_ms * 1e-3)) * MODEL_IMAD_PER_POINT / 1e9,
+                "peak": imad32_peak / 1e9, "unit": "G IMAD32/s",
+                "frac": (n / (acc_ms * 1e-3)) * MODEL_IMAD_PER_POINT / imad32_peak,
+                "traffic": None,
+                "model": "SURVEY 8(d): 43,520 32-bit IMAD per point (16 windows x 10 modmul x 272); "
+                         "peak = live IMAD.WIDE.U32 microbenchmark x 2",
+                "executed_frac": madds * MODMUL_PER_MADD * IMAD32_PER_MODMUL / (acc_ms * 1e-3) / imad32_peak,
+                "kernel_ms": acc_ms, "kernel_share_of_step": acc["ms"] / max(sum(p["ms"] for p in prof.values()), 1e-9),
+                "hbm_algorithmic_gbs": n * 96 / (acc_ms * 1e-3) / 1e9,
+                "hbm_peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src,
+            },
+            "profile_ms_per_step": {k: v["ms"] / K for k, v in prof.items()},
+        }
+        srs.destroy(); dsc.free(); pinned.free()
+        return res
+
+    # ------------------------------------------------------------------ NTT
+    def bench_ntt():
+        w = pow(5, (R_BN254 - 1) // n_total, R_BN254)
+        wl = ints_to_limbs([w], R_BN254)[0]
+        pinned = _ffi.PinnedArray((n_total, 4))
+        pinned.array[:] = random_scalars(n_total, R_BN254, seed=args.logn + 7 * rank)
+        d = _ffi.DeviceBuffer(n_total * 32).upload(pinned.array)
+        for _ in range(Wm):
+            device.ntt_dev("bn254", d, n_total, wl)
+        sampler = ClockSampler(local)
+        barrier()
+        l0 = _ffi.launch_count()
+        _ffi.timer_start() if world == 1 else None
+        if world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        for _ in range(K):
+            device.ntt_dev("bn254", d, n_total, wl)
+        if world == 1:
+            ms = _ffi.timer_stop()
+        else:
+            e1.record(); e1.synchronize()
+            ms = e0.elapsed_time(e1)
+        barrier()
+        launches = _ffi.launch_count() - l0
+        clocks = sampler.stop()
+        ms = max_over_ranks(ms)
+        _ffi.profile_reset(); _ffi.profile_enable(True)
+        for _ in range(K):
+            device.ntt_dev("bn254", d, n_total, wl)
+        _ffi.profile_enable(False)
+        pr = _ffi.profile_get(1)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            device.ntt("bn254", pinned.array, wl)            # H2D + kernels + D2H inside the call
+        barrier()
+        ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        ntt_ms = pr["ms"] / K                                   # all passes of one transform
+        hbm = 64.0 * n_total / (ntt_ms * 1e-3) / 1e9
+        modmuls = 0.5 * n_total * args.logn
+        res = {
+            "value": world * n_total * K / (ms * 1e-3), "ms": ms, "launches": launches, "clocks": clocks,
+            "e2e": {"value": world * n_total * K / (ms_e2e * 1e-3), "unit": "elements/s",
+                    "h2d_bytes_per_step": n_total * 32 * world, "d2h_bytes_per_step": n_total * 32 * world,
+                    "ms_per_step": ms_e2e / K, "host_buffers": "pinned (cudaHostAlloc)"},
+            "roofline": {
+                "bound": "hbm", "kernel": "ntt_pass_kernel (all passes of one transform)",
+                "achieved": hbm, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": hbm / peaks.get("hbm_gbs"),
+                "traffic": None, "peak_source": peak_src,
+                "model": "SURVEY 8(d): algorithmic bytes = 2 x 32 B x n (twiddles not counted)",
+                "passes": pr["launches"] // K, "kernel_ms": ntt_ms,
+                "imad_frac": modmuls * IMAD32_PER_MODMUL / (ntt_ms * 1e-3) / imad32_peak,
+                "imad_model": "SURVEY 8(d): (n/2) log2 n modmul x 272 IMAD32; the binding bound for 256-bit fields",
+            },
+        }
+        d.free(); pinned.free()
+        return res
+
+    primary = bench_msm() if args.workload == "msm" else bench_ntt()
+    secondary = None
+    if args.workload == "msm" and not args.no_secondary:
+        secondary = bench_ntt()
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        if args.workload == "msm":
+            v, wall = cpu_msm_rate(4096, 1)
+            cpu = {"value": v, "unit": "points/s", "cores": 1, "kind": "port",
+                   "sample": f"4096-point commit (kzg.py:112-116 loop on the restated py_ecc arithmetic), {wall:.1f} s",
+                   "host_cpus": os.cpu_count()}
+            if secondary is not None:
+                v2, wall2 = cpu_ntt_rate(17, 1)
+                secondary["cpu_baseline"] = {"value": v2, "unit": "elements/s", "cores": 1, "kind": "port",
+                                             "sample": f"2^17-element recursive fft_ff (fft_ff.py:3-37 on CPython ints), {wall2:.1f} s"}
+        else:
+            v, wall = cpu_ntt_rate(18, 1)
+            cpu = {"value": v, "unit": "elements/s", "cores": 1, "kind": "port",
+                   "sample": f"2^18-element recursive fft_ff (fft_ff.py:3-37 on CPython ints), {wall:.1f} s",
+                   "host_cpus": os.cpu_count()}
+
+    if rank == 0:
+        if args.workload == "msm":
+            metric, unit = "g1_msm_points_per_s", "points/s"
+            workload = (f"BN254 G1 MSM (KZG commit) of 2^{args.logn} points" +
+                        (f" per GPU, SRS/scalars sharded by index range over {world} GPUs, NCCL all-gather of XYZZ partials"
+                         if world > 1 and args.scaling == "weak" else
+                         (f" split over {world} GPUs" if world > 1 else "")))
+            footprint = "inputs 1.5 GiB/GPU (SRS 1 GiB + scalars 512 MiB at 2^24) exceed the 126 MB L2"
+        else:
+            metric, unit = "ntt_elements_per_s", "elements/s"
+            workload = f"BN254 scalar-field NTT of 2^{args.logn} elements" + (f", one vector per GPU ({world} replicas)" if world > 1 else "")
+            footprint = "512 MiB vector at 2^24 exceeds the 126 MB L2"
+        line = {
+            "metric": metric, "value": primary["value"], "unit": unit, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": primary["ms"] / K, "higher_is_better": True,
+            "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
+            "dtype": "u32x8 (256-bit modular integers, Montgomery)", "data": "synthetic",
+            "config": {"workload": workload, "curve": "bn254", "logn": args.logn, "l2": footprint,
+                       "srs": "tau^i*G1 generated on device from a fixed tau", "scalars": "uniform in [0,r), numpy PCG64"},
+            "clocks": primary["clocks"], "e2e": primary["e2e"], "gpu_launches": primary["launches"],
+            "roofline": primary["roofline"], "cpu_baseline": cpu,
+            "imad_wide_peak_per_s": imad_wide_peak, "device": info["name"],
+        }
+        if "profile_ms_per_step" in primary:
+            line["profile_ms_per_step"] = primary["profile_ms_per_step"]
+        if secondary is not None:
+            line["ntt"] = {"metric": "ntt_elements_per_s", "value": secondary["value"], "unit": "elements/s",
+                           "ms_per_step": secondary["ms"] / K, "e2e": secondary["e2e"], "roofline": secondary["roofline"],
+                           "gpu_launches": secondary["launches"], "clocks": secondary["clocks"],
+                           "cpu_baseline": secondary.get("cpu_baseline"),
+                           "config": {"workload": f"BN254 scalar-field NTT of 2^{args.logn} elements, natural order in/out"}}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="msm", choices=["msm", "ntt"])
+    ap.add_argument("--logn", type=int, default=24)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the NTT half of the metric")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3 if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -53,6 +53,14 @@ int kzgpu_free(void* d_ptr);
 int kzgpu_h2d(void* d_dst, const void* src, size_t bytes);
 int kzgpu_d2h(void* dst, const void* d_src, size_t bytes);
 int kzgpu_sync(void);
+/* page-locked host memory (cudaHostAlloc) so that host<->device copies of the timed e2e
+ * path run at PCIe rate */
+int kzgpu_host_alloc(void** h_ptr, size_t bytes);
+int kzgpu_host_free(void* h_ptr);
+/* run every subsequent launch/copy on the caller's stream (a cudaStream_t passed as void*);
+ * NULL restores the library's own stream.  Lets a host that already owns a stream (e.g. the
+ * torch.distributed/NCCL plumbing of the multi-GPU bench) order and time the kernels. */
+int kzgpu_set_stream(void* cuda_stream);
 /* CUDA-event timing on the library's stream (bench.py: device time of a bracketed region) */
 int kzgpu_timer_start(void);
 int kzgpu_timer_stop(float* ms);
@@ -64,6 +72,9 @@ int kzgpu_srs_create(int curve, const uint64_t* affine_xy, size_t n, uint64_t* h
 /* Device-side replacement of the setup loop kzg.py:69-72 for a given secret tau
  * (canonical, 4 limbs): points[i] = tau^i * G1, i < n. */
 int kzgpu_srs_generate(int curve, const uint64_t* tau, size_t n, uint64_t* handle);
+/* same for the index range [start, start + n): points[i] = tau^(start + i) * G1 -- one GPU's
+ * shard of a point-sharded SRS */
+int kzgpu_srs_generate_range(int curve, const uint64_t* tau, size_t start, size_t n, uint64_t* handle);
 int kzgpu_srs_destroy(uint64_t handle);
 int kzgpu_srs_size(uint64_t handle, size_t* n);
 /* read back `count` points starting at `first` as canonical affine limbs */
@@ -130,6 +141,12 @@ int kzgpu_field_op(int curve, int which, int op, const uint64_t* a, const uint64
  * kind: 0 = IMAD.WIDE.U32 carry chain (raw pipe), 1 = Fp(BN254) Montgomery mul,
  *       2 = Fp(BLS12-381) Montgomery mul, 3 = XYZZ mixed add BN254, 4 = XYZZ mixed add BLS */
 int kzgpu_microbench(int kind, int blocks, int threads, int iters, float* ms, double* ops);
+/* per-kernel device timing (CUDA events on the launching stream) for bench.py's roofline:
+ * which: 0 = MSM bucket-accumulate kernel, 1 = NTT pass kernel, 2 = MSM sort (histogram+scatter),
+ *        3 = MSM bucket reduction + window fold.  Accumulates while enabled. */
+int kzgpu_profile_enable(int on);
+int kzgpu_profile_reset(void);
+int kzgpu_profile_get(int which, double* total_ms, uint64_t* launches, double* work_units);
 /* number of kernel launches issued by the library since init (bench.py "gpu_launches") */
 int kzgpu_launch_count(uint64_t* count);
 

@@ -46,10 +46,14 @@ SIGNATURES = {
     "kzgpu_h2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "kzgpu_d2h": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "kzgpu_sync": (ctypes.c_int, []),
+    "kzgpu_host_alloc": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]),
+    "kzgpu_host_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "kzgpu_set_stream": (ctypes.c_int, [ctypes.c_void_p]),
     "kzgpu_timer_start": (ctypes.c_int, []),
     "kzgpu_timer_stop": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
     "kzgpu_srs_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, _u64p]),
     "kzgpu_srs_generate": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, _u64p]),
+    "kzgpu_srs_generate_range": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, _u64p]),
     "kzgpu_srs_destroy": (ctypes.c_int, [ctypes.c_uint64]),
     "kzgpu_srs_size": (ctypes.c_int, [ctypes.c_uint64, _szp]),
     "kzgpu_srs_read": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p]),
@@ -66,6 +70,9 @@ SIGNATURES = {
     "kzgpu_open_quotient": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, _szp, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _szp, ctypes.c_void_p]),
     "kzgpu_field_op": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "kzgpu_microbench": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]),
+    "kzgpu_profile_enable": (ctypes.c_int, [ctypes.c_int]),
+    "kzgpu_profile_reset": (ctypes.c_int, []),
+    "kzgpu_profile_get": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), _u64p, ctypes.POINTER(ctypes.c_double)]),
     "kzgpu_launch_count": (ctypes.c_int, [_u64p]),
 }
 
@@ -190,3 +197,45 @@ def microbench(kind, blocks, threads, iters):
     ops = ctypes.c_double(0)
     check(lib.kzgpu_microbench(kind, blocks, threads, iters, ctypes.byref(ms), ctypes.byref(ops)))
     return ms.value, ops.value
+
+
+def set_stream(cuda_stream):
+    """Run the library on the caller's CUDA stream (int handle, e.g. torch's cuda_stream); 0/None = own."""
+    check(init().kzgpu_set_stream(ctypes.c_void_p(cuda_stream or 0)))
+
+
+def profile_enable(on=True):
+    check(init().kzgpu_profile_enable(1 if on else 0))
+
+
+def profile_reset():
+    check(init().kzgpu_profile_reset())
+
+
+def profile_get(which):
+    ms = ctypes.c_double(0)
+    n = ctypes.c_uint64(0)
+    w = ctypes.c_double(0)
+    check(init().kzgpu_profile_get(which, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(w)))
+    return {"ms": ms.value, "launches": n.value, "work": w.value}
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc'ed memory (for the e2e leg of bench.py)."""
+
+    def __init__(self, shape, dtype=np.uint64):
+        lib = init()
+        self.shape = tuple(shape)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = ctypes.c_void_p(0)
+        check(lib.kzgpu_host_alloc(ctypes.byref(p), self.nbytes))
+        self.ptr = p
+        buf = (ctypes.c_uint8 * self.nbytes).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+
+    def free(self):
+        if self.ptr is not None and _lib is not None and _inited:
+            self.array = None
+            _lib.kzgpu_host_free(self.ptr)
+        self.ptr = None

@@ -15,12 +15,40 @@ struct KzgpuCtx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t own_stream = nullptr;
   uint64_t launches = 0;
   char err[512] = {0};
+  // per-kernel profiling (bench.py roofline): enabled -> events around selected launches
+  bool profile = false;
+  double prof_ms[4] = {0, 0, 0, 0};
+  uint64_t prof_launches[4] = {0, 0, 0, 0};
+  double prof_work[4] = {0, 0, 0, 0};
 };
 
 KzgpuCtx& kz_ctx();
 int kz_fail(int code, const char* fmt, ...);
+
+// scoped CUDA-event timer around one or more launches of a profiled kernel class
+struct KzProf {
+  int which;
+  bool on;
+  cudaEvent_t a = nullptr, b = nullptr;
+  KzProf(int which_) : which(which_), on(kz_ctx().profile) {
+    if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, kz_ctx().stream); }
+  }
+  void stop(uint64_t launches, double work) {
+    if (!on) return;
+    cudaEventRecord(b, kz_ctx().stream);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    KzgpuCtx& cx = kz_ctx();
+    cx.prof_ms[which] += ms; cx.prof_launches[which] += launches; cx.prof_work[which] += work;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    on = false;
+  }
+  ~KzProf() { if (on) { cudaEventDestroy(a); cudaEventDestroy(b); } }
+};
 
 #define KZ_REQUIRE_INIT() \
   do { if (!kz_ctx().inited) return kz_fail(KZGPU_ENOTINIT, "kzgpu_init has not been called"); } while (0)

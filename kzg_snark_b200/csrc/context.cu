@@ -147,7 +147,8 @@ int kzgpu_init(int device) {
   if (prop.major != 10)
     return kz_fail(KZGPU_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
   cx.sm_count = prop.multiProcessorCount;
-  KZ_CUDA(cudaStreamCreateWithFlags(&cx.stream, cudaStreamNonBlocking));
+  KZ_CUDA(cudaStreamCreateWithFlags(&cx.own_stream, cudaStreamNonBlocking));
+  cx.stream = cx.own_stream;
   KZ_CUDA(cudaEventCreate(&cx.ev0));
   KZ_CUDA(cudaEventCreate(&cx.ev1));
   cx.device = device;
@@ -165,7 +166,8 @@ int kzgpu_shutdown(void) {
   kz_poly_release();
   cudaEventDestroy(cx.ev0);
   cudaEventDestroy(cx.ev1);
-  cudaStreamDestroy(cx.stream);
+  cudaStreamDestroy(cx.own_stream);
+  cx.stream = cx.own_stream = nullptr;
   cx.inited = false;
   cx.device = -1;
   return 0;
@@ -224,6 +226,47 @@ int kzgpu_d2h(void* dst, const void* d_src, size_t bytes) {
 int kzgpu_sync(void) {
   KZ_REQUIRE_INIT();
   KZ_CUDA(cudaStreamSynchronize(kz_ctx().stream));
+  return 0;
+}
+
+int kzgpu_host_alloc(void** h_ptr, size_t bytes) {
+  KZ_REQUIRE_INIT();
+  if (!h_ptr) return kz_fail(KZGPU_EINVAL, "null pointer");
+  KZ_CUDA(cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+  return 0;
+}
+
+int kzgpu_host_free(void* h_ptr) {
+  KZ_REQUIRE_INIT();
+  KZ_CUDA(cudaFreeHost(h_ptr));
+  return 0;
+}
+
+int kzgpu_set_stream(void* cuda_stream) {
+  KZ_REQUIRE_INIT();
+  KzgpuCtx& cx = kz_ctx();
+  KZ_CUDA(cudaStreamSynchronize(cx.stream));
+  cx.stream = cuda_stream ? (cudaStream_t)cuda_stream : cx.own_stream;
+  return 0;
+}
+
+int kzgpu_profile_enable(int on) {
+  kz_ctx().profile = on != 0;
+  return 0;
+}
+
+int kzgpu_profile_reset(void) {
+  KzgpuCtx& cx = kz_ctx();
+  for (int i = 0; i < 4; i++) { cx.prof_ms[i] = 0; cx.prof_launches[i] = 0; cx.prof_work[i] = 0; }
+  return 0;
+}
+
+int kzgpu_profile_get(int which, double* total_ms, uint64_t* launches, double* work_units) {
+  if (which < 0 || which > 3) return KZGPU_EINVAL;
+  KzgpuCtx& cx = kz_ctx();
+  if (total_ms) *total_ms = cx.prof_ms[which];
+  if (launches) *launches = cx.prof_launches[which];
+  if (work_units) *work_units = cx.prof_work[which];
   return 0;
 }
 

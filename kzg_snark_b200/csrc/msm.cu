@@ -290,7 +290,7 @@ template <class Cfg> __global__ void srs_from_mont_kernel(const uint32_t* pts, s
 
 // SRS generation (kzg.py:69-72): point i = tau^i * G1.  dbl_table[j] = 2^j * G1 (affine, Montgomery).
 template <class Cfg>
-__global__ void __launch_bounds__(128) srs_generate_kernel(uint32_t* pts, size_t n, Fe<typename Cfg::Fr> tau_mont,
+__global__ void __launch_bounds__(128) srs_generate_kernel(uint32_t* pts, size_t start, size_t n, Fe<typename Cfg::Fr> tau_mont,
                                                           const uint32_t* __restrict__ dbl_table) {
   using P = typename Cfg::Fp;
   using R = typename Cfg::Fr;
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(128) srs_generate_kernel(uint32_t* pts, size_t
   if (i >= n) return;
   // tau^i in the scalar field
   Fe<R> base = tau_mont, e = fe_one<R>();
-  for (size_t k = i; k; k >>= 1) {
+  for (size_t k = start + i; k; k >>= 1) {
     if (k & 1) e = fe_mul<R>(e, base);
     if (k >> 1) base = fe_sqr<R>(base);
   }
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(128) srs_generate_kernel(uint32_t* pts, size_t
 }
 
 // ---------------------------------------------------------------- host side
-uint32_t choose_c(size_t n) {
+uint32_t choose_c(size_t n, int bits) {
   const char* env = getenv("KZGPU_MSM_C");
   if (env) {
     int v = atoi(env);
@@ -324,10 +324,21 @@ uint32_t choose_c(size_t n) {
   }
   uint32_t logn = 0;
   while ((1ull << (logn + 1)) <= n) logn++;
-  int c = (int)logn - 4;
-  if (c < 3) c = 3;
-  if (c > 20) c = 20;
-  return (uint32_t)c;
+  int c0 = (int)logn - 4;
+  if (c0 < 3) c0 = 3;
+  if (c0 > 20) c0 = 20;
+  // the top window holds bits - c*(W-1) bits; a nearly empty top window concentrates all points
+  // in a handful of buckets, so prefer the nearest c whose top window is at least half full
+  for (int d = 0; d <= 4; d++) {
+    for (int sgn = 1; sgn >= -1; sgn -= 2) {
+      int c = c0 + sgn * d;
+      if (c < 3 || c > 22) continue;
+      int W = (bits + 1 + c - 1) / c;
+      int top = bits - c * (W - 1);
+      if (2 * top >= c) return (uint32_t)c;
+    }
+  }
+  return (uint32_t)c0;
 }
 
 template <class Cfg>
@@ -336,7 +347,7 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   using R = typename Cfg::Fr;
   KzgpuCtx& cx = kz_ctx();
   cudaStream_t st = cx.stream;
-  const uint32_t c = choose_c(n);
+  const uint32_t c = choose_c(n, R::BITS);
   const uint32_t W = (R::BITS + 1 + c - 1) / c;
   const uint32_t B = 1u << (c - 1);
   const size_t nb = (size_t)W * B;
@@ -364,6 +375,7 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   KZ_CUDA(cudaMemsetAsync(counts, 0, nb * 4, st));
   KZ_CUDA(cudaMemsetAsync(flag, 0, 4, st));
   const uint32_t top_bits = R::BITS - 224;       // bits allowed in the top 32-bit word
+  KzProf prof_sort(2);
   if (n) {
     msm_sort_kernel<0><<<(unsigned)kz_div_up(n, 256), 256, 0, st>>>(d_scalars, n, c, W, top_bits, counts, nullptr, flag);
     KZ_LAUNCHED();
@@ -378,9 +390,13 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
     msm_sort_kernel<1><<<(unsigned)kz_div_up(n, 256), 256, 0, st>>>(d_scalars, n, c, W, top_bits, cursor, entries, flag);
     KZ_LAUNCHED();
   }
+  prof_sort.stop(5, (double)n);
+  KzProf prof_acc(0);
   msm_accumulate_kernel<Cfg><<<(unsigned)kz_div_up(nb, 128), 128, 0, st>>>(srs.d_points, first, offsets, entries, (uint32_t)nb,
                                                                           (uint32_t*)g_ws.buckets.p);
   KZ_LAUNCHED();
+  prof_acc.stop(1, (double)n * W);
+  KzProf prof_red(3);
   msm_reduce_kernel<Cfg><<<(unsigned)kz_div_up((size_t)cpw * W, 128), 128, 0, st>>>((uint32_t*)g_ws.buckets.p, B, CH, cpw, W,
                                                                                    (uint32_t*)g_ws.partials.p);
   KZ_LAUNCHED();
@@ -388,6 +404,7 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   KZ_LAUNCHED();
   msm_final_kernel<Cfg><<<1, 32, 0, st>>>((uint32_t*)g_ws.winsums.p, W, c, mode, d_out);
   KZ_LAUNCHED();
+  prof_red.stop(3, (double)nb);
   uint32_t hflag = 0;
   KZ_CUDA(cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, st));
   KZ_CUDA(cudaStreamSynchronize(st));
@@ -442,7 +459,7 @@ int srs_create_impl(const uint64_t* affine_xy, size_t n, uint64_t* handle) {
 }
 
 template <class Cfg>
-int srs_generate_impl(const uint64_t* tau, size_t n, uint64_t* handle) {
+int srs_generate_impl(const uint64_t* tau, size_t start, size_t n, uint64_t* handle) {
   using P = typename Cfg::Fp;
   using R = typename Cfg::Fr;
   KzgpuCtx& cx = kz_ctx();
@@ -465,7 +482,7 @@ int srs_generate_impl(const uint64_t* tau, size_t n, uint64_t* handle) {
   size_t bytes = n * 2 * P::N * 4;
   KZ_CUDA(cudaMalloc((void**)&s.d_points, bytes ? bytes : 16));
   if (n) {
-    srs_generate_kernel<Cfg><<<(unsigned)kz_div_up(n, 128), 128, 0, cx.stream>>>(s.d_points, n, fe_to_mont<R>(t), d_table);
+    srs_generate_kernel<Cfg><<<(unsigned)kz_div_up(n, 128), 128, 0, cx.stream>>>(s.d_points, start, n, fe_to_mont<R>(t), d_table);
     KZ_LAUNCHED();
   }
   KZ_CUDA(cudaStreamSynchronize(cx.stream));
@@ -520,12 +537,16 @@ int kzgpu_srs_create(int curve, const uint64_t* affine_xy, size_t n, uint64_t* h
   return kz_fail(KZGPU_EINVAL, "Unsupported curve type: %d", curve);
 }
 
-int kzgpu_srs_generate(int curve, const uint64_t* tau, size_t n, uint64_t* handle) {
+int kzgpu_srs_generate_range(int curve, const uint64_t* tau, size_t start, size_t n, uint64_t* handle) {
   KZ_REQUIRE_INIT();
   if (!handle || !tau) return kz_fail(KZGPU_EINVAL, "null pointer");
-  if (curve == KZGPU_BN254) return srs_generate_impl<BN254Cfg>(tau, n, handle);
-  if (curve == KZGPU_BLS12_381) return srs_generate_impl<BLS381Cfg>(tau, n, handle);
+  if (curve == KZGPU_BN254) return srs_generate_impl<BN254Cfg>(tau, start, n, handle);
+  if (curve == KZGPU_BLS12_381) return srs_generate_impl<BLS381Cfg>(tau, start, n, handle);
   return kz_fail(KZGPU_EINVAL, "Unsupported curve type: %d", curve);
+}
+
+int kzgpu_srs_generate(int curve, const uint64_t* tau, size_t n, uint64_t* handle) {
+  return kzgpu_srs_generate_range(curve, tau, 0, n, handle);
 }
 
 int kzgpu_srs_destroy(uint64_t handle) {

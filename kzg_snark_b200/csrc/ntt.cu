@@ -387,8 +387,10 @@ int run_plan(const NttPlan& pl, uint32_t* d_data, size_t batch) {
     uint32_t tile = 1u << (pp.b + pp.logC);
     uint32_t threads = tile / 8 < 32 ? 32 : (tile / 8 > (uint32_t)kThreads ? kThreads : tile / 8);
     dim3 grid((unsigned)(1ull << (pp.logQ - pp.logC)), (unsigned)batch);
+    KzProf prof(1);
     ntt_pass_kernel<P><<<grid, threads, (size_t)tile * 32, cx.stream>>>(a, c);
     KZ_LAUNCHED();
+    prof.stop(1, (double)n * (double)batch);
     src = dst;
   }
   if (m == 1) KZ_CUDA(cudaMemcpyAsync(d_data, src, bytes, cudaMemcpyDeviceToDevice, cx.stream));

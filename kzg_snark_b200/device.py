@@ -80,13 +80,14 @@ class Srs:
         return cls(cid, h.value, n)
 
     @classmethod
-    def generate(cls, curve, tau, n):
-        """ck[i] = tau^i * G1 computed on the device (kzg.py:69-72 with the secret supplied)."""
+    def generate(cls, curve, tau, n, start=0):
+        """ck[i] = tau^(start+i) * G1 computed on the device (kzg.py:69-72 with the secret
+        supplied); start > 0 gives one GPU's shard of a point-sharded key."""
         lib = _ffi.init()
         cid = curve_id(curve)
         t = np.frombuffer((int(tau) % FR[cid]).to_bytes(32, "little"), dtype="<u8").copy()
         h = ctypes.c_uint64(0)
-        check(lib.kzgpu_srs_generate(cid, ptr(t), n, ctypes.byref(h)))
+        check(lib.kzgpu_srs_generate_range(cid, ptr(t), start, n, ctypes.byref(h)))
         return cls(cid, h.value, n)
 
     def read(self, first, count):

@@ -1,0 +1,203 @@
+"""Drop-in replacement for the reference's kzg.py: class `KZG` with the same constructor,
+methods and attributes (kzg.py:18-288), whose prover-side hot path -- `commit` (G1 MSM) and
+`open` (xi-combination, synthetic division, MSM) -- runs on the sm_100a kernels behind
+libkzgpu.so.  `setup` builds the G1 powers on the device as well.
+
+What is NOT accelerated, by design: `check` and
+`batch_check` are verifier-side, O(#polynomials) group operations plus two pairings; as in the
+reference they run on py_ecc, and raise ImportError when py_ecc is not installed.
+
+The GPU context is a process-wide singleton (six KZG instances exist in one PLONK run,
+SURVEY.md section 8b); device copies of commitment keys are cached per `ck` list.
+There is no CPU fallback for commit/open/setup.
+"""
+
+import numpy as np
+
+from . import device
+from ._ffi import CURVE_IDS
+from .limbs import ints_to_limbs, int_to_limbs
+from .points import PointCodec
+
+try:                                                   # the reference's own algebra types
+    from sage.all import GF, PolynomialRing            # kzg.py:1
+    HAVE_SAGE = True
+except ImportError:                                    # not installed here: caller-side shim
+    from .sageshim import GF, PolynomialRing
+    HAVE_SAGE = False
+
+_G1 = {"bn254": (1, 2), "bls12_381": (
+    0x17F1D3A73197D7942695638C4FA9AC0FC3688C4F9774B905A14E3A3F171BAC586C55E83FF97A1AEFFB3AF00ADB22C6BB,
+    0x08B3F481E3AAA0F1A09E30ED741D8AE4FCF5E095D5D00AF600DB18CB2C04B3EDD03CC744A2888AE40CAA232946C5E7E1)}
+
+
+class CommitmentKey(list):
+    """ck = [tau^i * G1] as a plain list of py_ecc-shaped points (what kzg.py:69-72 returns),
+    carrying the handle of its device-resident copy so commit/open never re-upload it."""
+    srs = None
+
+
+def _needs_py_ecc(name):
+    def stub(*a, **k):
+        raise ImportError(f"py_ecc is required for the verifier-side operation `{name}` "
+                          "(KZG.check / batch_check are not part of the accelerated path)")
+    return stub
+
+
+# device copies of commitment keys handed in as plain lists: id(ck) -> (fingerprint, Srs)
+_SRS_CACHE = {}
+_SRS_CACHE_MAX = 8
+
+
+class KZG:
+    def __init__(self, curve_type="bn254"):
+        if curve_type not in CURVE_IDS:
+            raise ValueError(f"Unsupported curve type: {curve_type}")          # kzg.py:37
+        self.curve_type = curve_type
+        self._cid = CURVE_IDS[curve_type]
+        self._codec = PointCodec(curve_type, self._cid)
+        try:                                                                   # kzg.py:26-35
+            if curve_type == "bn254":
+                from py_ecc.optimized_bn128 import (G1, G2, multiply, add, curve_order, pairing,
+                                                    neg, Z1, Z2, eq)
+            else:
+                from py_ecc.optimized_bls12_381 import (G1, G2, multiply, add, curve_order, pairing,
+                                                        neg, Z1, Z2, eq)
+            self.have_py_ecc = True
+        except ImportError:
+            self.have_py_ecc = False
+            curve_order = device.FR[self._cid]
+            gx, gy = _G1[curve_type]
+            G1 = (self._codec.fq(gx), self._codec.fq(gy), self._codec.fq(1))
+            Z1 = self._codec.Z1
+            G2 = Z2 = None
+            multiply, add, neg, pairing, eq = (_needs_py_ecc(n) for n in
+                                               ("multiply", "add", "neg", "pairing", "eq"))
+        self.G1, self.G2, self.Z1, self.Z2 = G1, G2, Z1, Z2                    # kzg.py:40-49
+        self.multiply, self.add, self.neg = multiply, add, neg
+        self.pairing, self.eq = pairing, eq
+        self.curve_order = curve_order
+        self.Fq = GF(curve_order)                                              # kzg.py:52-54
+        self.R = PolynomialRing(self.Fq, "X")
+        self.X = self.R.gen()
+
+    # ------------------------------------------------------------------ helpers
+    def _coeff_limbs(self, poly):
+        """polynomial (Sage / shim / list of int-likes) -> (len, 4) uint64, trailing zeros kept out."""
+        q = self.curve_order
+        c = getattr(poly, "c", None)
+        if isinstance(c, list):                         # shim Poly: ints already
+            coeffs = c
+        else:
+            coeffs = poly.list()                        # kzg.py:110
+        if not coeffs:
+            return np.zeros((0, 4), dtype=np.uint64)
+        return ints_to_limbs(coeffs, q)
+
+    def _coerce_polys(self, polynomials):
+        out = []
+        for poly in polynomials:                        # kzg.py:92-97 / 136-141
+            out.append(self.R(poly) if isinstance(poly, list) else poly)
+        return out
+
+    def _device_srs(self, ck):
+        srs = getattr(ck, "srs", None)
+        if srs is not None and srs.handle and srs.n == len(ck):
+            return srs
+        n = len(ck)
+        aff = self._codec.to_affine_ints
+        fp = (n, aff(ck[0]) if n else None, aff(ck[n // 2]) if n else None, aff(ck[-1]) if n else None, self._cid)
+        hit = _SRS_CACHE.get(id(ck))
+        if hit is not None and hit[0] == fp and hit[1].handle:
+            return hit[1]
+        srs = device.Srs.from_affine(self._cid, self._codec.points_to_limbs(ck))
+        if len(_SRS_CACHE) >= _SRS_CACHE_MAX:
+            old = next(iter(_SRS_CACHE))
+            _SRS_CACHE.pop(old)[1].destroy()
+        _SRS_CACHE[id(ck)] = (fp, srs)
+        return srs
+
+    # ------------------------------------------------------------------ setup (kzg.py:56-78)
+    def setup(self, max_degree, tau=None):
+        """(ck, rk).  ck[i] = tau^i * G1 is computed on the device and kept resident; rk = tau*G2
+        needs py_ecc's G2 arithmetic (None without it).  `tau` may be supplied for reproducible
+        tests; by default it is drawn like the reference does (kzg.py:67)."""
+        if tau is None:
+            tau = self.Fq.random_element()
+        t = int(tau) % self.curve_order
+        srs = device.Srs.generate(self._cid, t, max_degree + 1)
+        rows = srs.read(0, max_degree + 1)
+        ck = CommitmentKey(self._codec.from_device(r, not r.any()) for r in rows)
+        ck.srs = srs
+        rk = self.multiply(self.G2, t) if self.have_py_ecc else None
+        return (ck, rk)
+
+    # ------------------------------------------------------------------ commit (kzg.py:80-120)
+    def commit(self, ck, polynomials):
+        polys = self._coerce_polys(polynomials)
+        max_degree = len(ck) - 1
+        for poly in polys:
+            if poly.degree() > max_degree:              # kzg.py:103-106, same message
+                raise ValueError(
+                    f"Polynomial degree {poly.degree()} exceeds maximum allowed degree {max_degree}"
+                )
+        if not polys:
+            return []
+        srs = self._device_srs(ck)
+        out, infs = device.msm_batch(srs, [self._coeff_limbs(p) for p in polys])
+        return [self._codec.from_device(o, f) for o, f in zip(out, infs)]
+
+    # ------------------------------------------------------------------ open (kzg.py:122-159)
+    def open(self, ck, polynomials, z, xi):
+        polys = self._coerce_polys(polynomials)
+        q = self.curve_order
+        z = self.Fq(z)
+        xi = self.Fq(xi)
+        srs = self._device_srs(ck)
+        max_degree = len(ck) - 1
+        wdeg = max((p.degree() for p in polys), default=-1) - 1
+        if wdeg > max_degree:
+            raise ValueError(f"Polynomial degree {wdeg} exceeds maximum allowed degree {max_degree}")
+        out, inf = device.open_proof(srs, [self._coeff_limbs(p) for p in polys],
+                                     int_to_limbs(z, q), int_to_limbs(xi, q))
+        return self._codec.from_device(out, inf)
+
+    # ------------------------------------------------------------------ verifier side (py_ecc)
+    def check(self, rk, commitments, z, evaluations, proof, xi):
+        """e(C - v*G1, G2) == e(proof, tau*G2 - z*G2) with C, v the xi-combinations
+        (kzg.py:161-211).  Runs on py_ecc like the reference."""
+        z = self.Fq(z)
+        xi = self.Fq(xi)
+        C = self.Z1
+        v = self.Fq(0)
+        for i, comm in enumerate(commitments):
+            C = self.add(C, self.multiply(comm, int(xi ** (i + 1))))
+        for i, e in enumerate(evaluations):
+            v += xi ** (i + 1) * self.Fq(e)
+        lhs_pt = self.add(C, self.neg(self.multiply(self.G1, int(v))))
+        rhs_g2 = self.add(rk, self.neg(self.multiply(self.G2, int(z))))
+        return self.pairing(self.G2, lhs_pt) == self.pairing(rhs_g2, proof)
+
+    def batch_check(self, rk, commitments_list, z_list, evaluations_list, proof_list, xi_list, r=None):
+        """One pairing equation for several openings (kzg.py:213-288):
+        e(sum r^i (C_i - v_i G1 + z_i pi_i), G2) == e(sum r^i pi_i, tau G2)."""
+        if r is None:
+            r = self.Fq.random_element()
+        left = self.Z1
+        right = self.Z1
+        for i, (commitments, z, evaluations, proof, xi) in enumerate(
+                zip(commitments_list, z_list, evaluations_list, proof_list, xi_list)):
+            z = self.Fq(z)
+            xi = self.Fq(xi)
+            C = self.Z1
+            v = self.Fq(0)
+            for j, comm in enumerate(commitments):
+                xp = xi ** (j + 1)
+                C = self.add(C, self.multiply(comm, int(xp)))
+                v += xp * self.Fq(evaluations[j])
+            term = self.add(C, self.neg(self.multiply(self.G1, int(v))))
+            term = self.add(term, self.multiply(proof, int(z)))
+            rp = int(r ** (i + 1))
+            left = self.add(left, self.multiply(term, rp))
+            right = self.add(right, self.multiply(proof, rp))
+        return self.pairing(self.G2, left) == self.pairing(rk, right)
