@@ -33,6 +33,7 @@ uint64_t g_next_handle = 1;
 
 struct MsmWs {
   KzScratch counts, offsets, cursor, entries, buckets, partials, winsums, blocksums, result, flag, scal;
+  KzScratch ntasks, task_off, size_hist, t_start, t_len, t_dest, tparts;
 };
 MsmWs g_ws;
 
@@ -70,46 +71,69 @@ template <class P> __device__ __forceinline__ void st_xyzz(uint32_t* buf, size_t
   for (int i = 0; i < P::N; i++) q[i] = make_uint4(d[4 * i], d[4 * i + 1], d[4 * i + 2], d[4 * i + 3]);
 }
 
-// signed digit of window w (c bits) of the 256-bit scalar s, with the running carry
-__device__ __forceinline__ int signed_digit(const uint32_t* s, uint32_t w, uint32_t c, uint32_t& carry) {
+// Signed-window recoding without a serial carry: add 2^(c-1) to every window below the top one
+// once (s' = s + OFF), then window w of s' minus 2^(c-1) is a digit in [-2^(c-1), 2^(c-1)) and
+// the top window (unsigned, it absorbs the last carry) is at most 2^(c-1) because the scalar has
+// at most c*W - 1 bits.  Each digit then depends on s' alone, so windows can be processed in
+// any order (the scatter pass below is window-major).
+struct DigitOffset { uint32_t w[8]; };
+
+__device__ __forceinline__ void load_scalar_plus_offset(const uint32_t* __restrict__ scalars, size_t i, const DigitOffset& off,
+                                                        uint32_t* s) {
+  const uint4* q = reinterpret_cast<const uint4*>(scalars + i * 8);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  uint32_t t[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  MpPrims<8>::add_cc(s, t, off.w);
+}
+
+__device__ __forceinline__ int signed_digit(const uint32_t* s, uint32_t w, uint32_t c, uint32_t W) {
   uint32_t bit = w * c;
   uint32_t word = bit >> 5, sh = bit & 31;
   uint64_t lo = word < 8 ? s[word] : 0u;
   uint64_t hi = word + 1 < 8 ? s[word + 1] : 0u;
   uint32_t raw = (uint32_t)(((lo | (hi << 32)) >> sh) & ((1ull << c) - 1));
-  uint32_t d = raw + carry;
-  if (d > (1u << (c - 1))) { carry = 1; return (int)d - (int)(1u << c); }
-  carry = 0;
-  return (int)d;
+  return w + 1 < W ? (int)raw - (int)(1u << (c - 1)) : (int)raw;
 }
 
 // ---------------------------------------------------------------- kernels
-// pass = 0: histogram;  pass = 1: scatter (cursor pre-loaded with the bucket offsets)
-template <int PASS>
-__global__ void msm_sort_kernel(const uint32_t* __restrict__ scalars, size_t n, uint32_t c, uint32_t W, uint32_t top_bits,
-                                uint32_t* __restrict__ counts_or_cursor, uint32_t* __restrict__ entries, uint32_t* __restrict__ flag) {
+// histogram of (window, |digit| - 1): one thread per scalar, L2 atomics on the 4*W*2^(c-1)-byte table
+__global__ void msm_hist_kernel(const uint32_t* __restrict__ scalars, size_t n, uint32_t c, uint32_t W, uint32_t top_bits,
+                                DigitOffset off, uint32_t* __restrict__ counts, uint32_t* __restrict__ flag) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t s[8];
-  const uint4* q = reinterpret_cast<const uint4*>(scalars + i * 8);
-  uint4 a = __ldg(q), b = __ldg(q + 1);
-  s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
-  if (PASS == 0 && top_bits < 32 && (s[7] >> top_bits)) atomicOr(flag, 1u);   // scalar >= 2^bits: not canonical
-  const uint32_t B = 1u << (c - 1);
-  uint32_t carry = 0;
-  for (uint32_t w = 0; w < W; w++) {
-    int d = signed_digit(s, w, c, carry);
-    if (d == 0) continue;
-    uint32_t neg = d < 0 ? 1u : 0u;
-    uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
-    uint32_t bucket = w * B + (mag - 1);
-    if (PASS == 0) {
-      atomicAdd(counts_or_cursor + bucket, 1u);
-    } else {
-      uint32_t pos = atomicAdd(counts_or_cursor + bucket, 1u);
-      entries[pos] = (uint32_t)i | (neg << 31);
-    }
+  load_scalar_plus_offset(scalars, i, off, s);
+  // canonical scalars only: s + OFF must stay below 2^(c*W) <=> the raw scalar has <= BITS bits
+  {
+    const uint4* q = reinterpret_cast<const uint4*>(scalars + i * 8);
+    uint32_t top = __ldg(q + 1).w;
+    if (top_bits < 32 && (top >> top_bits)) atomicOr(flag, 1u);
   }
+  const uint32_t B = 1u << (c - 1);
+  for (uint32_t w = 0; w < W; w++) {
+    int d = signed_digit(s, w, c, W);
+    if (d == 0) continue;
+    uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+    atomicAdd(counts + w * B + (mag - 1), 1u);
+  }
+}
+
+// scatter, window-major (blockIdx.y = window): all blocks in flight write into the same
+// n*4-byte slice of `entries`, which fits the 126 MB L2 up to n = 2^24, so the 4-byte stores of
+// one bucket merge into full sectors before they reach HBM.
+__global__ void msm_scatter_kernel(const uint32_t* __restrict__ scalars, size_t n, uint32_t c, uint32_t W, DigitOffset off,
+                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t w = blockIdx.y;
+  uint32_t s[8];
+  load_scalar_plus_offset(scalars, i, off, s);
+  int d = signed_digit(s, w, c, W);
+  if (d == 0) return;
+  uint32_t neg = d < 0 ? 1u : 0u;
+  uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
+  uint32_t pos = atomicAdd(cursor + w * (1u << (c - 1)) + (mag - 1), 1u);
+  entries[pos] = (uint32_t)i | (neg << 31);
 }
 
 // exclusive scan, 3 kernels: (1) per-block scan of 1024 items + block totals, (2) scan of totals,
@@ -160,27 +184,149 @@ __global__ void scan_add_kernel(uint32_t* out, const uint32_t* blocksums, size_t
   if (i >= len) return;
   uint32_t v = out[i] + blocksums[i >> 10];
   out[i] = v;
-  cursor[i] = v;
+  if (cursor) cursor[i] = v;
 }
 
-// one thread per bucket: XYZZ accumulator in registers, points gathered through the sorted index
+// ---- task construction -------------------------------------------------------------------
+// A bucket of `size` points becomes ceil(size / T) tasks of at most T points, so that no thread
+// ever walks more than T points (heavy buckets: skewed scalars, short top window).  Tasks are
+// then counting-sorted by length, longest first, so that the 32 lanes of a warp run the same
+// number of mixed additions (Poisson-distributed bucket sizes would otherwise cost ~25% in
+// divergence) and the tail of the grid is made of the shortest tasks.
+//
+// pass 1: ntasks[b] and the global histogram of task lengths
+__global__ void task_count_kernel(const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t T, uint32_t* __restrict__ ntasks,
+                                  uint32_t* __restrict__ size_hist) {
+  extern __shared__ uint32_t sh_hist[];           // T + 1 bins
+  for (uint32_t i = threadIdx.x; i <= T; i += blockDim.x) sh_hist[i] = 0;
+  __syncthreads();
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nb) {
+    uint32_t size = offsets[b + 1] - offsets[b];
+    uint32_t full = size / T, rem = size - full * T;
+    ntasks[b] = full + (rem ? 1u : 0u);
+    if (full) atomicAdd(&sh_hist[T], full);
+    if (rem) atomicAdd(&sh_hist[rem], 1u);
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i <= T; i += blockDim.x)
+    if (sh_hist[i]) atomicAdd(&size_hist[i], sh_hist[i]);
+}
+
+// size_cursor[s] = number of tasks longer than s (descending order), single block
+__global__ void task_size_scan_kernel(const uint32_t* __restrict__ size_hist, uint32_t T, uint32_t* __restrict__ size_cursor) {
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+    for (uint32_t s = T; s >= 1; s--) { size_cursor[s] = acc; acc += size_hist[s]; }
+    size_cursor[0] = acc;                          // total number of tasks
+  }
+}
+
+// pass 2: emit the tasks into their length class.  One warp per 32 buckets: each lane emits its
+// bucket's first task, the remaining tasks of multi-task buckets are emitted by the whole warp.
+__global__ void task_emit_kernel(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ ntasks,
+                                 const uint32_t* __restrict__ task_off, uint32_t nb, uint32_t T,
+                                 uint32_t* __restrict__ size_cursor, uint32_t* __restrict__ t_start, uint32_t* __restrict__ t_len,
+                                 uint32_t* __restrict__ t_dest) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t my_start = 0, my_size = 0, my_nt = 0, my_off = 0;
+  if (b < nb) { my_start = offsets[b]; my_size = offsets[b + 1] - my_start; my_nt = ntasks[b]; my_off = task_off[b]; }
+  auto emit = [&](uint32_t bucket, uint32_t bstart, uint32_t bsize, uint32_t nt, uint32_t toff, uint32_t j) {
+    uint32_t s0 = j * T;
+    uint32_t len = bsize - s0 < T ? bsize - s0 : T;
+    // warp-aggregated slot reservation: lanes emitting the same length share one atomic
+    uint32_t am = __activemask();
+    uint32_t peers = __match_any_sync(am, len);
+    int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(&size_cursor[len], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    uint32_t pos = base + __popc(peers & ((1u << lane) - 1u));
+    t_start[pos] = bstart + s0;
+    t_len[pos] = len;
+    t_dest[pos] = nt == 1 ? (bucket | 0x80000000u) : (toff + j);     // direct to the bucket, or a partial slot
+  };
+  if (my_nt) emit(b, my_start, my_size, my_nt, my_off, 0);
+  uint32_t multi = __ballot_sync(0xffffffffu, my_nt > 1);
+  while (multi) {
+    int src = __ffs(multi) - 1;
+    multi &= multi - 1;
+    uint32_t bb = __shfl_sync(0xffffffffu, b, src), bs = __shfl_sync(0xffffffffu, my_start, src);
+    uint32_t bz = __shfl_sync(0xffffffffu, my_size, src), bn = __shfl_sync(0xffffffffu, my_nt, src);
+    uint32_t bo = __shfl_sync(0xffffffffu, my_off, src);
+    for (uint32_t j = 1 + lane; j < bn; j += 32) emit(bb, bs, bz, bn, bo, j);
+  }
+}
+
+// one thread per task: XYZZ accumulator in registers, points gathered through the sorted index;
+// the next point is fetched while the current mixed addition runs
 template <class Cfg>
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __restrict__ points, size_t first,
-                                                            const uint32_t* __restrict__ offsets,
-                                                            const uint32_t* __restrict__ entries, uint32_t nbuckets,
-                                                            uint32_t* __restrict__ buckets) {
+                                                            const uint32_t* __restrict__ entries,
+                                                            const uint32_t* __restrict__ t_start, const uint32_t* __restrict__ t_len,
+                                                            const uint32_t* __restrict__ t_dest, const uint32_t* __restrict__ n_tasks,
+                                                            uint32_t* __restrict__ buckets, uint32_t* __restrict__ partials) {
   using P = typename Cfg::Fp;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nbuckets) return;
-  uint32_t start = offsets[t], end = offsets[t + 1];
+  if (t >= *n_tasks) return;
+  uint32_t e = t_start[t], len = t_len[t], dest = t_dest[t];
   XYZZ<P> acc = xyzz_inf<P>();
-  for (uint32_t e = start; e < end; e++) {
-    uint32_t ent = __ldg(entries + e);
-    Affine<P> pt = ld_affine<P>(points, first + (ent & 0x7fffffffu));
-    if (ent >> 31) pt.y = fe_neg<P>(pt.y);
+  uint32_t ent = __ldg(entries + e);
+  Affine<P> nxt = ld_affine<P>(points, first + (ent & 0x7fffffffu));
+  uint32_t nneg = ent >> 31;
+  for (uint32_t k = 0; k < len; k++) {
+    Affine<P> pt = nxt;
+    uint32_t neg = nneg;
+    if (k + 1 < len) {
+      ent = __ldg(entries + e + k + 1);
+      nxt = ld_affine<P>(points, first + (ent & 0x7fffffffu));
+      nneg = ent >> 31;
+    }
+    if (neg) pt.y = fe_neg<P>(pt.y);
     xyzz_madd<P>(acc, pt);
   }
-  st_xyzz<P>(buckets, t, acc);
+  if (dest >> 31) st_xyzz<P>(buckets, dest & 0x7fffffffu, acc);
+  else st_xyzz<P>(partials, dest, acc);
+}
+
+// buckets that were split (ntasks > 1) or are empty: fold the partial sums / write the identity.
+// One warp per 32 buckets; a bucket with more than 64 partials is folded by the whole warp
+// (strided serial sums, then a warp-shuffle tree reduction).
+template <class P> __device__ __forceinline__ XYZZ<P> shfl_xyzz(const XYZZ<P>& a, int delta) {
+  XYZZ<P> r;
+  const uint32_t* s = a.x.v;
+  uint32_t* d = r.x.v;
+#pragma unroll
+  for (int i = 0; i < 4 * P::N; i++) d[i] = __shfl_down_sync(0xffffffffu, s[i], delta);
+  return r;
+}
+template <class Cfg>
+__global__ void __launch_bounds__(128) msm_merge_kernel(const uint32_t* __restrict__ ntasks, const uint32_t* __restrict__ task_off,
+                                                       uint32_t nb, const uint32_t* __restrict__ partials, uint32_t* __restrict__ buckets) {
+  using P = typename Cfg::Fp;
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t nt = b < nb ? ntasks[b] : 1u, off = b < nb ? task_off[b] : 0u;
+  if (b < nb && nt == 0) st_xyzz<P>(buckets, b, xyzz_inf<P>());
+  if (b < nb && nt > 1 && nt <= 64) {
+    XYZZ<P> acc = ld_xyzz<P>(partials, off);
+    for (uint32_t j = 1; j < nt; j++) acc = xyzz_add<P>(acc, ld_xyzz<P>(partials, off + j));
+    st_xyzz<P>(buckets, b, acc);
+  }
+  uint32_t heavy = __ballot_sync(0xffffffffu, b < nb && nt > 64);
+  while (heavy) {
+    int src = __ffs(heavy) - 1;
+    heavy &= heavy - 1;
+    uint32_t bb = __shfl_sync(0xffffffffu, b, src), bn = __shfl_sync(0xffffffffu, nt, src), bo = __shfl_sync(0xffffffffu, off, src);
+    XYZZ<P> acc = xyzz_inf<P>();
+    for (uint32_t j = lane; j < bn; j += 32) acc = xyzz_add<P>(acc, ld_xyzz<P>(partials, bo + j));
+    for (int d = 16; d > 0; d >>= 1) {
+      XYZZ<P> o = shfl_xyzz<P>(acc, d);
+      acc = xyzz_add<P>(acc, o);
+    }
+    if (lane == 0) st_xyzz<P>(buckets, bb, acc);
+  }
 }
 
 // chunked running sum: thread (w, chunk) reduces CH consecutive buckets of window w to
@@ -375,9 +521,15 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   KZ_CUDA(cudaMemsetAsync(counts, 0, nb * 4, st));
   KZ_CUDA(cudaMemsetAsync(flag, 0, 4, st));
   const uint32_t top_bits = R::BITS - 224;       // bits allowed in the top 32-bit word
+  DigitOffset doff;
+  for (int k = 0; k < 8; k++) doff.w[k] = 0;
+  for (uint32_t w = 0; w + 1 < W; w++) {
+    uint32_t bit = w * c + (c - 1);
+    if (bit < 256) doff.w[bit >> 5] |= 1u << (bit & 31);
+  }
   KzProf prof_sort(2);
   if (n) {
-    msm_sort_kernel<0><<<(unsigned)kz_div_up(n, 256), 256, 0, st>>>(d_scalars, n, c, W, top_bits, counts, nullptr, flag);
+    msm_hist_kernel<<<(unsigned)kz_div_up(n, 256), 256, 0, st>>>(d_scalars, n, c, W, top_bits, doff, counts, flag);
     KZ_LAUNCHED();
   }
   scan_block_kernel<<<(unsigned)nblk, 256, 0, st>>>(counts, offsets, (uint32_t*)g_ws.blocksums.p, nb);
@@ -387,15 +539,52 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   scan_add_kernel<<<(unsigned)kz_div_up(nb, 256), 256, 0, st>>>(offsets, (uint32_t*)g_ws.blocksums.p, nb, cursor);
   KZ_LAUNCHED();
   if (n) {
-    msm_sort_kernel<1><<<(unsigned)kz_div_up(n, 256), 256, 0, st>>>(d_scalars, n, c, W, top_bits, cursor, entries, flag);
+    dim3 grid((unsigned)kz_div_up(n, 256), W);
+    msm_scatter_kernel<<<grid, 256, 0, st>>>(d_scalars, n, c, W, doff, cursor, entries);
     KZ_LAUNCHED();
   }
-  prof_sort.stop(5, (double)n);
-  KzProf prof_acc(0);
-  msm_accumulate_kernel<Cfg><<<(unsigned)kz_div_up(nb, 128), 128, 0, st>>>(srs.d_points, first, offsets, entries, (uint32_t)nb,
-                                                                          (uint32_t*)g_ws.buckets.p);
+  // tasks: split heavy buckets, sort by length
+  uint32_t mean = (uint32_t)(n / B) + 1;
+  uint32_t T = 32;
+  while (T < 2 * mean && T < 1024) T <<= 1;
+  const size_t max_tasks = nb + ((size_t)n * W) / T + 1;
+  if ((rc = g_ws.ntasks.ensure(nb * 4))) return rc;
+  if ((rc = g_ws.task_off.ensure((nb + 1) * 4))) return rc;
+  if ((rc = g_ws.size_hist.ensure(2 * (1024 + 1) * 4))) return rc;
+  if ((rc = g_ws.t_start.ensure(max_tasks * 4))) return rc;
+  if ((rc = g_ws.t_len.ensure(max_tasks * 4))) return rc;
+  if ((rc = g_ws.t_dest.ensure(max_tasks * 4))) return rc;
+  if ((rc = g_ws.tparts.ensure(max_tasks * 4 * P::N * 4))) return rc;
+  uint32_t* ntasks = (uint32_t*)g_ws.ntasks.p;
+  uint32_t* task_off = (uint32_t*)g_ws.task_off.p;
+  uint32_t* size_hist = (uint32_t*)g_ws.size_hist.p;
+  uint32_t* size_cursor = size_hist + (1024 + 1);
+  KZ_CUDA(cudaMemsetAsync(size_hist, 0, (1024 + 1) * 4, st));
+  task_count_kernel<<<(unsigned)kz_div_up(nb, 256), 256, (T + 1) * 4, st>>>(offsets, (uint32_t)nb, T, ntasks, size_hist);
   KZ_LAUNCHED();
-  prof_acc.stop(1, (double)n * W);
+  scan_block_kernel<<<(unsigned)nblk, 256, 0, st>>>(ntasks, task_off, (uint32_t*)g_ws.blocksums.p, nb);
+  KZ_LAUNCHED();
+  scan_sums_kernel<<<1, 256, 0, st>>>((uint32_t*)g_ws.blocksums.p, nblk, task_off + nb);
+  KZ_LAUNCHED();
+  scan_add_kernel<<<(unsigned)kz_div_up(nb, 256), 256, 0, st>>>(task_off, (uint32_t*)g_ws.blocksums.p, nb, nullptr);
+  KZ_LAUNCHED();
+  task_size_scan_kernel<<<1, 32, 0, st>>>(size_hist, T, size_cursor);
+  KZ_LAUNCHED();
+  // size_cursor[0] holds the task total and is not used as a cursor (no task has length 0)
+  task_emit_kernel<<<(unsigned)kz_div_up(nb, 256), 256, 0, st>>>(offsets, ntasks, task_off, (uint32_t)nb, T, size_cursor,
+                                                                (uint32_t*)g_ws.t_start.p, (uint32_t*)g_ws.t_len.p,
+                                                                (uint32_t*)g_ws.t_dest.p);
+  KZ_LAUNCHED();
+  prof_sort.stop(11, (double)n);
+  KzProf prof_acc(0);
+  msm_accumulate_kernel<Cfg><<<(unsigned)kz_div_up(max_tasks, 128), 128, 0, st>>>(
+      srs.d_points, first, entries, (uint32_t*)g_ws.t_start.p, (uint32_t*)g_ws.t_len.p, (uint32_t*)g_ws.t_dest.p, size_cursor,
+      (uint32_t*)g_ws.buckets.p, (uint32_t*)g_ws.tparts.p);
+  KZ_LAUNCHED();
+  msm_merge_kernel<Cfg><<<(unsigned)kz_div_up(nb, 128), 128, 0, st>>>(ntasks, task_off, (uint32_t)nb, (uint32_t*)g_ws.tparts.p,
+                                                                     (uint32_t*)g_ws.buckets.p);
+  KZ_LAUNCHED();
+  prof_acc.stop(2, (double)n * W);
   KzProf prof_red(3);
   msm_reduce_kernel<Cfg><<<(unsigned)kz_div_up((size_t)cpw * W, 128), 128, 0, st>>>((uint32_t*)g_ws.buckets.p, B, CH, cpw, W,
                                                                                    (uint32_t*)g_ws.partials.p);
@@ -506,7 +695,8 @@ void kz_msm_release() {
   for (auto& kv : g_srs) cudaFree(kv.second.d_points);
   g_srs.clear();
   KzScratch* all[] = {&g_ws.counts, &g_ws.offsets, &g_ws.cursor, &g_ws.entries, &g_ws.buckets, &g_ws.partials,
-                      &g_ws.winsums, &g_ws.blocksums, &g_ws.result, &g_ws.flag, &g_ws.scal};
+                      &g_ws.winsums, &g_ws.blocksums, &g_ws.result, &g_ws.flag, &g_ws.scal,
+                      &g_ws.ntasks, &g_ws.task_off, &g_ws.size_hist, &g_ws.t_start, &g_ws.t_len, &g_ws.t_dest, &g_ws.tparts};
   for (auto* s : all) s->release();
 }
 

@@ -41,7 +41,7 @@ def main():
             t0 = time.time(); srs = device.Srs.generate(0, tau, n); tg = time.time() - t0
             sc = random_scalars(n, R_BN, seed=logn)
             d = _ffi.DeviceBuffer(n * 32).upload(sc)
-            cs = [None] if logn < 20 else [None, logn - 6, logn - 5, logn - 3]
+            cs = [None] if logn < 24 else [None, 19, 21, 22]
             for c in cs:
                 if c is None: os.environ.pop("KZGPU_MSM_C", None)
                 else: os.environ["KZGPU_MSM_C"] = str(c)
