@@ -33,7 +33,7 @@ uint64_t g_next_handle = 1;
 
 struct MsmWs {
   KzScratch counts, offsets, cursor, entries, buckets, partials, winsums, blocksums, result, flag, scal;
-  KzScratch ntasks, task_off, size_hist, t_start, t_len, t_dest, tparts;
+  KzScratch ntasks, task_off, size_hist, t_start, t_len, t_dest, tparts, multi;
 };
 MsmWs g_ws;
 
@@ -196,7 +196,8 @@ __global__ void scan_add_kernel(uint32_t* out, const uint32_t* blocksums, size_t
 //
 // pass 1: ntasks[b] and the global histogram of task lengths
 __global__ void task_count_kernel(const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t T, uint32_t* __restrict__ ntasks,
-                                  uint32_t* __restrict__ size_hist) {
+                                  uint32_t* __restrict__ size_hist, uint32_t* __restrict__ multi_count,
+                                  uint32_t* __restrict__ multi_list) {
   extern __shared__ uint32_t sh_hist[];           // T + 1 bins
   for (uint32_t i = threadIdx.x; i <= T; i += blockDim.x) sh_hist[i] = 0;
   __syncthreads();
@@ -204,7 +205,9 @@ __global__ void task_count_kernel(const uint32_t* __restrict__ offsets, uint32_t
   if (b < nb) {
     uint32_t size = offsets[b + 1] - offsets[b];
     uint32_t full = size / T, rem = size - full * T;
-    ntasks[b] = full + (rem ? 1u : 0u);
+    uint32_t nt = full + (rem ? 1u : 0u);
+    ntasks[b] = nt;
+    if (nt > 1) multi_list[atomicAdd(multi_count, 1u)] = b;     // buckets whose partial sums need a fold
     if (full) atomicAdd(&sh_hist[T], full);
     if (rem) atomicAdd(&sh_hist[rem], 1u);
   }
@@ -290,9 +293,9 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __r
   else st_xyzz<P>(partials, dest, acc);
 }
 
-// buckets that were split (ntasks > 1) or are empty: fold the partial sums / write the identity.
-// One warp per 32 buckets; a bucket with more than 64 partials is folded by the whole warp
-// (strided serial sums, then a warp-shuffle tree reduction).
+// Buckets that were split into several tasks: fold their partial sums.  Persistent grid, one
+// warp per split bucket (from the compact list built by task_count_kernel): lanes sum strided
+// partials serially, then a warp-shuffle tree reduction combines the 32 lane sums.
 template <class P> __device__ __forceinline__ XYZZ<P> shfl_xyzz(const XYZZ<P>& a, int delta) {
   XYZZ<P> r;
   const uint32_t* s = a.x.v;
@@ -303,30 +306,33 @@ template <class P> __device__ __forceinline__ XYZZ<P> shfl_xyzz(const XYZZ<P>& a
 }
 template <class Cfg>
 __global__ void __launch_bounds__(128) msm_merge_kernel(const uint32_t* __restrict__ ntasks, const uint32_t* __restrict__ task_off,
-                                                       uint32_t nb, const uint32_t* __restrict__ partials, uint32_t* __restrict__ buckets) {
+                                                       const uint32_t* __restrict__ multi_count,
+                                                       const uint32_t* __restrict__ multi_list,
+                                                       const uint32_t* __restrict__ partials, uint32_t* __restrict__ buckets) {
   using P = typename Cfg::Fp;
   const uint32_t lane = threadIdx.x & 31;
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t nt = b < nb ? ntasks[b] : 1u, off = b < nb ? task_off[b] : 0u;
-  if (b < nb && nt == 0) st_xyzz<P>(buckets, b, xyzz_inf<P>());
-  if (b < nb && nt > 1 && nt <= 64) {
-    XYZZ<P> acc = ld_xyzz<P>(partials, off);
-    for (uint32_t j = 1; j < nt; j++) acc = xyzz_add<P>(acc, ld_xyzz<P>(partials, off + j));
-    st_xyzz<P>(buckets, b, acc);
-  }
-  uint32_t heavy = __ballot_sync(0xffffffffu, b < nb && nt > 64);
-  while (heavy) {
-    int src = __ffs(heavy) - 1;
-    heavy &= heavy - 1;
-    uint32_t bb = __shfl_sync(0xffffffffu, b, src), bn = __shfl_sync(0xffffffffu, nt, src), bo = __shfl_sync(0xffffffffu, off, src);
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t nmulti = *multi_count;
+  for (uint32_t k = warp; k < nmulti; k += nwarps) {
+    uint32_t b = multi_list[k];
+    uint32_t nt = ntasks[b], off = task_off[b];
     XYZZ<P> acc = xyzz_inf<P>();
-    for (uint32_t j = lane; j < bn; j += 32) acc = xyzz_add<P>(acc, ld_xyzz<P>(partials, bo + j));
+    for (uint32_t j = lane; j < nt; j += 32) acc = xyzz_add<P>(acc, ld_xyzz<P>(partials, off + j));
     for (int d = 16; d > 0; d >>= 1) {
       XYZZ<P> o = shfl_xyzz<P>(acc, d);
       acc = xyzz_add<P>(acc, o);
     }
-    if (lane == 0) st_xyzz<P>(buckets, bb, acc);
+    if (lane == 0) st_xyzz<P>(buckets, b, acc);
   }
+}
+
+// empty buckets hold the identity
+template <class Cfg>
+__global__ void msm_clear_empty_kernel(const uint32_t* __restrict__ ntasks, uint32_t nb, uint32_t* __restrict__ buckets) {
+  using P = typename Cfg::Fp;
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nb && ntasks[b] == 0) st_xyzz<P>(buckets, b, xyzz_inf<P>());
 }
 
 // chunked running sum: thread (w, chunk) reduces CH consecutive buckets of window w to
@@ -555,12 +561,17 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   if ((rc = g_ws.t_len.ensure(max_tasks * 4))) return rc;
   if ((rc = g_ws.t_dest.ensure(max_tasks * 4))) return rc;
   if ((rc = g_ws.tparts.ensure(max_tasks * 4 * P::N * 4))) return rc;
+  const size_t max_multi = ((size_t)n * W) / T + 1;          // a split bucket holds more than T points
+  if ((rc = g_ws.multi.ensure((max_multi + 1) * 4))) return rc;
+  uint32_t* multi_count = (uint32_t*)g_ws.multi.p;
+  uint32_t* multi_list = multi_count + 1;
+  KZ_CUDA(cudaMemsetAsync(multi_count, 0, 4, st));
   uint32_t* ntasks = (uint32_t*)g_ws.ntasks.p;
   uint32_t* task_off = (uint32_t*)g_ws.task_off.p;
   uint32_t* size_hist = (uint32_t*)g_ws.size_hist.p;
   uint32_t* size_cursor = size_hist + (1024 + 1);
   KZ_CUDA(cudaMemsetAsync(size_hist, 0, (1024 + 1) * 4, st));
-  task_count_kernel<<<(unsigned)kz_div_up(nb, 256), 256, (T + 1) * 4, st>>>(offsets, (uint32_t)nb, T, ntasks, size_hist);
+  task_count_kernel<<<(unsigned)kz_div_up(nb, 256), 256, (T + 1) * 4, st>>>(offsets, (uint32_t)nb, T, ntasks, size_hist, multi_count, multi_list);
   KZ_LAUNCHED();
   scan_block_kernel<<<(unsigned)nblk, 256, 0, st>>>(ntasks, task_off, (uint32_t*)g_ws.blocksums.p, nb);
   KZ_LAUNCHED();
@@ -581,10 +592,12 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
       srs.d_points, first, entries, (uint32_t*)g_ws.t_start.p, (uint32_t*)g_ws.t_len.p, (uint32_t*)g_ws.t_dest.p, size_cursor,
       (uint32_t*)g_ws.buckets.p, (uint32_t*)g_ws.tparts.p);
   KZ_LAUNCHED();
-  msm_merge_kernel<Cfg><<<(unsigned)kz_div_up(nb, 128), 128, 0, st>>>(ntasks, task_off, (uint32_t)nb, (uint32_t*)g_ws.tparts.p,
-                                                                     (uint32_t*)g_ws.buckets.p);
+  msm_merge_kernel<Cfg><<<cx.sm_count * 4, 128, 0, st>>>(ntasks, task_off, multi_count, multi_list, (uint32_t*)g_ws.tparts.p,
+                                                        (uint32_t*)g_ws.buckets.p);
   KZ_LAUNCHED();
-  prof_acc.stop(2, (double)n * W);
+  msm_clear_empty_kernel<Cfg><<<(unsigned)kz_div_up(nb, 256), 256, 0, st>>>(ntasks, (uint32_t)nb, (uint32_t*)g_ws.buckets.p);
+  KZ_LAUNCHED();
+  prof_acc.stop(3, (double)n * W);
   KzProf prof_red(3);
   msm_reduce_kernel<Cfg><<<(unsigned)kz_div_up((size_t)cpw * W, 128), 128, 0, st>>>((uint32_t*)g_ws.buckets.p, B, CH, cpw, W,
                                                                                    (uint32_t*)g_ws.partials.p);
@@ -696,7 +709,7 @@ void kz_msm_release() {
   g_srs.clear();
   KzScratch* all[] = {&g_ws.counts, &g_ws.offsets, &g_ws.cursor, &g_ws.entries, &g_ws.buckets, &g_ws.partials,
                       &g_ws.winsums, &g_ws.blocksums, &g_ws.result, &g_ws.flag, &g_ws.scal,
-                      &g_ws.ntasks, &g_ws.task_off, &g_ws.size_hist, &g_ws.t_start, &g_ws.t_len, &g_ws.t_dest, &g_ws.tparts};
+                      &g_ws.ntasks, &g_ws.task_off, &g_ws.size_hist, &g_ws.t_start, &g_ws.t_len, &g_ws.t_dest, &g_ws.tparts, &g_ws.multi};
   for (auto* s : all) s->release();
 }
 

@@ -38,8 +38,10 @@ struct NttPassArgs {
   uint64_t n;
   uint32_t b, logC, logK, logQ;
   uint32_t nd;
-  uint32_t d[3];
+  uint32_t dpack;         // layer widths, 2 bits each (kept out of an array: no local-memory indexing)
 };
+
+__device__ __forceinline__ uint32_t layer_width(uint32_t dpack, uint32_t s) { return (dpack >> (2 * s)) & 3u; }
 
 template <class P> __device__ __forceinline__ Fe<P> ld_fe(const uint32_t* p) {
   Fe<P> r;
@@ -131,7 +133,7 @@ __device__ __forceinline__ void ntt_layer(uint32_t* sm, const NttPassArgs& a, co
     // V = number formed by the output digits of the previous layers (first layer = least significant)
     uint32_t V = 0, hb = high, sh = done;
     for (int s = (int)li - 1; s >= 0; s--) {
-      uint32_t dd = a.d[s];
+      uint32_t dd = layer_width(a.dpack, s);
       sh -= dd;
       V |= (hb & ((1u << dd) - 1)) << sh;
       hb >>= dd;
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(NttPassArgs a, Nt
 
   uint32_t off = a.b, done = 0;
   for (uint32_t li = 0; li < a.nd; li++) {
-    uint32_t d = a.d[li];
+    uint32_t d = layer_width(a.dpack, li);
     off -= d;
     if (d == 3) ntt_layer<P, 3>(sm, a, c, li, off, done);
     else if (d == 2) ntt_layer<P, 2>(sm, a, c, li, off, done);
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(NttPassArgs a, Nt
     // X[kt] sits at the digit-reversed row
     uint32_t l = 0, ob = a.b, kr = kt;
     for (uint32_t s = 0; s < a.nd; s++) {
-      uint32_t dd = a.d[s];
+      uint32_t dd = layer_width(a.dpack, s);
       ob -= dd;
       l |= (kr & ((1u << dd) - 1)) << ob;
       kr >>= dd;
@@ -383,7 +385,8 @@ int run_plan(const NttPlan& pl, uint32_t* d_data, size_t batch) {
     NttPassArgs a;
     a.in = src; a.out = dst; a.bnd = pp.bnd; a.post = pp.post; a.wR = pp.wR;
     a.n = n; a.b = pp.b; a.logC = pp.logC; a.logK = pp.logK; a.logQ = pp.logQ; a.nd = pp.nd;
-    for (int k = 0; k < 3; k++) a.d[k] = pp.d[k];
+    a.dpack = 0;
+    for (uint32_t k = 0; k < pp.nd; k++) a.dpack |= pp.d[k] << (2 * k);
     uint32_t tile = 1u << (pp.b + pp.logC);
     uint32_t threads = tile / 8 < 32 ? 32 : (tile / 8 > (uint32_t)kThreads ? kThreads : tile / 8);
     dim3 grid((unsigned)(1ull << (pp.logQ - pp.logC)), (unsigned)batch);
