@@ -77,6 +77,11 @@ int kzgpu_srs_generate(int curve, const uint64_t* tau, size_t n, uint64_t* handl
 int kzgpu_srs_generate_range(int curve, const uint64_t* tau, size_t start, size_t n, uint64_t* handle);
 int kzgpu_srs_destroy(uint64_t handle);
 int kzgpu_srs_size(uint64_t handle, size_t* n);
+/* storage layout of a key: window bits c and table count W of the precomputed fixed-base
+ * tables T_w[i] = 2^(c w) * P_i (c = 0, W = 1: plain key), and the device bytes held.
+ * Environment: KZGPU_SRS_TABLES=0 disables the tables, KZGPU_SRS_TABLES=c=NN forces c,
+ * KZGPU_SRS_TABLE_GIB caps their size (default 35% of device memory). */
+int kzgpu_srs_info(uint64_t handle, int* c_tab, int* w_tab, size_t* device_bytes);
 /* read back `count` points starting at `first` as canonical affine limbs */
 int kzgpu_srs_read(uint64_t handle, size_t first, size_t count, uint64_t* affine_xy);
 

@@ -56,6 +56,7 @@ SIGNATURES = {
     "kzgpu_srs_generate_range": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, _u64p]),
     "kzgpu_srs_destroy": (ctypes.c_int, [ctypes.c_uint64]),
     "kzgpu_srs_size": (ctypes.c_int, [ctypes.c_uint64, _szp]),
+    "kzgpu_srs_info": (ctypes.c_int, [ctypes.c_uint64, _intp, _intp, _szp]),
     "kzgpu_srs_read": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p]),
     "kzgpu_msm": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, _intp]),
     "kzgpu_msm_dev": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, _intp]),

@@ -22,10 +22,17 @@ namespace {
 struct BN254Cfg { using Fp = FpBN254; using Fr = FrBN254; static constexpr int id = KZGPU_BN254; };
 struct BLS381Cfg { using Fp = FpBLS381; using Fr = FrBLS381; static constexpr int id = KZGPU_BLS12_381; };
 
+// The commitment key is fixed for the life of a prover, so by default it is stored as W window
+// tables T_w[i] = 2^(c*w) * P_i (w < W; T_0 is the key itself): every signed digit of every
+// scalar then lands in ONE shared set of 2^(c-1) buckets and the MSM needs neither the
+// per-window bucket sets nor the final Horner chain of c*W doublings.  Costs W x the key's
+// footprint (12 GiB for 2^24 BN254 points at c = 22) -- what the 180 GB of HBM3e is for -- and a
+// one-off build.  c_tab == 0: plain key (tables disabled or too large), per-call window choice.
 struct Srs {
   int curve;
   size_t n;
-  uint32_t* d_points;     // affine, Montgomery form, [x | y] per point
+  uint32_t* d_points;     // affine, Montgomery form, [x | y] per point; W_tab tables of n points
+  uint32_t c_tab = 0, W_tab = 1;
 };
 
 std::map<uint64_t, Srs> g_srs;
@@ -98,7 +105,7 @@ __device__ __forceinline__ int signed_digit(const uint32_t* s, uint32_t w, uint3
 // ---------------------------------------------------------------- kernels
 // histogram of (window, |digit| - 1): one thread per scalar, L2 atomics on the 4*W*2^(c-1)-byte table
 __global__ void msm_hist_kernel(const uint32_t* __restrict__ scalars, size_t n, uint32_t c, uint32_t W, uint32_t top_bits,
-                                DigitOffset off, uint32_t* __restrict__ counts, uint32_t* __restrict__ flag) {
+                                DigitOffset off, uint32_t tabled, uint32_t* __restrict__ counts, uint32_t* __restrict__ flag) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t s[8];
@@ -114,26 +121,44 @@ __global__ void msm_hist_kernel(const uint32_t* __restrict__ scalars, size_t n, 
     int d = signed_digit(s, w, c, W);
     if (d == 0) continue;
     uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-    atomicAdd(counts + w * B + (mag - 1), 1u);
+    atomicAdd(counts + (tabled ? 0u : w * B) + (mag - 1), 1u);
   }
 }
 
-// scatter, window-major (blockIdx.y = window): all blocks in flight write into the same
-// n*4-byte slice of `entries`, which fits the 126 MB L2 up to n = 2^24, so the 4-byte stores of
-// one bucket merge into full sectors before they reach HBM.
+// scatter.  Plain key: window-major (blockIdx.y = window) -- all blocks in flight write into the
+// same n*4-byte slice of `entries`, which fits the 126 MB L2 up to n = 2^24, so the 4-byte
+// stores of one bucket merge into full sectors before they reach HBM.  Tabled key: one shared
+// bucket set, so the same locality is obtained by passes over bucket ranges (blockIdx.y = pass,
+// each pass owns 2^log_range consecutive buckets).  The stored entry is the index of the point
+// to add: first + i in table w (w * n_srs + first + i), sign in bit 31.
+template <bool TABLED>
 __global__ void msm_scatter_kernel(const uint32_t* __restrict__ scalars, size_t n, uint32_t c, uint32_t W, DigitOffset off,
-                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
+                                   uint32_t first, uint32_t n_srs, uint32_t log_range, uint32_t* __restrict__ cursor,
+                                   uint32_t* __restrict__ entries) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t w = blockIdx.y;
   uint32_t s[8];
   load_scalar_plus_offset(scalars, i, off, s);
-  int d = signed_digit(s, w, c, W);
-  if (d == 0) return;
-  uint32_t neg = d < 0 ? 1u : 0u;
-  uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
-  uint32_t pos = atomicAdd(cursor + w * (1u << (c - 1)) + (mag - 1), 1u);
-  entries[pos] = (uint32_t)i | (neg << 31);
+  if (TABLED) {
+    const uint32_t pass = blockIdx.y;
+    for (uint32_t w = 0; w < W; w++) {
+      int d = signed_digit(s, w, c, W);
+      if (d == 0) continue;
+      uint32_t neg = d < 0 ? 1u : 0u;
+      uint32_t bucket = (neg ? (uint32_t)(-d) : (uint32_t)d) - 1;
+      if ((bucket >> log_range) != pass) continue;
+      uint32_t pos = atomicAdd(cursor + bucket, 1u);
+      entries[pos] = (w * n_srs + first + (uint32_t)i) | (neg << 31);
+    }
+  } else {
+    const uint32_t w = blockIdx.y;
+    int d = signed_digit(s, w, c, W);
+    if (d == 0) return;
+    uint32_t neg = d < 0 ? 1u : 0u;
+    uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
+    uint32_t pos = atomicAdd(cursor + w * (1u << (c - 1)) + (mag - 1), 1u);
+    entries[pos] = (first + (uint32_t)i) | (neg << 31);
+  }
 }
 
 // exclusive scan, 3 kernels: (1) per-block scan of 1024 items + block totals, (2) scan of totals,
@@ -265,7 +290,7 @@ __global__ void task_emit_kernel(const uint32_t* __restrict__ offsets, const uin
 // one thread per task: XYZZ accumulator in registers, points gathered through the sorted index;
 // the next point is fetched while the current mixed addition runs
 template <class Cfg>
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __restrict__ points, size_t first,
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __restrict__ points,
                                                             const uint32_t* __restrict__ entries,
                                                             const uint32_t* __restrict__ t_start, const uint32_t* __restrict__ t_len,
                                                             const uint32_t* __restrict__ t_dest, const uint32_t* __restrict__ n_tasks,
@@ -276,14 +301,14 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __r
   uint32_t e = t_start[t], len = t_len[t], dest = t_dest[t];
   XYZZ<P> acc = xyzz_inf<P>();
   uint32_t ent = __ldg(entries + e);
-  Affine<P> nxt = ld_affine<P>(points, first + (ent & 0x7fffffffu));
+  Affine<P> nxt = ld_affine<P>(points, ent & 0x7fffffffu);
   uint32_t nneg = ent >> 31;
   for (uint32_t k = 0; k < len; k++) {
     Affine<P> pt = nxt;
     uint32_t neg = nneg;
     if (k + 1 < len) {
       ent = __ldg(entries + e + k + 1);
-      nxt = ld_affine<P>(points, first + (ent & 0x7fffffffu));
+      nxt = ld_affine<P>(points, ent & 0x7fffffffu);
       nneg = ent >> 31;
     }
     if (neg) pt.y = fe_neg<P>(pt.y);
@@ -385,7 +410,8 @@ __global__ void msm_final_kernel(const uint32_t* __restrict__ winsums, uint32_t 
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   XYZZ<P> acc = xyzz_inf<P>();
   for (uint32_t w = W; w-- > 0;) {
-    for (uint32_t k = 0; k < c; k++) acc = xyzz_dbl<P>(acc);
+    if (!xyzz_is_inf<P>(acc))
+      for (uint32_t k = 0; k < c; k++) acc = xyzz_dbl<P>(acc);
     acc = xyzz_add<P>(acc, ld_xyzz<P>(winsums, w));
   }
   if (mode == 0) { st_xyzz<P>(out, 0, acc); return; }
@@ -438,6 +464,26 @@ template <class Cfg> __global__ void srs_from_mont_kernel(const uint32_t* pts, s
   for (int k = 0; k < P::N; k++) v.v[k] = pts[(2 * first + i) * P::N + k];
   v = fe_from_mont<P>(v);
   for (int k = 0; k < P::N; k++) out[i * P::N + k] = v.v[k];
+}
+
+// window table w from table w-1: T_w[i] = 2^c * T_{w-1}[i], normalised back to affine
+template <class Cfg>
+__global__ void __launch_bounds__(128) srs_table_kernel(const uint32_t* __restrict__ prev, uint32_t* __restrict__ next, size_t n,
+                                                       uint32_t c) {
+  using P = typename Cfg::Fp;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<P> a = ld_affine<P>(prev, i);
+  Affine<P> r;
+  if (aff_is_inf<P>(a)) {
+    r = a;
+  } else {
+    XYZZ<P> q = xyzz_dbl_affine<P>(a);
+    for (uint32_t k = 1; k < c; k++) q = xyzz_dbl<P>(q);
+    r = xyzz_to_affine<P>(q);
+  }
+  uint32_t* o = next + i * (2 * P::N);
+  for (int k = 0; k < P::N; k++) { o[k] = r.x.v[k]; o[P::N + k] = r.y.v[k]; }
 }
 
 // SRS generation (kzg.py:69-72): point i = tau^i * G1.  dbl_table[j] = 2^j * G1 (affine, Montgomery).
@@ -493,16 +539,47 @@ uint32_t choose_c(size_t n, int bits) {
   return (uint32_t)c0;
 }
 
+// window size of the precomputed tables for a key of n points: minimise
+//   10 * n * W(c)  (mixed additions, 10 modmul each)  +  28 * 2^(c-1)  (bucket reduction, 2 full adds per bucket)
+// subject to the memory cap and to 31-bit point indices.  Returns 0 when tables are disabled.
+uint32_t choose_table_c(size_t n, int bits, size_t point_bytes) {
+  const char* env = getenv("KZGPU_SRS_TABLES");
+  if (env && env[0] == '0') return 0;
+  if (env && env[0] == 'c' && env[1] == '=') {
+    int v = atoi(env + 2);
+    if (v >= 2 && v <= 24) return (uint32_t)v;
+  }
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  double cap = 0.35 * (double)total_b;
+  const char* cap_env = getenv("KZGPU_SRS_TABLE_GIB");
+  if (cap_env) cap = atof(cap_env) * 1073741824.0;
+  if ((double)free_b * 0.6 < cap) cap = (double)free_b * 0.6;
+  double best = 1e300;
+  uint32_t best_c = 0;
+  for (uint32_t c = 2; c <= 24; c++) {
+    uint32_t W = (bits + 1 + c - 1) / c;
+    double mem = (double)W * (double)n * (double)point_bytes;
+    if (mem > cap || (double)W * (double)n >= 2147483648.0) continue;
+    double cost = 10.0 * (double)(n ? n : 1) * W + 28.0 * (double)(1ull << (c - 1));
+    if (cost < best) { best = cost; best_c = c; }
+  }
+  return best_c;
+}
+
 template <class Cfg>
 int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, int mode, uint32_t* d_out) {
   using P = typename Cfg::Fp;
   using R = typename Cfg::Fr;
   KzgpuCtx& cx = kz_ctx();
   cudaStream_t st = cx.stream;
-  const uint32_t c = choose_c(n, R::BITS);
-  const uint32_t W = (R::BITS + 1 + c - 1) / c;
+  const bool tabled = srs.c_tab != 0;
+  const uint32_t c = tabled ? srs.c_tab : choose_c(n, R::BITS);
+  const uint32_t W = (R::BITS + 1 + c - 1) / c;          // digits per scalar
+  const uint32_t Wb = tabled ? 1u : W;                   // bucket sets
   const uint32_t B = 1u << (c - 1);
-  const size_t nb = (size_t)W * B;
+  const size_t nb = (size_t)Wb * B;
+  if (first + n > 0x7fffffffull) return kz_fail(KZGPU_EINVAL, "MSM index range exceeds 2^31");
   int rc;
   if ((rc = g_ws.counts.ensure(nb * 4))) return rc;
   if ((rc = g_ws.offsets.ensure((nb + 1) * 4))) return rc;
@@ -515,8 +592,8 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   uint32_t CH = 64;
   if (CH > B) CH = B;
   const uint32_t cpw = (B + CH - 1) / CH;
-  if ((rc = g_ws.partials.ensure((size_t)cpw * W * 4 * P::N * 4))) return rc;
-  if ((rc = g_ws.winsums.ensure((size_t)W * 4 * P::N * 4))) return rc;
+  if ((rc = g_ws.partials.ensure((size_t)cpw * Wb * 4 * P::N * 4))) return rc;
+  if ((rc = g_ws.winsums.ensure((size_t)Wb * 4 * P::N * 4))) return rc;
 
   uint32_t* counts = (uint32_t*)g_ws.counts.p;
   uint32_t* offsets = (uint32_t*)g_ws.offsets.p;
@@ -535,7 +612,7 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   }
   KzProf prof_sort(2);
   if (n) {
-    msm_hist_kernel<<<(unsigned)kz_div_up(n, 256), 256, 0, st>>>(d_scalars, n, c, W, top_bits, doff, counts, flag);
+    msm_hist_kernel<<<(unsigned)kz_div_up(n, 256), 256, 0, st>>>(d_scalars, n, c, W, top_bits, doff, tabled ? 1u : 0u, counts, flag);
     KZ_LAUNCHED();
   }
   scan_block_kernel<<<(unsigned)nblk, 256, 0, st>>>(counts, offsets, (uint32_t*)g_ws.blocksums.p, nb);
@@ -545,12 +622,21 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   scan_add_kernel<<<(unsigned)kz_div_up(nb, 256), 256, 0, st>>>(offsets, (uint32_t*)g_ws.blocksums.p, nb, cursor);
   KZ_LAUNCHED();
   if (n) {
-    dim3 grid((unsigned)kz_div_up(n, 256), W);
-    msm_scatter_kernel<<<grid, 256, 0, st>>>(d_scalars, n, c, W, doff, cursor, entries);
+    if (tabled) {
+      // passes over bucket ranges so that the slice of `entries` being written stays L2-resident (~64 MB)
+      uint32_t log_passes = 0;
+      while (((size_t)n * W * 4) >> log_passes > (64u << 20) && log_passes < c - 1 && log_passes < 6) log_passes++;
+      dim3 grid((unsigned)kz_div_up(n, 256), 1u << log_passes);
+      msm_scatter_kernel<true><<<grid, 256, 0, st>>>(d_scalars, n, c, W, doff, (uint32_t)first, (uint32_t)srs.n, (c - 1) - log_passes,
+                                                     cursor, entries);
+    } else {
+      dim3 grid((unsigned)kz_div_up(n, 256), W);
+      msm_scatter_kernel<false><<<grid, 256, 0, st>>>(d_scalars, n, c, W, doff, (uint32_t)first, (uint32_t)srs.n, 0, cursor, entries);
+    }
     KZ_LAUNCHED();
   }
   // tasks: split heavy buckets, sort by length
-  uint32_t mean = (uint32_t)(n / B) + 1;
+  uint32_t mean = (uint32_t)(((size_t)n * (tabled ? W : 1u)) / B) + 1;
   uint32_t T = 32;
   while (T < 2 * mean && T < 1024) T <<= 1;
   const size_t max_tasks = nb + ((size_t)n * W) / T + 1;
@@ -589,7 +675,7 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   prof_sort.stop(11, (double)n);
   KzProf prof_acc(0);
   msm_accumulate_kernel<Cfg><<<(unsigned)kz_div_up(max_tasks, 128), 128, 0, st>>>(
-      srs.d_points, first, entries, (uint32_t*)g_ws.t_start.p, (uint32_t*)g_ws.t_len.p, (uint32_t*)g_ws.t_dest.p, size_cursor,
+      srs.d_points, entries, (uint32_t*)g_ws.t_start.p, (uint32_t*)g_ws.t_len.p, (uint32_t*)g_ws.t_dest.p, size_cursor,
       (uint32_t*)g_ws.buckets.p, (uint32_t*)g_ws.tparts.p);
   KZ_LAUNCHED();
   msm_merge_kernel<Cfg><<<cx.sm_count * 4, 128, 0, st>>>(ntasks, task_off, multi_count, multi_list, (uint32_t*)g_ws.tparts.p,
@@ -599,12 +685,12 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   KZ_LAUNCHED();
   prof_acc.stop(3, (double)n * W);
   KzProf prof_red(3);
-  msm_reduce_kernel<Cfg><<<(unsigned)kz_div_up((size_t)cpw * W, 128), 128, 0, st>>>((uint32_t*)g_ws.buckets.p, B, CH, cpw, W,
-                                                                                   (uint32_t*)g_ws.partials.p);
+  msm_reduce_kernel<Cfg><<<(unsigned)kz_div_up((size_t)cpw * Wb, 128), 128, 0, st>>>((uint32_t*)g_ws.buckets.p, B, CH, cpw, Wb,
+                                                                                    (uint32_t*)g_ws.partials.p);
   KZ_LAUNCHED();
-  msm_window_kernel<Cfg><<<W, 128, 128 * 4 * P::N * 4, st>>>((uint32_t*)g_ws.partials.p, cpw, (uint32_t*)g_ws.winsums.p);
+  msm_window_kernel<Cfg><<<Wb, 128, 128 * 4 * P::N * 4, st>>>((uint32_t*)g_ws.partials.p, cpw, (uint32_t*)g_ws.winsums.p);
   KZ_LAUNCHED();
-  msm_final_kernel<Cfg><<<1, 32, 0, st>>>((uint32_t*)g_ws.winsums.p, W, c, mode, d_out);
+  msm_final_kernel<Cfg><<<1, 32, 0, st>>>((uint32_t*)g_ws.winsums.p, Wb, c, mode, d_out);
   KZ_LAUNCHED();
   prof_red.stop(3, (double)nb);
   uint32_t hflag = 0;
@@ -641,18 +727,54 @@ const Srs* find_srs(uint64_t handle) {
   return it == g_srs.end() ? nullptr : &it->second;
 }
 
+// allocate the key (W tables when enabled); build_tables() fills tables 1..W-1 from table 0
+template <class Cfg>
+int srs_alloc(Srs& s, size_t n) {
+  using P = typename Cfg::Fp;
+  using R = typename Cfg::Fr;
+  s.curve = Cfg::id; s.n = n; s.d_points = nullptr;
+  const size_t pt_bytes = 2 * P::N * 4;
+  s.c_tab = n ? choose_table_c(n, R::BITS, pt_bytes) : 0;
+  s.W_tab = s.c_tab ? (R::BITS + 1 + s.c_tab - 1) / s.c_tab : 1;
+  size_t bytes = n * pt_bytes * s.W_tab;
+  cudaError_t e = cudaMalloc((void**)&s.d_points, bytes ? bytes : 16);
+  if (e != cudaSuccess && s.c_tab) {          // not enough memory for the tables: plain key
+    cudaGetLastError();
+    s.c_tab = 0; s.W_tab = 1;
+    bytes = n * pt_bytes;
+    e = cudaMalloc((void**)&s.d_points, bytes ? bytes : 16);
+  }
+  if (e != cudaSuccess) return kz_fail(KZGPU_ECUDA, "cudaMalloc(%zu) for the SRS failed: %s", bytes, cudaGetErrorString(e));
+  return 0;
+}
+
+template <class Cfg>
+int srs_build_tables(Srs& s) {
+  using P = typename Cfg::Fp;
+  KzgpuCtx& cx = kz_ctx();
+  const size_t stride = s.n * 2 * P::N;
+  for (uint32_t w = 1; w < s.W_tab && s.c_tab; w++) {
+    srs_table_kernel<Cfg><<<(unsigned)kz_div_up(s.n, 128), 128, 0, cx.stream>>>(s.d_points + (w - 1) * stride, s.d_points + w * stride,
+                                                                              s.n, s.c_tab);
+    KZ_LAUNCHED();
+  }
+  return 0;
+}
+
 template <class Cfg>
 int srs_create_impl(const uint64_t* affine_xy, size_t n, uint64_t* handle) {
   using P = typename Cfg::Fp;
   KzgpuCtx& cx = kz_ctx();
   Srs s;
-  s.curve = Cfg::id; s.n = n; s.d_points = nullptr;
+  int rc0 = srs_alloc<Cfg>(s, n);
+  if (rc0) return rc0;
   size_t bytes = n * 2 * P::N * 4;
-  KZ_CUDA(cudaMalloc((void**)&s.d_points, bytes ? bytes : 16));
   if (n) {
     KZ_CUDA(cudaMemcpyAsync(s.d_points, affine_xy, bytes, cudaMemcpyHostToDevice, cx.stream));
     srs_to_mont_kernel<Cfg><<<(unsigned)kz_div_up(2 * n, 128), 128, 0, cx.stream>>>(s.d_points, n);
     KZ_LAUNCHED();
+    int rc1 = srs_build_tables<Cfg>(s);
+    if (rc1) return rc1;
     KZ_CUDA(cudaStreamSynchronize(cx.stream));
   }
   *handle = g_next_handle++;
@@ -680,12 +802,13 @@ int srs_generate_impl(const uint64_t* tau, size_t start, size_t n, uint64_t* han
   KZ_CUDA(cudaMalloc((void**)&d_table, table.size() * 4));
   KZ_CUDA(cudaMemcpyAsync(d_table, table.data(), table.size() * 4, cudaMemcpyHostToDevice, cx.stream));
   Srs s;
-  s.curve = Cfg::id; s.n = n; s.d_points = nullptr;
-  size_t bytes = n * 2 * P::N * 4;
-  KZ_CUDA(cudaMalloc((void**)&s.d_points, bytes ? bytes : 16));
+  int rc0 = srs_alloc<Cfg>(s, n);
+  if (rc0) return rc0;
   if (n) {
     srs_generate_kernel<Cfg><<<(unsigned)kz_div_up(n, 128), 128, 0, cx.stream>>>(s.d_points, start, n, fe_to_mont<R>(t), d_table);
     KZ_LAUNCHED();
+    int rc1 = srs_build_tables<Cfg>(s);
+    if (rc1) return rc1;
   }
   KZ_CUDA(cudaStreamSynchronize(cx.stream));
   cudaFree(d_table);
@@ -766,6 +889,16 @@ int kzgpu_srs_size(uint64_t handle, size_t* n) {
   const Srs* s = find_srs(handle);
   if (!s || !n) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle");
   *n = s->n;
+  return 0;
+}
+
+int kzgpu_srs_info(uint64_t handle, int* c_tab, int* w_tab, size_t* device_bytes) {
+  KZ_REQUIRE_INIT();
+  const Srs* s = find_srs(handle);
+  if (!s) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle");
+  if (c_tab) *c_tab = (int)s->c_tab;
+  if (w_tab) *w_tab = (int)s->W_tab;
+  if (device_bytes) *device_bytes = s->n * (s->curve == KZGPU_BN254 ? 64 : 96) * s->W_tab;
   return 0;
 }
 

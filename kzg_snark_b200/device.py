@@ -90,6 +90,12 @@ class Srs:
         check(lib.kzgpu_srs_generate_range(cid, ptr(t), start, n, ctypes.byref(h)))
         return cls(cid, h.value, n)
 
+    def info(self):
+        """{'c': window bits of the fixed-base tables (0 = plain key), 'tables': W, 'bytes': device footprint}"""
+        c, w, b = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_size_t(0)
+        check(_ffi.load_library().kzgpu_srs_info(self.handle, ctypes.byref(c), ctypes.byref(w), ctypes.byref(b)))
+        return {"c": c.value, "tables": w.value, "bytes": b.value}
+
     def read(self, first, count):
         out = np.zeros((count, 2 * FP_LIMBS[self.curve]), dtype=np.uint64)
         check(_ffi.load_library().kzgpu_srs_read(self.handle, first, count, ptr(out)))

@@ -189,6 +189,32 @@ def test_msm_edge_points(dev, curve):
     srs.destroy()
 
 
+@pytest.mark.parametrize("mode", ["0", "c=5", "c=11"])
+def test_msm_key_layouts_agree(dev, mode, monkeypatch):
+    """Plain key (per-call windows + Horner) and fixed-base window tables give the same point."""
+    cv = get_curve("bn254"); k = KZGOracle("bn254")
+    rng = random.Random(17)
+    tau = rng.randrange(1, cv.r)
+    n = 300
+    ck = k.setup_fast(n - 1, tau)
+    monkeypatch.setenv("KZGPU_SRS_TABLES", mode)
+    srs = dev.Srs.from_affine("bn254", affine_arr(cv, ck, 4))
+    info = srs.info()
+    assert (info["c"] == 0 and info["tables"] == 1) if mode == "0" else info["c"] == int(mode[2:])
+    for coeffs in ([rng.randrange(cv.r) for _ in range(n)], [1] * n, [cv.r - 1] * n, [0] * n,
+                   [rng.randrange(1 << 16) for _ in range(n)], [rng.randrange(cv.r) for _ in range(7)]):
+        out, inf = dev.msm(srs, L(coeffs, cv.r))
+        exp = cv.normalize(cv.multiply(cv.G1, poly_eval(coeffs, tau, cv.r)))
+        assert point_of(cv, out, inf, 4) == exp
+    # offset into the key (first > 0): sum_i s_i * ck[first + i]
+    out, inf = dev.msm(srs, L([3, 5, 7], cv.r), first=10)
+    acc = cv.Z1
+    for j, s_ in enumerate([3, 5, 7]):
+        acc = cv.add(acc, cv.multiply(ck[10 + j], s_))
+    assert point_of(cv, out, inf, 4) == cv.normalize(acc)
+    srs.destroy()
+
+
 def test_msm_degree_check(dev):
     cv = get_curve("bn254")
     srs = dev.Srs.from_affine("bn254", affine_arr(cv, [cv.G1] * 4, 4))
