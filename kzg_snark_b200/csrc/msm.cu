@@ -121,41 +121,33 @@ __global__ void msm_hist_kernel(const uint32_t* __restrict__ scalars, size_t n, 
     int d = signed_digit(s, w, c, W);
     if (d == 0) continue;
     uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-    atomicAdd(counts + (tabled ? 0u : w * B) + (mag - 1), 1u);
+    atomicAdd(counts + (tabled ? (mag - 1) * W + w : w * B + (mag - 1)), 1u);
   }
 }
 
-// scatter.  Plain key: window-major (blockIdx.y = window) -- all blocks in flight write into the
-// same n*4-byte slice of `entries`, which fits the 126 MB L2 up to n = 2^24, so the 4-byte
-// stores of one bucket merge into full sectors before they reach HBM.  Tabled key: one shared
-// bucket set, so the same locality is obtained by passes over bucket ranges (blockIdx.y = pass,
-// each pass owns 2^log_range consecutive buckets).  The stored entry is the index of the point
-// to add: first + i in table w (w * n_srs + first + i), sign in bit 31.
+// scatter, window-major (blockIdx.y = window).  The counting sort keeps one sub-list per
+// (bucket, window): plain key -> key w*B + b (each window has its own bucket set); tabled key ->
+// key b*W + w, so the W sub-lists of a bucket are adjacent and form ONE list of the shared
+// bucket.  Either way the blocks in flight work on one window, whose writes touch about one
+// 32-byte sector per sub-list (<= 64 MB in total at 2^24), so the 4-byte stores merge in the
+// 126 MB L2 into full sectors before they reach HBM.  The stored entry is the index of the
+// point to add (tabled: w * n_srs + first + i, in table w), sign in bit 31.
 template <bool TABLED>
 __global__ void msm_scatter_kernel(const uint32_t* __restrict__ scalars, size_t n, uint32_t c, uint32_t W, DigitOffset off,
-                                   uint32_t first, uint32_t n_srs, uint32_t log_range, uint32_t* __restrict__ cursor,
-                                   uint32_t* __restrict__ entries) {
+                                   uint32_t first, uint32_t n_srs, uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t s[8];
   load_scalar_plus_offset(scalars, i, off, s);
+  const uint32_t w = blockIdx.y;
+  int d = signed_digit(s, w, c, W);
+  if (d == 0) return;
+  uint32_t neg = d < 0 ? 1u : 0u;
+  uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
   if (TABLED) {
-    const uint32_t pass = blockIdx.y;
-    for (uint32_t w = 0; w < W; w++) {
-      int d = signed_digit(s, w, c, W);
-      if (d == 0) continue;
-      uint32_t neg = d < 0 ? 1u : 0u;
-      uint32_t bucket = (neg ? (uint32_t)(-d) : (uint32_t)d) - 1;
-      if ((bucket >> log_range) != pass) continue;
-      uint32_t pos = atomicAdd(cursor + bucket, 1u);
-      entries[pos] = (w * n_srs + first + (uint32_t)i) | (neg << 31);
-    }
+    uint32_t pos = atomicAdd(cursor + (mag - 1) * W + w, 1u);
+    entries[pos] = (w * n_srs + first + (uint32_t)i) | (neg << 31);
   } else {
-    const uint32_t w = blockIdx.y;
-    int d = signed_digit(s, w, c, W);
-    if (d == 0) return;
-    uint32_t neg = d < 0 ? 1u : 0u;
-    uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
     uint32_t pos = atomicAdd(cursor + w * (1u << (c - 1)) + (mag - 1), 1u);
     entries[pos] = (first + (uint32_t)i) | (neg << 31);
   }
@@ -220,7 +212,8 @@ __global__ void scan_add_kernel(uint32_t* out, const uint32_t* blocksums, size_t
 // divergence) and the tail of the grid is made of the shortest tasks.
 //
 // pass 1: ntasks[b] and the global histogram of task lengths
-__global__ void task_count_kernel(const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t T, uint32_t* __restrict__ ntasks,
+__global__ void task_count_kernel(const uint32_t* __restrict__ offsets, uint32_t ostride, uint32_t nb, uint32_t T,
+                                  uint32_t* __restrict__ ntasks,
                                   uint32_t* __restrict__ size_hist, uint32_t* __restrict__ multi_count,
                                   uint32_t* __restrict__ multi_list) {
   extern __shared__ uint32_t sh_hist[];           // T + 1 bins
@@ -228,7 +221,7 @@ __global__ void task_count_kernel(const uint32_t* __restrict__ offsets, uint32_t
   __syncthreads();
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < nb) {
-    uint32_t size = offsets[b + 1] - offsets[b];
+    uint32_t size = offsets[(size_t)(b + 1) * ostride] - offsets[(size_t)b * ostride];
     uint32_t full = size / T, rem = size - full * T;
     uint32_t nt = full + (rem ? 1u : 0u);
     ntasks[b] = nt;
@@ -252,14 +245,17 @@ __global__ void task_size_scan_kernel(const uint32_t* __restrict__ size_hist, ui
 
 // pass 2: emit the tasks into their length class.  One warp per 32 buckets: each lane emits its
 // bucket's first task, the remaining tasks of multi-task buckets are emitted by the whole warp.
-__global__ void task_emit_kernel(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ ntasks,
+__global__ void task_emit_kernel(const uint32_t* __restrict__ offsets, uint32_t ostride, const uint32_t* __restrict__ ntasks,
                                  const uint32_t* __restrict__ task_off, uint32_t nb, uint32_t T,
                                  uint32_t* __restrict__ size_cursor, uint32_t* __restrict__ t_start, uint32_t* __restrict__ t_len,
                                  uint32_t* __restrict__ t_dest) {
   const uint32_t lane = threadIdx.x & 31;
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t my_start = 0, my_size = 0, my_nt = 0, my_off = 0;
-  if (b < nb) { my_start = offsets[b]; my_size = offsets[b + 1] - my_start; my_nt = ntasks[b]; my_off = task_off[b]; }
+  if (b < nb) {
+    my_start = offsets[(size_t)b * ostride]; my_size = offsets[(size_t)(b + 1) * ostride] - my_start;
+    my_nt = ntasks[b]; my_off = task_off[b];
+  }
   auto emit = [&](uint32_t bucket, uint32_t bstart, uint32_t bsize, uint32_t nt, uint32_t toff, uint32_t j) {
     uint32_t s0 = j * T;
     uint32_t len = bsize - s0 < T ? bsize - s0 : T;
@@ -380,16 +376,17 @@ __global__ void __launch_bounds__(128) msm_reduce_kernel(const uint32_t* __restr
   st_xyzz<P>(partials, t, acc);
 }
 
-// block per window: sum the window's chunk partials (strided serial + shared-memory tree)
+// one level of the per-window tree sum: block (bx, w) adds `per_block` consecutive points of
+// window w (strided serial sums, then a shared-memory tree) into out[w * gridDim.x + bx]
 template <class Cfg>
-__global__ void __launch_bounds__(128) msm_window_kernel(const uint32_t* __restrict__ partials, uint32_t chunks_per_window,
-                                                        uint32_t* __restrict__ winsums) {
+__global__ void __launch_bounds__(128) msm_window_kernel(const uint32_t* __restrict__ in, uint32_t count, uint32_t per_block,
+                                                        uint32_t* __restrict__ out) {
   using P = typename Cfg::Fp;
   extern __shared__ uint32_t shw[];
-  uint32_t w = blockIdx.x;
+  const uint32_t w = blockIdx.y;
+  const uint32_t lo = blockIdx.x * per_block, hi = lo + per_block < count ? lo + per_block : count;
   XYZZ<P> acc = xyzz_inf<P>();
-  for (uint32_t ch = threadIdx.x; ch < chunks_per_window; ch += blockDim.x)
-    acc = xyzz_add<P>(acc, ld_xyzz<P>(partials, (size_t)w * chunks_per_window + ch));
+  for (uint32_t k = lo + threadIdx.x; k < hi; k += blockDim.x) acc = xyzz_add<P>(acc, ld_xyzz<P>(in, (size_t)w * count + k));
   st_xyzz<P>(shw, threadIdx.x, acc);
   __syncthreads();
   for (uint32_t off = blockDim.x / 2; off > 0; off >>= 1) {
@@ -399,7 +396,7 @@ __global__ void __launch_bounds__(128) msm_window_kernel(const uint32_t* __restr
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) st_xyzz<P>(winsums, w, ld_xyzz<P>(shw, 0));
+  if (threadIdx.x == 0) st_xyzz<P>(out, (size_t)w * gridDim.x + blockIdx.x, ld_xyzz<P>(shw, 0));
 }
 
 // Horner over windows (top first), optional normalisation.
@@ -578,22 +575,25 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   const uint32_t W = (R::BITS + 1 + c - 1) / c;          // digits per scalar
   const uint32_t Wb = tabled ? 1u : W;                   // bucket sets
   const uint32_t B = 1u << (c - 1);
-  const size_t nb = (size_t)Wb * B;
+  const size_t nb = (size_t)Wb * B;                     // buckets
+  const size_t ns = (size_t)W * B;                      // sort keys: one sub-list per (bucket, window)
+  const uint32_t ostride = tabled ? W : 1u;             // offsets[] entries per bucket
   if (first + n > 0x7fffffffull) return kz_fail(KZGPU_EINVAL, "MSM index range exceeds 2^31");
   int rc;
-  if ((rc = g_ws.counts.ensure(nb * 4))) return rc;
-  if ((rc = g_ws.offsets.ensure((nb + 1) * 4))) return rc;
-  if ((rc = g_ws.cursor.ensure(nb * 4))) return rc;
+  if ((rc = g_ws.counts.ensure(ns * 4))) return rc;
+  if ((rc = g_ws.offsets.ensure((ns + 1) * 4))) return rc;
+  if ((rc = g_ws.cursor.ensure(ns * 4))) return rc;
   if ((rc = g_ws.entries.ensure((size_t)n * W * 4 + 4))) return rc;
   if ((rc = g_ws.buckets.ensure(nb * 4 * P::N * 4))) return rc;
   if ((rc = g_ws.flag.ensure(4))) return rc;
-  const size_t nblk = kz_div_up(nb, 1024);
-  if ((rc = g_ws.blocksums.ensure(nblk * 4))) return rc;
+  const size_t nblk_s = kz_div_up(ns, 1024), nblk = kz_div_up(nb, 1024);
+  if ((rc = g_ws.blocksums.ensure(nblk_s * 4))) return rc;
   uint32_t CH = 64;
   if (CH > B) CH = B;
   const uint32_t cpw = (B + CH - 1) / CH;
   if ((rc = g_ws.partials.ensure((size_t)cpw * Wb * 4 * P::N * 4))) return rc;
-  if ((rc = g_ws.winsums.ensure((size_t)Wb * 4 * P::N * 4))) return rc;
+  const size_t lvl1 = kz_div_up(cpw, 1024);
+  if ((rc = g_ws.winsums.ensure(2 * (size_t)Wb * (lvl1 + 1) * 4 * P::N * 4))) return rc;
 
   uint32_t* counts = (uint32_t*)g_ws.counts.p;
   uint32_t* offsets = (uint32_t*)g_ws.offsets.p;
@@ -601,7 +601,7 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   uint32_t* entries = (uint32_t*)g_ws.entries.p;
   uint32_t* flag = (uint32_t*)g_ws.flag.p;
 
-  KZ_CUDA(cudaMemsetAsync(counts, 0, nb * 4, st));
+  KZ_CUDA(cudaMemsetAsync(counts, 0, ns * 4, st));
   KZ_CUDA(cudaMemsetAsync(flag, 0, 4, st));
   const uint32_t top_bits = R::BITS - 224;       // bits allowed in the top 32-bit word
   DigitOffset doff;
@@ -615,24 +615,18 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
     msm_hist_kernel<<<(unsigned)kz_div_up(n, 256), 256, 0, st>>>(d_scalars, n, c, W, top_bits, doff, tabled ? 1u : 0u, counts, flag);
     KZ_LAUNCHED();
   }
-  scan_block_kernel<<<(unsigned)nblk, 256, 0, st>>>(counts, offsets, (uint32_t*)g_ws.blocksums.p, nb);
+  scan_block_kernel<<<(unsigned)nblk_s, 256, 0, st>>>(counts, offsets, (uint32_t*)g_ws.blocksums.p, ns);
   KZ_LAUNCHED();
-  scan_sums_kernel<<<1, 256, 0, st>>>((uint32_t*)g_ws.blocksums.p, nblk, offsets + nb);
+  scan_sums_kernel<<<1, 256, 0, st>>>((uint32_t*)g_ws.blocksums.p, nblk_s, offsets + ns);
   KZ_LAUNCHED();
-  scan_add_kernel<<<(unsigned)kz_div_up(nb, 256), 256, 0, st>>>(offsets, (uint32_t*)g_ws.blocksums.p, nb, cursor);
+  scan_add_kernel<<<(unsigned)kz_div_up(ns, 256), 256, 0, st>>>(offsets, (uint32_t*)g_ws.blocksums.p, ns, cursor);
   KZ_LAUNCHED();
   if (n) {
-    if (tabled) {
-      // passes over bucket ranges so that the slice of `entries` being written stays L2-resident (~64 MB)
-      uint32_t log_passes = 0;
-      while (((size_t)n * W * 4) >> log_passes > (64u << 20) && log_passes < c - 1 && log_passes < 6) log_passes++;
-      dim3 grid((unsigned)kz_div_up(n, 256), 1u << log_passes);
-      msm_scatter_kernel<true><<<grid, 256, 0, st>>>(d_scalars, n, c, W, doff, (uint32_t)first, (uint32_t)srs.n, (c - 1) - log_passes,
-                                                     cursor, entries);
-    } else {
-      dim3 grid((unsigned)kz_div_up(n, 256), W);
-      msm_scatter_kernel<false><<<grid, 256, 0, st>>>(d_scalars, n, c, W, doff, (uint32_t)first, (uint32_t)srs.n, 0, cursor, entries);
-    }
+    dim3 grid((unsigned)kz_div_up(n, 256), W);
+    if (tabled)
+      msm_scatter_kernel<true><<<grid, 256, 0, st>>>(d_scalars, n, c, W, doff, (uint32_t)first, (uint32_t)srs.n, cursor, entries);
+    else
+      msm_scatter_kernel<false><<<grid, 256, 0, st>>>(d_scalars, n, c, W, doff, (uint32_t)first, (uint32_t)srs.n, cursor, entries);
     KZ_LAUNCHED();
   }
   // tasks: split heavy buckets, sort by length
@@ -657,7 +651,7 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   uint32_t* size_hist = (uint32_t*)g_ws.size_hist.p;
   uint32_t* size_cursor = size_hist + (1024 + 1);
   KZ_CUDA(cudaMemsetAsync(size_hist, 0, (1024 + 1) * 4, st));
-  task_count_kernel<<<(unsigned)kz_div_up(nb, 256), 256, (T + 1) * 4, st>>>(offsets, (uint32_t)nb, T, ntasks, size_hist, multi_count, multi_list);
+  task_count_kernel<<<(unsigned)kz_div_up(nb, 256), 256, (T + 1) * 4, st>>>(offsets, ostride, (uint32_t)nb, T, ntasks, size_hist, multi_count, multi_list);
   KZ_LAUNCHED();
   scan_block_kernel<<<(unsigned)nblk, 256, 0, st>>>(ntasks, task_off, (uint32_t*)g_ws.blocksums.p, nb);
   KZ_LAUNCHED();
@@ -668,7 +662,7 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   task_size_scan_kernel<<<1, 32, 0, st>>>(size_hist, T, size_cursor);
   KZ_LAUNCHED();
   // size_cursor[0] holds the task total and is not used as a cursor (no task has length 0)
-  task_emit_kernel<<<(unsigned)kz_div_up(nb, 256), 256, 0, st>>>(offsets, ntasks, task_off, (uint32_t)nb, T, size_cursor,
+  task_emit_kernel<<<(unsigned)kz_div_up(nb, 256), 256, 0, st>>>(offsets, ostride, ntasks, task_off, (uint32_t)nb, T, size_cursor,
                                                                 (uint32_t*)g_ws.t_start.p, (uint32_t*)g_ws.t_len.p,
                                                                 (uint32_t*)g_ws.t_dest.p);
   KZ_LAUNCHED();
@@ -688,9 +682,18 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   msm_reduce_kernel<Cfg><<<(unsigned)kz_div_up((size_t)cpw * Wb, 128), 128, 0, st>>>((uint32_t*)g_ws.buckets.p, B, CH, cpw, Wb,
                                                                                     (uint32_t*)g_ws.partials.p);
   KZ_LAUNCHED();
-  msm_window_kernel<Cfg><<<Wb, 128, 128 * 4 * P::N * 4, st>>>((uint32_t*)g_ws.partials.p, cpw, (uint32_t*)g_ws.winsums.p);
-  KZ_LAUNCHED();
-  msm_final_kernel<Cfg><<<1, 32, 0, st>>>((uint32_t*)g_ws.winsums.p, Wb, c, mode, d_out);
+  // tree sum of the chunk partials of each window, 1024 per block and level
+  const uint32_t* lvl_in = (const uint32_t*)g_ws.partials.p;
+  uint32_t count = cpw, lvl_launches = 0;
+  uint32_t* pong[2] = {(uint32_t*)g_ws.winsums.p, (uint32_t*)g_ws.winsums.p + (size_t)Wb * (lvl1 + 1) * 4 * P::N};
+  while (count > 1) {
+    uint32_t blocks = (count + 1023) / 1024;
+    uint32_t* lvl_out = pong[lvl_launches & 1];
+    msm_window_kernel<Cfg><<<dim3(blocks, Wb), 128, 128 * 4 * P::N * 4, st>>>(lvl_in, count, 1024, lvl_out);
+    KZ_LAUNCHED();
+    lvl_in = lvl_out; count = blocks; lvl_launches++;
+  }
+  msm_final_kernel<Cfg><<<1, 32, 0, st>>>(lvl_in, Wb, c, mode, d_out);
   KZ_LAUNCHED();
   prof_red.stop(3, (double)nb);
   uint32_t hflag = 0;
