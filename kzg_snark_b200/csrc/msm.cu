@@ -40,7 +40,7 @@ uint64_t g_next_handle = 1;
 
 struct MsmWs {
   KzScratch counts, offsets, cursor, entries, buckets, partials, winsums, blocksums, result, flag, scal;
-  KzScratch ntasks, task_off, size_hist, t_start, t_len, t_dest, tparts, multi;
+  KzScratch ntasks, task_off, size_hist, t_start, t_len, t_dest, tparts, multi, sort_tmp, coarse;
 };
 MsmWs g_ws;
 
@@ -103,53 +103,192 @@ __device__ __forceinline__ int signed_digit(const uint32_t* s, uint32_t w, uint3
 }
 
 // ---------------------------------------------------------------- kernels
-// histogram of (window, |digit| - 1): one thread per scalar, L2 atomics on the 4*W*2^(c-1)-byte table
-__global__ void msm_hist_kernel(const uint32_t* __restrict__ scalars, size_t n, uint32_t c, uint32_t W, uint32_t top_bits,
-                                DigitOffset off, uint32_t tabled, uint32_t* __restrict__ counts, uint32_t* __restrict__ flag) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t s[8];
-  load_scalar_plus_offset(scalars, i, off, s);
-  // canonical scalars only: s + OFF must stay below 2^(c*W) <=> the raw scalar has <= BITS bits
-  {
-    const uint4* q = reinterpret_cast<const uint4*>(scalars + i * 8);
-    uint32_t top = __ldg(q + 1).w;
-    if (top_bits < 32 && (top >> top_bits)) atomicOr(flag, 1u);
+// Bucket sort of the n*W (key, value) digit entries, key = bucket (plain key: w * B + bucket),
+// value = index of the point to add (tabled: w * n_srs + first + i, in table w) with the digit's
+// sign in bit 31.  Two-level MSD counting sort; every atomic that is hit once per entry lives in
+// shared memory, global atomics are one per (block, bin):
+//   pass 1 (coarse = key >> f, <= 4096 bins): coarse histogram -> scan -> partition into tmp[] as
+//          64-bit (key << 32 | value) records, block-aggregated range reservation;
+//   pass 2 (fine = key & (2^f - 1)), one block per <= kSortChunk records of ONE coarse bin:
+//          fine histogram -> (global scan over all keys) -> scatter of the 32-bit values.
+// A block of pass 2 writes into the <= 2^f bucket lists of its coarse bin, a window of a few
+// hundred KB, so the 4-byte stores merge into full sectors in L2.  HBM traffic: scalars 2 x 32 B
+// per point, records 8 B written + 2 x 8 B read per entry, values 4 B written per entry.
+constexpr uint32_t kSortTile = 2048;        // scalars per block in pass 1
+constexpr uint32_t kSortChunk = 32768;      // records per block in pass 2
+constexpr uint32_t kMaxCoarse = 4096;
+
+struct SortGeom { uint32_t c, W, B, f, ncoarse, tabled, first, n_srs, top_bits; };
+
+__device__ __forceinline__ bool digit_entry(const uint32_t* s, uint32_t w, const SortGeom& g, uint32_t i, uint32_t& key, uint32_t& val) {
+  int d = signed_digit(s, w, g.c, g.W);
+  if (d == 0) return false;
+  uint32_t neg = d < 0 ? 1u : 0u;
+  uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
+  if (g.tabled) { key = mag - 1; val = (w * g.n_srs + g.first + i) | (neg << 31); }
+  else { key = w * g.B + (mag - 1); val = (g.first + i) | (neg << 31); }
+  return true;
+}
+
+// pass 1a: coarse histogram (block-local in shared memory, one global add per non-empty bin)
+__global__ void __launch_bounds__(256) msm_coarse_hist_kernel(const uint32_t* __restrict__ scalars, size_t n, SortGeom g, DigitOffset off,
+                                                              uint32_t* __restrict__ coarse_counts, uint32_t* __restrict__ flag) {
+  extern __shared__ uint32_t sh[];
+  for (uint32_t b = threadIdx.x; b < g.ncoarse; b += blockDim.x) sh[b] = 0;
+  __syncthreads();
+  const size_t base = (size_t)blockIdx.x * kSortTile;
+  for (uint32_t k = threadIdx.x; k < kSortTile; k += blockDim.x) {
+    size_t i = base + k;
+    if (i >= n) break;
+    uint32_t s[8];
+    load_scalar_plus_offset(scalars, i, off, s);
+    // canonical scalars only: s + OFF must stay below 2^(c*W) <=> the raw scalar has <= BITS bits
+    {
+      const uint4* q = reinterpret_cast<const uint4*>(scalars + i * 8);
+      uint32_t top = __ldg(q + 1).w;
+      if (g.top_bits < 32 && (top >> g.top_bits)) atomicOr(flag, 1u);
+    }
+    for (uint32_t w = 0; w < g.W; w++) {
+      uint32_t key, val;
+      if (digit_entry(s, w, g, (uint32_t)i, key, val)) atomicAdd(&sh[key >> g.f], 1u);
+    }
   }
-  const uint32_t B = 1u << (c - 1);
-  for (uint32_t w = 0; w < W; w++) {
-    int d = signed_digit(s, w, c, W);
-    if (d == 0) continue;
-    uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-    atomicAdd(counts + (tabled ? (mag - 1) * W + w : w * B + (mag - 1)), 1u);
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < g.ncoarse; b += blockDim.x)
+    if (sh[b]) atomicAdd(&coarse_counts[b], sh[b]);
+}
+
+// pass 1b: scan of the coarse counts (single block): coarse_off[0..ncoarse], write cursors, and
+// the block table of pass 2 (blk_off[b] = first block of coarse bin b, kSortChunk records each)
+__global__ void __launch_bounds__(1024) msm_coarse_scan_kernel(const uint32_t* __restrict__ coarse_counts, uint32_t ncoarse,
+                                                               uint32_t* __restrict__ coarse_off, uint32_t* __restrict__ coarse_cur,
+                                                               uint32_t* __restrict__ blk_off) {
+  __shared__ uint32_t sa[1024], sb[1024];
+  // 4 bins per thread (ncoarse <= 4096)
+  uint32_t v[4], u[4], sv = 0, su = 0;
+  for (int k = 0; k < 4; k++) {
+    uint32_t b = threadIdx.x * 4 + k;
+    v[k] = b < ncoarse ? coarse_counts[b] : 0;
+    u[k] = (v[k] + kSortChunk - 1) / kSortChunk;
+    sv += v[k]; su += u[k];
+  }
+  sa[threadIdx.x] = sv; sb[threadIdx.x] = su;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    uint32_t ta = threadIdx.x >= o ? sa[threadIdx.x - o] : 0, tb = threadIdx.x >= o ? sb[threadIdx.x - o] : 0;
+    __syncthreads();
+    sa[threadIdx.x] += ta; sb[threadIdx.x] += tb;
+    __syncthreads();
+  }
+  uint32_t ea = sa[threadIdx.x] - sv, eb = sb[threadIdx.x] - su;
+  for (int k = 0; k < 4; k++) {
+    uint32_t b = threadIdx.x * 4 + k;
+    if (b < ncoarse) { coarse_off[b] = ea; coarse_cur[b] = ea; blk_off[b] = eb; }
+    ea += v[k]; eb += u[k];
+  }
+  if (threadIdx.x == 1023) { coarse_off[ncoarse] = sa[1023]; blk_off[ncoarse] = sb[1023]; }
+}
+
+// pass 1c: partition into coarse bins.  Shared memory: count[ncoarse] then reused as the running
+// position of this block's reserved range in every bin.
+__global__ void __launch_bounds__(256) msm_partition_kernel(const uint32_t* __restrict__ scalars, size_t n, SortGeom g, DigitOffset off,
+                                                            uint32_t* __restrict__ coarse_cur, uint64_t* __restrict__ tmp) {
+  extern __shared__ uint32_t sh[];
+  for (uint32_t b = threadIdx.x; b < g.ncoarse; b += blockDim.x) sh[b] = 0;
+  __syncthreads();
+  const size_t base = (size_t)blockIdx.x * kSortTile;
+  for (uint32_t k = threadIdx.x; k < kSortTile; k += blockDim.x) {
+    size_t i = base + k;
+    if (i >= n) break;
+    uint32_t s[8];
+    load_scalar_plus_offset(scalars, i, off, s);
+    for (uint32_t w = 0; w < g.W; w++) {
+      uint32_t key, val;
+      if (digit_entry(s, w, g, (uint32_t)i, key, val)) atomicAdd(&sh[key >> g.f], 1u);
+    }
+  }
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < g.ncoarse; b += blockDim.x) {
+    uint32_t cnt = sh[b];
+    sh[b] = cnt ? atomicAdd(&coarse_cur[b], cnt) : 0u;
+  }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < kSortTile; k += blockDim.x) {
+    size_t i = base + k;
+    if (i >= n) break;
+    uint32_t s[8];
+    load_scalar_plus_offset(scalars, i, off, s);
+    for (uint32_t w = 0; w < g.W; w++) {
+      uint32_t key, val;
+      if (digit_entry(s, w, g, (uint32_t)i, key, val)) {
+        uint32_t pos = atomicAdd(&sh[key >> g.f], 1u);
+        tmp[pos] = ((uint64_t)key << 32) | val;
+      }
+    }
   }
 }
 
-// scatter, window-major (blockIdx.y = window).  The counting sort keeps one sub-list per
-// (bucket, window): plain key -> key w*B + b (each window has its own bucket set); tabled key ->
-// key b*W + w, so the W sub-lists of a bucket are adjacent and form ONE list of the shared
-// bucket.  Either way the blocks in flight work on one window, whose writes touch about one
-// 32-byte sector per sub-list (<= 64 MB in total at 2^24), so the 4-byte stores merge in the
-// 126 MB L2 into full sectors before they reach HBM.  The stored entry is the index of the
-// point to add (tabled: w * n_srs + first + i, in table w), sign in bit 31.
-template <bool TABLED>
-__global__ void msm_scatter_kernel(const uint32_t* __restrict__ scalars, size_t n, uint32_t c, uint32_t W, DigitOffset off,
-                                   uint32_t first, uint32_t n_srs, uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t s[8];
-  load_scalar_plus_offset(scalars, i, off, s);
-  const uint32_t w = blockIdx.y;
-  int d = signed_digit(s, w, c, W);
-  if (d == 0) return;
-  uint32_t neg = d < 0 ? 1u : 0u;
-  uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
-  if (TABLED) {
-    uint32_t pos = atomicAdd(cursor + (mag - 1) * W + w, 1u);
-    entries[pos] = (w * n_srs + first + (uint32_t)i) | (neg << 31);
-  } else {
-    uint32_t pos = atomicAdd(cursor + w * (1u << (c - 1)) + (mag - 1), 1u);
-    entries[pos] = (first + (uint32_t)i) | (neg << 31);
+// block -> (coarse bin, record range) through the block table
+__device__ __forceinline__ bool sort_chunk_range(const uint32_t* __restrict__ coarse_off, const uint32_t* __restrict__ blk_off,
+                                                 uint32_t ncoarse, uint32_t& bin, uint32_t& lo, uint32_t& hi) {
+  __shared__ uint32_t s_bin;
+  if (blockIdx.x >= blk_off[ncoarse]) return false;
+  if (threadIdx.x == 0) {
+    uint32_t a = 0, b = ncoarse;                 // last bin with blk_off[bin] <= blockIdx.x
+    while (b - a > 1) {
+      uint32_t m = (a + b) >> 1;
+      if (blk_off[m] <= blockIdx.x) a = m; else b = m;
+    }
+    s_bin = a;
+  }
+  __syncthreads();
+  bin = s_bin;
+  uint32_t chunk = blockIdx.x - blk_off[bin];
+  lo = coarse_off[bin] + chunk * kSortChunk;
+  hi = coarse_off[bin + 1];
+  if (hi > lo + kSortChunk) hi = lo + kSortChunk;
+  return true;
+}
+
+// pass 2a: per-key counts
+__global__ void __launch_bounds__(256) msm_fine_hist_kernel(const uint64_t* __restrict__ tmp, const uint32_t* __restrict__ coarse_off,
+                                                            const uint32_t* __restrict__ blk_off, uint32_t ncoarse, uint32_t f,
+                                                            uint32_t nkeys, uint32_t* __restrict__ counts) {
+  extern __shared__ uint32_t sh[];
+  uint32_t bin, lo, hi;
+  if (!sort_chunk_range(coarse_off, blk_off, ncoarse, bin, lo, hi)) return;
+  const uint32_t F = 1u << f;
+  for (uint32_t j = threadIdx.x; j < F; j += blockDim.x) sh[j] = 0;
+  __syncthreads();
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&sh[(uint32_t)(tmp[i] >> 32) & (F - 1)], 1u);
+  __syncthreads();
+  for (uint32_t j = threadIdx.x; j < F; j += blockDim.x) {
+    uint32_t key = (bin << f) + j;
+    if (sh[j] && key < nkeys) atomicAdd(&counts[key], sh[j]);
+  }
+}
+
+// pass 2b: scatter of the values into the per-key lists
+__global__ void __launch_bounds__(256) msm_fine_scatter_kernel(const uint64_t* __restrict__ tmp, const uint32_t* __restrict__ coarse_off,
+                                                               const uint32_t* __restrict__ blk_off, uint32_t ncoarse, uint32_t f,
+                                                               uint32_t nkeys, uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
+  extern __shared__ uint32_t sh[];
+  uint32_t bin, lo, hi;
+  if (!sort_chunk_range(coarse_off, blk_off, ncoarse, bin, lo, hi)) return;
+  const uint32_t F = 1u << f;
+  for (uint32_t j = threadIdx.x; j < F; j += blockDim.x) sh[j] = 0;
+  __syncthreads();
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&sh[(uint32_t)(tmp[i] >> 32) & (F - 1)], 1u);
+  __syncthreads();
+  for (uint32_t j = threadIdx.x; j < F; j += blockDim.x) {
+    uint32_t key = (bin << f) + j, cnt = sh[j];
+    sh[j] = (cnt && key < nkeys) ? atomicAdd(&cursor[key], cnt) : 0u;
+  }
+  __syncthreads();
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    uint64_t rec = tmp[i];
+    uint32_t pos = atomicAdd(&sh[(uint32_t)(rec >> 32) & (F - 1)], 1u);
+    entries[pos] = (uint32_t)rec;
   }
 }
 
@@ -575,19 +714,28 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   const uint32_t W = (R::BITS + 1 + c - 1) / c;          // digits per scalar
   const uint32_t Wb = tabled ? 1u : W;                   // bucket sets
   const uint32_t B = 1u << (c - 1);
-  const size_t nb = (size_t)Wb * B;                     // buckets
-  const size_t ns = (size_t)W * B;                      // sort keys: one sub-list per (bucket, window)
-  const uint32_t ostride = tabled ? W : 1u;             // offsets[] entries per bucket
+  const size_t nb = (size_t)Wb * B;                     // buckets = sort keys
   if (first + n > 0x7fffffffull) return kz_fail(KZGPU_EINVAL, "MSM index range exceeds 2^31");
+  // sort geometry: f fine bits, <= kMaxCoarse coarse bins
+  uint32_t f = 10;
+  while ((1ull << f) > nb && f > 0) f--;
+  while (((nb + (1ull << f) - 1) >> f) > kMaxCoarse && f < 13) f++;
+  const uint32_t ncoarse = (uint32_t)((nb + (1ull << f) - 1) >> f);
+  if (ncoarse > kMaxCoarse) return kz_fail(KZGPU_EINVAL, "MSM window c=%u gives too many buckets (%zu)", c, nb);
+  const size_t max_entries = (size_t)n * W;
+  if (max_entries >= 0xffffffffull) return kz_fail(KZGPU_EINVAL, "MSM of %zu points x %u digits exceeds 2^32 entries", n, W);
+  const size_t max_sort_blocks = max_entries / kSortChunk + ncoarse + 1;
   int rc;
-  if ((rc = g_ws.counts.ensure(ns * 4))) return rc;
-  if ((rc = g_ws.offsets.ensure((ns + 1) * 4))) return rc;
-  if ((rc = g_ws.cursor.ensure(ns * 4))) return rc;
-  if ((rc = g_ws.entries.ensure((size_t)n * W * 4 + 4))) return rc;
+  if ((rc = g_ws.counts.ensure(nb * 4))) return rc;
+  if ((rc = g_ws.offsets.ensure((nb + 1) * 4))) return rc;
+  if ((rc = g_ws.cursor.ensure(nb * 4))) return rc;
+  if ((rc = g_ws.entries.ensure(max_entries * 4 + 4))) return rc;
+  if ((rc = g_ws.sort_tmp.ensure(max_entries * 8 + 8))) return rc;
+  if ((rc = g_ws.coarse.ensure((size_t)(4 * kMaxCoarse + 4) * 4))) return rc;
   if ((rc = g_ws.buckets.ensure(nb * 4 * P::N * 4))) return rc;
   if ((rc = g_ws.flag.ensure(4))) return rc;
-  const size_t nblk_s = kz_div_up(ns, 1024), nblk = kz_div_up(nb, 1024);
-  if ((rc = g_ws.blocksums.ensure(nblk_s * 4))) return rc;
+  const size_t nblk = kz_div_up(nb, 1024);
+  if ((rc = g_ws.blocksums.ensure(nblk * 4))) return rc;
   uint32_t CH = 64;
   if (CH > B) CH = B;
   const uint32_t cpw = (B + CH - 1) / CH;
@@ -599,11 +747,20 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   uint32_t* offsets = (uint32_t*)g_ws.offsets.p;
   uint32_t* cursor = (uint32_t*)g_ws.cursor.p;
   uint32_t* entries = (uint32_t*)g_ws.entries.p;
+  uint64_t* sort_tmp = (uint64_t*)g_ws.sort_tmp.p;
+  uint32_t* coarse_counts = (uint32_t*)g_ws.coarse.p;
+  uint32_t* coarse_off = coarse_counts + kMaxCoarse;        // ncoarse + 1 entries
+  uint32_t* coarse_cur = coarse_off + kMaxCoarse + 1;
+  uint32_t* blk_off = coarse_cur + kMaxCoarse;              // ncoarse + 1 entries
   uint32_t* flag = (uint32_t*)g_ws.flag.p;
 
-  KZ_CUDA(cudaMemsetAsync(counts, 0, ns * 4, st));
+  KZ_CUDA(cudaMemsetAsync(counts, 0, nb * 4, st));
+  KZ_CUDA(cudaMemsetAsync(coarse_counts, 0, kMaxCoarse * 4, st));
   KZ_CUDA(cudaMemsetAsync(flag, 0, 4, st));
-  const uint32_t top_bits = R::BITS - 224;       // bits allowed in the top 32-bit word
+  SortGeom geo;
+  geo.c = c; geo.W = W; geo.B = B; geo.f = f; geo.ncoarse = ncoarse; geo.tabled = tabled ? 1u : 0u;
+  geo.first = (uint32_t)first; geo.n_srs = (uint32_t)srs.n;
+  geo.top_bits = R::BITS - 224;                  // bits allowed in the top 32-bit word
   DigitOffset doff;
   for (int k = 0; k < 8; k++) doff.w[k] = 0;
   for (uint32_t w = 0; w + 1 < W; w++) {
@@ -612,23 +769,28 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   }
   KzProf prof_sort(2);
   if (n) {
-    msm_hist_kernel<<<(unsigned)kz_div_up(n, 256), 256, 0, st>>>(d_scalars, n, c, W, top_bits, doff, tabled ? 1u : 0u, counts, flag);
+    const unsigned tiles = (unsigned)kz_div_up(n, kSortTile);
+    msm_coarse_hist_kernel<<<tiles, 256, ncoarse * 4, st>>>(d_scalars, n, geo, doff, coarse_counts, flag);
+    KZ_LAUNCHED();
+    msm_coarse_scan_kernel<<<1, 1024, 0, st>>>(coarse_counts, ncoarse, coarse_off, coarse_cur, blk_off);
+    KZ_LAUNCHED();
+    msm_partition_kernel<<<tiles, 256, ncoarse * 4, st>>>(d_scalars, n, geo, doff, coarse_cur, sort_tmp);
+    KZ_LAUNCHED();
+    msm_fine_hist_kernel<<<(unsigned)max_sort_blocks, 256, (4u << f), st>>>(sort_tmp, coarse_off, blk_off, ncoarse, f, (uint32_t)nb, counts);
     KZ_LAUNCHED();
   }
-  scan_block_kernel<<<(unsigned)nblk_s, 256, 0, st>>>(counts, offsets, (uint32_t*)g_ws.blocksums.p, ns);
+  scan_block_kernel<<<(unsigned)nblk, 256, 0, st>>>(counts, offsets, (uint32_t*)g_ws.blocksums.p, nb);
   KZ_LAUNCHED();
-  scan_sums_kernel<<<1, 256, 0, st>>>((uint32_t*)g_ws.blocksums.p, nblk_s, offsets + ns);
+  scan_sums_kernel<<<1, 256, 0, st>>>((uint32_t*)g_ws.blocksums.p, nblk, offsets + nb);
   KZ_LAUNCHED();
-  scan_add_kernel<<<(unsigned)kz_div_up(ns, 256), 256, 0, st>>>(offsets, (uint32_t*)g_ws.blocksums.p, ns, cursor);
+  scan_add_kernel<<<(unsigned)kz_div_up(nb, 256), 256, 0, st>>>(offsets, (uint32_t*)g_ws.blocksums.p, nb, cursor);
   KZ_LAUNCHED();
   if (n) {
-    dim3 grid((unsigned)kz_div_up(n, 256), W);
-    if (tabled)
-      msm_scatter_kernel<true><<<grid, 256, 0, st>>>(d_scalars, n, c, W, doff, (uint32_t)first, (uint32_t)srs.n, cursor, entries);
-    else
-      msm_scatter_kernel<false><<<grid, 256, 0, st>>>(d_scalars, n, c, W, doff, (uint32_t)first, (uint32_t)srs.n, cursor, entries);
+    msm_fine_scatter_kernel<<<(unsigned)max_sort_blocks, 256, (4u << f), st>>>(sort_tmp, coarse_off, blk_off, ncoarse, f, (uint32_t)nb, cursor,
+                                                                             entries);
     KZ_LAUNCHED();
   }
+  const uint32_t ostride = 1u;                          // offsets[] entries per bucket
   // tasks: split heavy buckets, sort by length
   uint32_t mean = (uint32_t)(((size_t)n * (tabled ? W : 1u)) / B) + 1;
   uint32_t T = 32;
@@ -672,13 +834,13 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
       srs.d_points, entries, (uint32_t*)g_ws.t_start.p, (uint32_t*)g_ws.t_len.p, (uint32_t*)g_ws.t_dest.p, size_cursor,
       (uint32_t*)g_ws.buckets.p, (uint32_t*)g_ws.tparts.p);
   KZ_LAUNCHED();
+  prof_acc.stop(1, (double)n * W);
+  KzProf prof_red(3);
   msm_merge_kernel<Cfg><<<cx.sm_count * 4, 128, 0, st>>>(ntasks, task_off, multi_count, multi_list, (uint32_t*)g_ws.tparts.p,
                                                         (uint32_t*)g_ws.buckets.p);
   KZ_LAUNCHED();
   msm_clear_empty_kernel<Cfg><<<(unsigned)kz_div_up(nb, 256), 256, 0, st>>>(ntasks, (uint32_t)nb, (uint32_t*)g_ws.buckets.p);
   KZ_LAUNCHED();
-  prof_acc.stop(3, (double)n * W);
-  KzProf prof_red(3);
   msm_reduce_kernel<Cfg><<<(unsigned)kz_div_up((size_t)cpw * Wb, 128), 128, 0, st>>>((uint32_t*)g_ws.buckets.p, B, CH, cpw, Wb,
                                                                                     (uint32_t*)g_ws.partials.p);
   KZ_LAUNCHED();
@@ -835,7 +997,8 @@ void kz_msm_release() {
   g_srs.clear();
   KzScratch* all[] = {&g_ws.counts, &g_ws.offsets, &g_ws.cursor, &g_ws.entries, &g_ws.buckets, &g_ws.partials,
                       &g_ws.winsums, &g_ws.blocksums, &g_ws.result, &g_ws.flag, &g_ws.scal,
-                      &g_ws.ntasks, &g_ws.task_off, &g_ws.size_hist, &g_ws.t_start, &g_ws.t_len, &g_ws.t_dest, &g_ws.tparts, &g_ws.multi};
+                      &g_ws.ntasks, &g_ws.task_off, &g_ws.size_hist, &g_ws.t_start, &g_ws.t_len, &g_ws.t_dest, &g_ws.tparts, &g_ws.multi,
+                      &g_ws.sort_tmp, &g_ws.coarse};
   for (auto* s : all) s->release();
 }
 
