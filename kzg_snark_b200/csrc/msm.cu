@@ -114,8 +114,9 @@ __device__ __forceinline__ int signed_digit(const uint32_t* s, uint32_t w, uint3
 // A block of pass 2 writes into the <= 2^f bucket lists of its coarse bin, a window of a few
 // hundred KB, so the 4-byte stores merge into full sectors in L2.  HBM traffic: scalars 2 x 32 B
 // per point, records 8 B written + 2 x 8 B read per entry, values 4 B written per entry.
-constexpr uint32_t kSortTile = 2048;        // scalars per block in pass 1
-constexpr uint32_t kSortChunk = 32768;      // records per block in pass 2
+constexpr uint32_t kSortTile = 2048;        // scalars per block in the coarse histogram
+constexpr uint32_t kSortStage = 11264;      // records staged per block in the partition (88 KB)
+constexpr uint32_t kSortChunk = 16384;      // records per block in pass 2 (64 KB staged)
 constexpr uint32_t kMaxCoarse = 4096;
 
 struct SortGeom { uint32_t c, W, B, f, ncoarse, tabled, first, n_srs, top_bits; };
@@ -189,31 +190,65 @@ __global__ void __launch_bounds__(1024) msm_coarse_scan_kernel(const uint32_t* _
   if (threadIdx.x == 1023) { coarse_off[ncoarse] = sa[1023]; blk_off[ncoarse] = sb[1023]; }
 }
 
-// pass 1c: partition into coarse bins.  Shared memory: count[ncoarse] then reused as the running
-// position of this block's reserved range in every bin.
-__global__ void __launch_bounds__(256) msm_partition_kernel(const uint32_t* __restrict__ scalars, size_t n, SortGeom g, DigitOffset off,
-                                                            uint32_t* __restrict__ coarse_cur, uint64_t* __restrict__ tmp) {
-  extern __shared__ uint32_t sh[];
-  for (uint32_t b = threadIdx.x; b < g.ncoarse; b += blockDim.x) sh[b] = 0;
+// exclusive scan of arr[0..nbins) in shared memory, in place; returns the total.
+// scratch: blockDim.x words.  Every thread of the block must call it.
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t* arr, uint32_t nbins, uint32_t* scratch) {
+  const uint32_t per = (nbins + blockDim.x - 1) / blockDim.x;
+  const uint32_t lo = threadIdx.x * per, hi = lo + per < nbins ? lo + per : nbins;
+  uint32_t sum = 0;
+  for (uint32_t b = lo; b < hi; b++) sum += arr[b];
+  scratch[threadIdx.x] = sum;
   __syncthreads();
-  const size_t base = (size_t)blockIdx.x * kSortTile;
-  for (uint32_t k = threadIdx.x; k < kSortTile; k += blockDim.x) {
+  for (uint32_t o = 1; o < blockDim.x; o <<= 1) {
+    uint32_t t = threadIdx.x >= o ? scratch[threadIdx.x - o] : 0;
+    __syncthreads();
+    scratch[threadIdx.x] += t;
+    __syncthreads();
+  }
+  uint32_t run = scratch[threadIdx.x] - sum;
+  const uint32_t total = scratch[blockDim.x - 1];
+  for (uint32_t b = lo; b < hi; b++) { uint32_t v = arr[b]; arr[b] = run; run += v; }
+  __syncthreads();
+  return total;
+}
+
+// pass 1c: partition into coarse bins.  The tile's records are first sorted by bin in shared
+// memory (count -> scan -> place), the range of every bin is reserved with ONE global atomic, and
+// the staged records are written out in order, so that a bin's run leaves the SM as consecutive
+// 8-byte stores within a few instructions (partial sectors are completed while still in L2).
+// Shared memory: cur[ncoarse] | delta[ncoarse] | scan scratch[blockDim] | stage[tile * W] (u64)
+__global__ void __launch_bounds__(512) msm_partition_kernel(const uint32_t* __restrict__ scalars, size_t n, uint32_t tile, SortGeom g,
+                                                            DigitOffset off, uint32_t* __restrict__ coarse_cur,
+                                                            uint64_t* __restrict__ tmp) {
+  extern __shared__ uint64_t sh64[];
+  uint64_t* stage = sh64;
+  uint32_t* cur = reinterpret_cast<uint32_t*>(stage + (size_t)tile * g.W);
+  uint32_t* delta = cur + g.ncoarse;
+  uint32_t* scratch = delta + g.ncoarse;
+  for (uint32_t b = threadIdx.x; b < g.ncoarse; b += blockDim.x) cur[b] = 0;
+  __syncthreads();
+  const size_t base = (size_t)blockIdx.x * tile;
+  for (uint32_t k = threadIdx.x; k < tile; k += blockDim.x) {
     size_t i = base + k;
     if (i >= n) break;
     uint32_t s[8];
     load_scalar_plus_offset(scalars, i, off, s);
     for (uint32_t w = 0; w < g.W; w++) {
       uint32_t key, val;
-      if (digit_entry(s, w, g, (uint32_t)i, key, val)) atomicAdd(&sh[key >> g.f], 1u);
+      if (digit_entry(s, w, g, (uint32_t)i, key, val)) atomicAdd(&cur[key >> g.f], 1u);
     }
   }
   __syncthreads();
+  // reserve the global range of every non-empty bin (count still in cur[]), then local offsets
   for (uint32_t b = threadIdx.x; b < g.ncoarse; b += blockDim.x) {
-    uint32_t cnt = sh[b];
-    sh[b] = cnt ? atomicAdd(&coarse_cur[b], cnt) : 0u;
+    uint32_t cnt = cur[b];
+    delta[b] = cnt ? atomicAdd(&coarse_cur[b], cnt) : 0u;
   }
   __syncthreads();
-  for (uint32_t k = threadIdx.x; k < kSortTile; k += blockDim.x) {
+  const uint32_t total = block_excl_scan(cur, g.ncoarse, scratch);
+  for (uint32_t b = threadIdx.x; b < g.ncoarse; b += blockDim.x) delta[b] -= cur[b];     // global pos = local pos + delta
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < tile; k += blockDim.x) {
     size_t i = base + k;
     if (i >= n) break;
     uint32_t s[8];
@@ -221,10 +256,15 @@ __global__ void __launch_bounds__(256) msm_partition_kernel(const uint32_t* __re
     for (uint32_t w = 0; w < g.W; w++) {
       uint32_t key, val;
       if (digit_entry(s, w, g, (uint32_t)i, key, val)) {
-        uint32_t pos = atomicAdd(&sh[key >> g.f], 1u);
-        tmp[pos] = ((uint64_t)key << 32) | val;
+        uint32_t pos = atomicAdd(&cur[key >> g.f], 1u);
+        stage[pos] = ((uint64_t)key << 32) | val;
       }
     }
+  }
+  __syncthreads();
+  for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) {
+    uint64_t rec = stage[j];
+    tmp[j + delta[(uint32_t)(rec >> 32) >> g.f]] = rec;
   }
 }
 
@@ -268,27 +308,41 @@ __global__ void __launch_bounds__(256) msm_fine_hist_kernel(const uint64_t* __re
   }
 }
 
-// pass 2b: scatter of the values into the per-key lists
-__global__ void __launch_bounds__(256) msm_fine_scatter_kernel(const uint64_t* __restrict__ tmp, const uint32_t* __restrict__ coarse_off,
+// pass 2b: scatter of the values into the per-key lists, staged like pass 1c: the chunk's values
+// are sorted by fine key in shared memory and every key's run is written by a group of 8 lanes.
+// Shared memory: cur[F] | gpos[F] | scan scratch[blockDim] | stage[kSortChunk] (u32)
+__global__ void __launch_bounds__(512) msm_fine_scatter_kernel(const uint64_t* __restrict__ tmp, const uint32_t* __restrict__ coarse_off,
                                                                const uint32_t* __restrict__ blk_off, uint32_t ncoarse, uint32_t f,
                                                                uint32_t nkeys, uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
   extern __shared__ uint32_t sh[];
   uint32_t bin, lo, hi;
   if (!sort_chunk_range(coarse_off, blk_off, ncoarse, bin, lo, hi)) return;
   const uint32_t F = 1u << f;
-  for (uint32_t j = threadIdx.x; j < F; j += blockDim.x) sh[j] = 0;
+  uint32_t* cur = sh;
+  uint32_t* gpos = cur + F;
+  uint32_t* scratch = gpos + F;
+  uint32_t* stage = scratch + blockDim.x;
+  for (uint32_t j = threadIdx.x; j < F; j += blockDim.x) cur[j] = 0;
   __syncthreads();
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&sh[(uint32_t)(tmp[i] >> 32) & (F - 1)], 1u);
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&cur[(uint32_t)(tmp[i] >> 32) & (F - 1)], 1u);
   __syncthreads();
   for (uint32_t j = threadIdx.x; j < F; j += blockDim.x) {
-    uint32_t key = (bin << f) + j, cnt = sh[j];
-    sh[j] = (cnt && key < nkeys) ? atomicAdd(&cursor[key], cnt) : 0u;
+    uint32_t key = (bin << f) + j, cnt = cur[j];
+    gpos[j] = (cnt && key < nkeys) ? atomicAdd(&cursor[key], cnt) : 0u;
   }
   __syncthreads();
+  block_excl_scan(cur, F, scratch);
   for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     uint64_t rec = tmp[i];
-    uint32_t pos = atomicAdd(&sh[(uint32_t)(rec >> 32) & (F - 1)], 1u);
-    entries[pos] = (uint32_t)rec;
+    uint32_t pos = atomicAdd(&cur[(uint32_t)(rec >> 32) & (F - 1)], 1u);
+    stage[pos] = (uint32_t)rec;
+  }
+  __syncthreads();
+  // cur[j] is now the END of key j's run in stage[]; its start is cur[j-1] (0 for j == 0)
+  const uint32_t grp = threadIdx.x >> 3, ln = threadIdx.x & 7, ngrp = blockDim.x >> 3;
+  for (uint32_t j = grp; j < F; j += ngrp) {
+    uint32_t s0 = j ? cur[j - 1] : 0u, s1 = cur[j], gp = gpos[j];
+    for (uint32_t k = s0 + ln; k < s1; k += 8) entries[gp + (k - s0)] = stage[k];
   }
 }
 
@@ -774,7 +828,9 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
     KZ_LAUNCHED();
     msm_coarse_scan_kernel<<<1, 1024, 0, st>>>(coarse_counts, ncoarse, coarse_off, coarse_cur, blk_off);
     KZ_LAUNCHED();
-    msm_partition_kernel<<<tiles, 256, ncoarse * 4, st>>>(d_scalars, n, geo, doff, coarse_cur, sort_tmp);
+    const uint32_t ptile = kSortStage / W;                       // scalars per partition block
+    const size_t psmem = (size_t)ptile * W * 8 + (2 * (size_t)ncoarse + 512) * 4;
+    msm_partition_kernel<<<(unsigned)kz_div_up(n, ptile), 512, psmem, st>>>(d_scalars, n, ptile, geo, doff, coarse_cur, sort_tmp);
     KZ_LAUNCHED();
     msm_fine_hist_kernel<<<(unsigned)max_sort_blocks, 256, (4u << f), st>>>(sort_tmp, coarse_off, blk_off, ncoarse, f, (uint32_t)nb, counts);
     KZ_LAUNCHED();
@@ -786,7 +842,7 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   scan_add_kernel<<<(unsigned)kz_div_up(nb, 256), 256, 0, st>>>(offsets, (uint32_t*)g_ws.blocksums.p, nb, cursor);
   KZ_LAUNCHED();
   if (n) {
-    msm_fine_scatter_kernel<<<(unsigned)max_sort_blocks, 256, (4u << f), st>>>(sort_tmp, coarse_off, blk_off, ncoarse, f, (uint32_t)nb, cursor,
+    msm_fine_scatter_kernel<<<(unsigned)max_sort_blocks, 512, ((8u << f) + (512 + kSortChunk) * 4), st>>>(sort_tmp, coarse_off, blk_off, ncoarse, f, (uint32_t)nb, cursor,
                                                                              entries);
     KZ_LAUNCHED();
   }
@@ -883,6 +939,8 @@ int set_smem_attrs() {
   if (done) return 0;
   KZ_CUDA(cudaFuncSetAttribute(msm_window_kernel<BLS381Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 4 * 12 * 4));
   KZ_CUDA(cudaFuncSetAttribute(g1_fold_kernel<BLS381Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 4 * 12 * 4));
+  KZ_CUDA(cudaFuncSetAttribute(msm_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortStage * 8 + (2 * kMaxCoarse + 512) * 4));
+  KZ_CUDA(cudaFuncSetAttribute(msm_fine_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 << 13) + (512 + kSortChunk) * 4));
   done = true;
   return 0;
 }
