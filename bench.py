@@ -59,7 +59,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(device), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(device), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -295,7 +295,6 @@ def run_gpu(args):
             ms = e0.elapsed_time(e1)
         barrier()
         launches = _ffi.launch_count() - l0
-        clocks = sampler.stop()
         ms = max_over_ranks(ms)
         # per-kernel profile (second region, CUDA events around the kernels on the launching stream)
         _ffi.profile_reset(); _ffi.profile_enable(True)
@@ -310,7 +309,8 @@ def run_gpu(args):
             step_e2e()
         barrier()
         ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
-        acc = prof["accumulate"]
+        clocks = sampler.stop()                                  # sampled over the timed, per-kernel and e2e regions
+        acc = prof["accumulate"]                                 # the bucket-accumulate kernel alone, one launch per MSM
         acc_ms = acc["ms"] / max(acc["launches"], 1)
         madds = acc["work"] / max(acc["launches"], 1)            # mixed additions per launch (n * windows upper bound)
         pts_per_s = world * n * K / (ms * 1e-3)
@@ -362,7 +362,6 @@ def run_gpu(args):
             ms = e0.elapsed_time(e1)
         barrier()
         launches = _ffi.launch_count() - l0
-        clocks = sampler.stop()
         ms = max_over_ranks(ms)
         _ffi.profile_reset(); _ffi.profile_enable(True)
         for _ in range(K):
@@ -375,6 +374,7 @@ def run_gpu(args):
             device.ntt("bn254", pinned.array, wl)            # H2D + kernels + D2H inside the call
         barrier()
         ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        clocks = sampler.stop()
         ntt_ms = pr["ms"] / K                                   # all passes of one transform
         hbm = 64.0 * n_total / (ntt_ms * 1e-3) / 1e9
         modmuls = 0.5 * n_total * args.logn
@@ -460,7 +460,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="msm", choices=["msm", "ntt"])

@@ -40,8 +40,14 @@ def build(force=False, verbose=False):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
 
+    hdr_t = max([os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC) if f.endswith(".cuh")] +
+                [os.path.getmtime(os.path.join(os.path.dirname(HERE), "include", "kzgpu.h"))])
+
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        if (not force and not verbose and os.path.exists(obj)
+                and os.path.getmtime(obj) > max(hdr_t, os.path.getmtime(os.path.join(CSRC, src)))):
+            return obj                                   # object is newer than its source and every header
         cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

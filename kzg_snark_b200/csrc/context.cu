@@ -1,6 +1,9 @@
 // Library context, device-memory plumbing, field self-test and throughput microbenchmarks.
 #include "common.cuh"
 #include <cstring>
+#include <cctype>
+#include <unistd.h>
+#include <sys/syscall.h>
 
 void kz_ntt_release();
 void kz_msm_release();
@@ -94,6 +97,47 @@ __global__ void mb_imad_kernel(uint32_t* sink, int iters, uint32_t seed) {
   uint32_t s = top;
   for (int c = 0; c < 4; c++)
     for (int i = 0; i < 8; i++) s ^= acc[c][i];
+  if (s == 0x12345678u) sink[0] = s;
+}
+
+// IMAD.WIDE chains as in mb_imad_kernel plus ALU independent 3-input adds per 8 wide multiplies:
+// measures whether ALU-pipe work issues in the shadow of a saturated IMAD.WIDE stream.
+template <int ALU> __global__ void mb_imad_alu_kernel(uint32_t* sink, int iters, uint32_t seed) {
+  uint32_t acc[4][8], a[8], z[8];
+  for (int i = 0; i < 8; i++) { a[i] = seed * (i + 3) + threadIdx.x; z[i] = seed + i * 5 + threadIdx.x; }
+  for (int c = 0; c < 4; c++)
+    for (int i = 0; i < 8; i++) acc[c][i] = seed + c * 17 + i;
+  uint32_t top = 0;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      MpPrims<8>::mad_even(acc[c], a, acc[(c + 1) & 3][0], top);
+#pragma unroll
+      for (int k = 0; k < ALU / 2; k++) asm volatile("xor.b32 %0, %0, %1; shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(z[k & 7]) : "r"(a[(k + 1) & 7]), "r"(seed));
+      MpPrims<8>::mad_even(acc[c], a + 1, acc[(c + 2) & 3][1], top);
+#pragma unroll
+      for (int k = 0; k < ALU / 2; k++) asm volatile("xor.b32 %0, %0, %1; shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(z[(k + 4) & 7]) : "r"(a[(k + 2) & 7]), "r"(seed));
+    }
+  }
+  uint32_t s = top;
+  for (int c = 0; c < 4; c++)
+    for (int i = 0; i < 8; i++) s ^= acc[c][i];
+  for (int i = 0; i < 8; i++) s ^= z[i];
+  if (s == 0x12345678u) sink[0] = s;
+}
+
+// narrow multiply-add rate: independent 32-bit mad.lo chains (IMAD)
+__global__ void mb_imad32_kernel(uint32_t* sink, int iters, uint32_t seed) {
+  uint32_t x[16], a = seed + threadIdx.x, b = seed * 3 + 1;
+  for (int i = 0; i < 16; i++) x[i] = seed + i;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+      for (int i = 0; i < 16; i++) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(a), "r"(b));
+  }
+  uint32_t s = 0;
+  for (int i = 0; i < 16; i++) s ^= x[i];
   if (s == 0x12345678u) sink[0] = s;
 }
 
@@ -229,10 +273,35 @@ int kzgpu_sync(void) {
   return 0;
 }
 
+// NUMA node of the GPU (from sysfs), -1 if unknown
+static int gpu_numa_node(int device) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return -1;
+  for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+  char path[128];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE* f = fopen(path, "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+
+// Page-locked host memory, placed on the GPU's own NUMA node when the kernel lets us say so:
+// a buffer on the far socket halves the device->host rate of the e2e path.
 int kzgpu_host_alloc(void** h_ptr, size_t bytes) {
   KZ_REQUIRE_INIT();
   if (!h_ptr) return kz_fail(KZGPU_EINVAL, "null pointer");
-  KZ_CUDA(cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+  const int node = gpu_numa_node(kz_ctx().device);
+  bool policy_set = false;
+  if (node >= 0 && node < 64) {
+    unsigned long mask = 1ul << node;
+    policy_set = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, 65ul) == 0;
+  }
+  cudaError_t e = cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (policy_set) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+  if (e != cudaSuccess) return kz_fail(KZGPU_ECUDA, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
   return 0;
 }
 
@@ -314,6 +383,9 @@ int kzgpu_microbench(int kind, int blocks, int threads, int iters, float* ms, do
       case 2: mb_mul_kernel<FpBLS381><<<blocks, threads, 0, cx.stream>>>(sink, iters, 12345u); per_thread = 4.0 * iters; break;
       case 3: mb_madd_kernel<FpBN254><<<blocks, threads, 0, cx.stream>>>(sink, iters, 12345u); per_thread = 1.0 * iters; break;
       case 4: mb_madd_kernel<FpBLS381><<<blocks, threads, 0, cx.stream>>>(sink, iters, 12345u); per_thread = 1.0 * iters; break;
+      case 5: mb_imad_alu_kernel<8><<<blocks, threads, 0, cx.stream>>>(sink, iters, 12345u); per_thread = 32.0 * iters; break;    // 2 ALU ops per wide
+      case 6: mb_imad_alu_kernel<16><<<blocks, threads, 0, cx.stream>>>(sink, iters, 12345u); per_thread = 32.0 * iters; break;   // 4 ALU ops per wide
+      case 7: mb_imad32_kernel<<<blocks, threads, 0, cx.stream>>>(sink, iters, 12345u); per_thread = 32.0 * iters; break;
       default: cudaFree(sink); return kz_fail(KZGPU_EINVAL, "unknown microbench kind %d", kind);
     }
     KZ_LAUNCHED();

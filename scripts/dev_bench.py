@@ -14,9 +14,9 @@ def main():
     sm = info["sm_count"]
     res = {}
     if "micro" in what:
-        for kind, name in ((0, "imad_wide"), (1, "fe_mul_bn254"), (2, "fe_mul_bls381"), (3, "madd_bn254"), (4, "madd_bls381")):
+        for kind, name in ((0, "imad_wide"), (5, "imad_wide+2alu"), (6, "imad_wide+4alu"), (7, "imad32"), (1, "fe_mul_bn254"), (2, "fe_mul_bls381"), (3, "madd_bn254"), (4, "madd_bls381")):
             for threads, bps in ((256, 2), (128, 4), (256, 4), (128, 2)):
-                iters = 2000 if kind < 3 else 400
+                iters = 400 if kind in (3, 4) else 2000
                 ms, ops = _ffi.microbench(kind, sm * bps, threads, iters)
                 print(f"micro {name:14s} blocks/SM={bps} threads={threads}: {ms:8.3f} ms  {ops/ms/1e6:10.2f} Gop/s", flush=True)
                 res.setdefault(name, []).append(ops / ms / 1e6)
