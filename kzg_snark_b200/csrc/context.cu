@@ -141,6 +141,33 @@ __global__ void mb_imad32_kernel(uint32_t* sink, int iters, uint32_t seed) {
   if (s == 0x12345678u) sink[0] = s;
 }
 
+// FP64 pipe: independent DFMA.RZ chains, optionally with ALU (IADD3 pairs = 64-bit adds) and
+// IMAD.WIDE work interleaved -- is the FP64 pipe a second multiplier next to the integer one?
+template <int ALU, int WIDE> __global__ void mb_dfma_kernel(uint32_t* sink, int iters, uint32_t seed) {
+  double x[8], a = 1.0 + 1e-9 * (seed & 7), b = 1e-3 * threadIdx.x;
+  unsigned long long z[4];
+  uint32_t acc[8], m[8];
+  uint32_t top = 0;
+  for (int i = 0; i < 8; i++) { x[i] = (double)(seed + i); acc[i] = seed + i; m[i] = seed * (i + 3) + threadIdx.x; }
+  for (int i = 0; i < 4; i++) z[i] = seed + i;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) x[i] = __fma_rz(x[i], a, b);
+#pragma unroll
+      for (int k = 0; k < ALU; k++) z[k & 3] += __double_as_longlong(x[k & 7]) + z[(k + 1) & 3];
+      if (WIDE) MpPrims<8>::mad_even(acc, m, acc[r], top);
+    }
+  }
+  double s = 0;
+  for (int i = 0; i < 8; i++) s += x[i];
+  unsigned long long t = top;
+  for (int i = 0; i < 4; i++) t ^= z[i];
+  for (int i = 0; i < 8; i++) t ^= acc[i];
+  if (s == 0.12345 || t == 0x12345678ull) sink[0] = (uint32_t)t;
+}
+
 template <class P> __global__ void mb_mul_kernel(uint32_t* sink, int iters, uint32_t seed) {
   Fe<P> x[4];
   for (int c = 0; c < 4; c++)
@@ -386,6 +413,10 @@ int kzgpu_microbench(int kind, int blocks, int threads, int iters, float* ms, do
       case 5: mb_imad_alu_kernel<8><<<blocks, threads, 0, cx.stream>>>(sink, iters, 12345u); per_thread = 32.0 * iters; break;    // 2 ALU ops per wide
       case 6: mb_imad_alu_kernel<16><<<blocks, threads, 0, cx.stream>>>(sink, iters, 12345u); per_thread = 32.0 * iters; break;   // 4 ALU ops per wide
       case 7: mb_imad32_kernel<<<blocks, threads, 0, cx.stream>>>(sink, iters, 12345u); per_thread = 32.0 * iters; break;
+      case 8: mb_dfma_kernel<0, 0><<<blocks, threads, 0, cx.stream>>>(sink, iters, 12345u); per_thread = 32.0 * iters; break;    // DFMA only
+      case 9: mb_dfma_kernel<8, 0><<<blocks, threads, 0, cx.stream>>>(sink, iters, 12345u); per_thread = 32.0 * iters; break;    // + one 64-bit 3-input add per DFMA
+      case 10: mb_dfma_kernel<0, 1><<<blocks, threads, 0, cx.stream>>>(sink, iters, 12345u); per_thread = 32.0 * iters; break;   // + one IMAD.WIDE per 2 DFMA
+      case 11: mb_dfma_kernel<8, 1><<<blocks, threads, 0, cx.stream>>>(sink, iters, 12345u); per_thread = 32.0 * iters; break;
       default: cudaFree(sink); return kz_fail(KZGPU_EINVAL, "unknown microbench kind %d", kind);
     }
     KZ_LAUNCHED();

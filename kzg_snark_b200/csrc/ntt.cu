@@ -23,9 +23,10 @@
 
 namespace {
 
-constexpr int kLogTile = 11;        // 2048 elements (64 KB of shared memory) per block
+constexpr int kLogTile = 10;        // 1024 elements (32 KB of shared memory) per block: four blocks per SM, so the
+                                    // global-load / store phases of one block hide behind the butterflies of the others
 constexpr int kMaxB = 9;            // R_t <= 512
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;
 
 template <class P> struct NttConsts { Fe<P> w8, w4, w8_3; };   // omega_8, omega_8^2, omega_8^3
 
@@ -119,7 +120,7 @@ template <class P, int D> __device__ __forceinline__ void dft_small(Fe<P>* x, co
 }
 
 template <class P, int D>
-__device__ __forceinline__ void ntt_layer(uint32_t* sm, const NttPassArgs& a, const NttConsts<P>& c,
+__device__ __forceinline__ void ntt_layer(uint32_t* sm, const uint32_t* smw, const NttPassArgs& a, const NttConsts<P>& c,
                                           uint32_t li, uint32_t off, uint32_t done) {
   const uint32_t tile_log = a.b + a.logC, tile = 1u << tile_log;
   const uint32_t ngroups = tile >> D;
@@ -149,7 +150,7 @@ __device__ __forceinline__ void ntt_layer(uint32_t* sm, const NttPassArgs& a, co
 #pragma unroll
       for (int u = 1; u < (1 << D); u++) {
         uint32_t e = ((uint32_t)u << off) * V;
-        x[u] = fe_mul<P>(x[u], ldg_fe<P>(a.wR + (size_t)e * P::N));
+        x[u] = fe_mul<P>(x[u], sm_ld<P>(smw, 1u << a.b, e));
       }
     }
     dft_small<P, D>(x, c);
@@ -162,22 +163,40 @@ __device__ __forceinline__ void ntt_layer(uint32_t* sm, const NttPassArgs& a, co
 }
 
 template <class P>
-__global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(NttPassArgs a, NttConsts<P> c) {
+__global__ void __launch_bounds__(kThreads, 4) ntt_pass_kernel(NttPassArgs a, NttConsts<P> c) {
   extern __shared__ uint32_t sm[];
   const uint32_t tile_log = a.b + a.logC, tile = 1u << tile_log;
+  // omega_R^e table as 8 word-planes behind the tile (read by the layers li > 0)
+  uint32_t* smw = sm + (size_t)P::N * tile;
+  if (a.nd > 1) {
+    const uint32_t R = 1u << a.b;
+    for (uint32_t e = threadIdx.x; e < R; e += blockDim.x) sm_st<P>(smw, R, e, ldg_fe<P>(a.wR + (size_t)e * P::N));
+  }
   const uint32_t Cmask = (1u << a.logC) - 1, Kmask = (1u << a.logK) - 1, Rmask = (1u << a.b) - 1;
   const size_t boff = (size_t)blockIdx.y * a.n;
   const size_t q0 = (size_t)blockIdx.x << a.logC;
 
-  for (uint32_t o = threadIdx.x; o < tile; o += blockDim.x) {
-    uint32_t l = o >> a.logC, cc = o & Cmask;
-    size_t qq = q0 + cc;
-    Fe<P> v = ld_fe<P>(a.in + (boff + ((size_t)l << a.logQ) + qq) * P::N);
-    if (a.bnd) {
-      size_t kk = qq & Kmask;
-      v = fe_mul<P>(v, ldg_fe<P>(a.bnd + (((size_t)l << a.logK) + kk) * P::N));
+  // load phase, four elements (and their boundary twiddles) in flight per thread
+  for (uint32_t o0 = threadIdx.x; o0 < tile; o0 += 4 * blockDim.x) {
+    Fe<P> v[4], tw[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint32_t o = o0 + k * blockDim.x;
+      if (o < tile) {
+        uint32_t l = o >> a.logC, cc = o & Cmask;
+        size_t qq = q0 + cc;
+        v[k] = ld_fe<P>(a.in + (boff + ((size_t)l << a.logQ) + qq) * P::N);
+        if (a.bnd) tw[k] = ldg_fe<P>(a.bnd + (((size_t)l << a.logK) + (qq & Kmask)) * P::N);
+      }
     }
-    sm_st<P>(sm, tile, swz(o, a.logC), v);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint32_t o = o0 + k * blockDim.x;
+      if (o < tile) {
+        if (a.bnd) v[k] = fe_mul<P>(v[k], tw[k]);
+        sm_st<P>(sm, tile, swz(o, a.logC), v[k]);
+      }
+    }
   }
   __syncthreads();
 
@@ -185,9 +204,9 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(NttPassArgs a, Nt
   for (uint32_t li = 0; li < a.nd; li++) {
     uint32_t d = layer_width(a.dpack, li);
     off -= d;
-    if (d == 3) ntt_layer<P, 3>(sm, a, c, li, off, done);
-    else if (d == 2) ntt_layer<P, 2>(sm, a, c, li, off, done);
-    else ntt_layer<P, 1>(sm, a, c, li, off, done);
+    if (d == 3) ntt_layer<P, 3>(sm, smw, a, c, li, off, done);
+    else if (d == 2) ntt_layer<P, 2>(sm, smw, a, c, li, off, done);
+    else ntt_layer<P, 1>(sm, smw, a, c, li, off, done);
     done += d;
     __syncthreads();
   }
@@ -371,8 +390,8 @@ int run_plan(const NttPlan& pl, uint32_t* d_data, size_t batch) {
   memcpy(c.w8.v, pl.consts, 32); memcpy(c.w4.v, pl.consts + 8, 32); memcpy(c.w8_3.v, pl.consts + 16, 32);
   static bool attr_set = false;
   if (!attr_set) {
-    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<FrBN254>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4 << kLogTile));
-    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<FrBLS381>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4 << kLogTile));
+    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<FrBN254>, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 * 4 << kLogTile) + (32 << kMaxB)));
+    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<FrBLS381>, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 * 4 << kLogTile) + (32 << kMaxB)));
     attr_set = true;
   }
   const uint32_t* src = d_data;
@@ -391,7 +410,7 @@ int run_plan(const NttPlan& pl, uint32_t* d_data, size_t batch) {
     uint32_t threads = tile / 8 < 32 ? 32 : (tile / 8 > (uint32_t)kThreads ? kThreads : tile / 8);
     dim3 grid((unsigned)(1ull << (pp.logQ - pp.logC)), (unsigned)batch);
     KzProf prof(1);
-    ntt_pass_kernel<P><<<grid, threads, (size_t)tile * 32, cx.stream>>>(a, c);
+    ntt_pass_kernel<P><<<grid, threads, (size_t)tile * 32 + (pp.nd > 1 ? (32u << pp.b) : 0u), cx.stream>>>(a, c);
     KZ_LAUNCHED();
     prof.stop(1, (double)n * (double)batch);
     src = dst;

@@ -14,7 +14,7 @@ def main():
     sm = info["sm_count"]
     res = {}
     if "micro" in what:
-        for kind, name in ((0, "imad_wide"), (5, "imad_wide+2alu"), (6, "imad_wide+4alu"), (7, "imad32"), (1, "fe_mul_bn254"), (2, "fe_mul_bls381"), (3, "madd_bn254"), (4, "madd_bls381")):
+        for kind, name in ((0, "imad_wide"), (5, "imad_wide+2alu"), (6, "imad_wide+4alu"), (7, "imad32"), (8, "dfma"), (9, "dfma+add64"), (10, "dfma+wide/2"), (11, "dfma+add64+wide/2"), (1, "fe_mul_bn254"), (2, "fe_mul_bls381"), (3, "madd_bn254"), (4, "madd_bls381")):
             for threads, bps in ((256, 2), (128, 4), (256, 4), (128, 2)):
                 iters = 400 if kind in (3, 4) else 2000
                 ms, ops = _ffi.microbench(kind, sm * bps, threads, iters)
