@@ -214,6 +214,8 @@ def run_gpu(args):
     dist = None
     torch = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)

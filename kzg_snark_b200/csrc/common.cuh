@@ -16,6 +16,8 @@ struct KzgpuCtx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;     // chunked host->device uploads overlapped with compute
+  cudaEvent_t copy_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   uint64_t launches = 0;
   char err[512] = {0};
   // per-kernel profiling (bench.py roofline): enabled -> events around selected launches

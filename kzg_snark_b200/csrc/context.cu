@@ -220,6 +220,8 @@ int kzgpu_init(int device) {
   cx.sm_count = prop.multiProcessorCount;
   KZ_CUDA(cudaStreamCreateWithFlags(&cx.own_stream, cudaStreamNonBlocking));
   cx.stream = cx.own_stream;
+  KZ_CUDA(cudaStreamCreateWithFlags(&cx.copy_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 4; k++) KZ_CUDA(cudaEventCreateWithFlags(&cx.copy_ev[k], cudaEventDisableTiming));
   KZ_CUDA(cudaEventCreate(&cx.ev0));
   KZ_CUDA(cudaEventCreate(&cx.ev1));
   cx.device = device;
@@ -238,6 +240,8 @@ int kzgpu_shutdown(void) {
   cudaEventDestroy(cx.ev0);
   cudaEventDestroy(cx.ev1);
   cudaStreamDestroy(cx.own_stream);
+  cudaStreamDestroy(cx.copy_stream);
+  for (int k = 0; k < 4; k++) cudaEventDestroy(cx.copy_ev[k]);
   cx.stream = cx.own_stream = nullptr;
   cx.inited = false;
   cx.device = -1;

@@ -483,12 +483,14 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __r
                                                             const uint32_t* __restrict__ entries,
                                                             const uint32_t* __restrict__ t_start, const uint32_t* __restrict__ t_len,
                                                             const uint32_t* __restrict__ t_dest, const uint32_t* __restrict__ n_tasks,
-                                                            uint32_t* __restrict__ buckets, uint32_t* __restrict__ partials) {
+                                                            uint32_t add_existing, uint32_t* __restrict__ buckets,
+                                                            uint32_t* __restrict__ partials) {
   using P = typename Cfg::Fp;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= *n_tasks) return;
   uint32_t e = t_start[t], len = t_len[t], dest = t_dest[t];
-  XYZZ<P> acc = xyzz_inf<P>();
+  // later chunks of a chunked MSM continue from the bucket's running sum
+  XYZZ<P> acc = (add_existing && (dest >> 31)) ? ld_xyzz<P>(buckets, dest & 0x7fffffffu) : xyzz_inf<P>();
   uint32_t ent = __ldg(entries + e);
   Affine<P> nxt = ld_affine<P>(points, ent & 0x7fffffffu);
   uint32_t nneg = ent >> 31;
@@ -521,7 +523,7 @@ template <class P> __device__ __forceinline__ XYZZ<P> shfl_xyzz(const XYZZ<P>& a
 template <class Cfg>
 __global__ void __launch_bounds__(128) msm_merge_kernel(const uint32_t* __restrict__ ntasks, const uint32_t* __restrict__ task_off,
                                                        const uint32_t* __restrict__ multi_count,
-                                                       const uint32_t* __restrict__ multi_list,
+                                                       const uint32_t* __restrict__ multi_list, uint32_t add_existing,
                                                        const uint32_t* __restrict__ partials, uint32_t* __restrict__ buckets) {
   using P = typename Cfg::Fp;
   const uint32_t lane = threadIdx.x & 31;
@@ -533,6 +535,7 @@ __global__ void __launch_bounds__(128) msm_merge_kernel(const uint32_t* __restri
     uint32_t nt = ntasks[b], off = task_off[b];
     XYZZ<P> acc = xyzz_inf<P>();
     for (uint32_t j = lane; j < nt; j += 32) acc = xyzz_add<P>(acc, ld_xyzz<P>(partials, off + j));
+    if (add_existing && lane == 0) acc = xyzz_add<P>(acc, ld_xyzz<P>(buckets, b));
     for (int d = 16; d > 0; d >>= 1) {
       XYZZ<P> o = shfl_xyzz<P>(acc, d);
       acc = xyzz_add<P>(acc, o);
@@ -758,11 +761,24 @@ uint32_t choose_table_c(size_t n, int bits, size_t point_bytes) {
 }
 
 template <class Cfg>
-int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, int mode, uint32_t* d_out) {
+int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, int mode, uint32_t* d_out,
+             const uint64_t* h_scalars = nullptr) {
   using P = typename Cfg::Fp;
   using R = typename Cfg::Fr;
   KzgpuCtx& cx = kz_ctx();
   cudaStream_t st = cx.stream;
+  // Host scalars (the e2e entry point): the upload is split into chunks on the copy stream and the
+  // MSM runs chunk by chunk into the same buckets, so that all but the first chunk's PCIe time
+  // hides behind the sort + accumulate of the previous chunk.
+  const uint32_t nchunks = (h_scalars && n >= (1u << 20)) ? 4u : 1u;
+  const size_t chunk_n = kz_div_up(n, nchunks);
+  if (h_scalars && n) {
+    for (uint32_t k = 0; k < nchunks; k++) {
+      size_t lo = k * chunk_n, cnt = lo < n ? (n - lo < chunk_n ? n - lo : chunk_n) : 0;
+      if (cnt) KZ_CUDA(cudaMemcpyAsync((void*)(d_scalars + lo * 8), h_scalars + lo * 4, cnt * 32, cudaMemcpyHostToDevice, cx.copy_stream));
+      KZ_CUDA(cudaEventRecord(cx.copy_ev[k], cx.copy_stream));
+    }
+  }
   const bool tabled = srs.c_tab != 0;
   const uint32_t c = tabled ? srs.c_tab : choose_c(n, R::BITS);
   const uint32_t W = (R::BITS + 1 + c - 1) / c;          // digits per scalar
@@ -776,7 +792,7 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   while (((nb + (1ull << f) - 1) >> f) > kMaxCoarse && f < 13) f++;
   const uint32_t ncoarse = (uint32_t)((nb + (1ull << f) - 1) >> f);
   if (ncoarse > kMaxCoarse) return kz_fail(KZGPU_EINVAL, "MSM window c=%u gives too many buckets (%zu)", c, nb);
-  const size_t max_entries = (size_t)n * W;
+  const size_t max_entries = (size_t)chunk_n * W;
   if (max_entries >= 0xffffffffull) return kz_fail(KZGPU_EINVAL, "MSM of %zu points x %u digits exceeds 2^32 entries", n, W);
   const size_t max_sort_blocks = max_entries / kSortChunk + ncoarse + 1;
   int rc;
@@ -808,8 +824,6 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   uint32_t* blk_off = coarse_cur + kMaxCoarse;              // ncoarse + 1 entries
   uint32_t* flag = (uint32_t*)g_ws.flag.p;
 
-  KZ_CUDA(cudaMemsetAsync(counts, 0, nb * 4, st));
-  KZ_CUDA(cudaMemsetAsync(coarse_counts, 0, kMaxCoarse * 4, st));
   KZ_CUDA(cudaMemsetAsync(flag, 0, 4, st));
   SortGeom geo;
   geo.c = c; geo.W = W; geo.B = B; geo.f = f; geo.ncoarse = ncoarse; geo.tabled = tabled ? 1u : 0u;
@@ -821,6 +835,19 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
     uint32_t bit = w * c + (c - 1);
     if (bit < 256) doff.w[bit >> 5] |= 1u << (bit & 31);
   }
+  const uint32_t* d_scalars_all = d_scalars;
+  const size_t n_all = n, first_all = first;
+  for (uint32_t chunk = 0; chunk < nchunks; chunk++) {
+  const size_t c_lo = chunk * chunk_n;
+  n = c_lo < n_all ? (n_all - c_lo < chunk_n ? n_all - c_lo : chunk_n) : 0;
+  if (chunk && !n) break;
+  d_scalars = d_scalars_all + c_lo * 8;
+  first = first_all + c_lo;
+  geo.first = (uint32_t)first;
+  const uint32_t add_existing = chunk ? 1u : 0u;
+  if (h_scalars) KZ_CUDA(cudaStreamWaitEvent(st, cx.copy_ev[chunk], 0));
+  KZ_CUDA(cudaMemsetAsync(counts, 0, nb * 4, st));
+  KZ_CUDA(cudaMemsetAsync(coarse_counts, 0, kMaxCoarse * 4, st));
   KzProf prof_sort(2);
   if (n) {
     const unsigned tiles = (unsigned)kz_div_up(n, kSortTile);
@@ -884,19 +911,24 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
                                                                 (uint32_t*)g_ws.t_start.p, (uint32_t*)g_ws.t_len.p,
                                                                 (uint32_t*)g_ws.t_dest.p);
   KZ_LAUNCHED();
-  prof_sort.stop(11, (double)n);
+  prof_sort.stop(chunk == 0 ? 1 : 0, (double)n);
   KzProf prof_acc(0);
   msm_accumulate_kernel<Cfg><<<(unsigned)kz_div_up(max_tasks, 128), 128, 0, st>>>(
       srs.d_points, entries, (uint32_t*)g_ws.t_start.p, (uint32_t*)g_ws.t_len.p, (uint32_t*)g_ws.t_dest.p, size_cursor,
-      (uint32_t*)g_ws.buckets.p, (uint32_t*)g_ws.tparts.p);
+      add_existing, (uint32_t*)g_ws.buckets.p, (uint32_t*)g_ws.tparts.p);
   KZ_LAUNCHED();
-  prof_acc.stop(1, (double)n * W);
+  prof_acc.stop(chunk == 0 ? 1 : 0, (double)n * W);
+  KzProf prof_merge(3);
+  msm_merge_kernel<Cfg><<<cx.sm_count * 4, 128, 0, st>>>(ntasks, task_off, multi_count, multi_list, add_existing,
+                                                        (uint32_t*)g_ws.tparts.p, (uint32_t*)g_ws.buckets.p);
+  KZ_LAUNCHED();
+  if (!add_existing) {
+    msm_clear_empty_kernel<Cfg><<<(unsigned)kz_div_up(nb, 256), 256, 0, st>>>(ntasks, (uint32_t)nb, (uint32_t*)g_ws.buckets.p);
+    KZ_LAUNCHED();
+  }
+  prof_merge.stop(0, 0.0);
+  }  // chunks
   KzProf prof_red(3);
-  msm_merge_kernel<Cfg><<<cx.sm_count * 4, 128, 0, st>>>(ntasks, task_off, multi_count, multi_list, (uint32_t*)g_ws.tparts.p,
-                                                        (uint32_t*)g_ws.buckets.p);
-  KZ_LAUNCHED();
-  msm_clear_empty_kernel<Cfg><<<(unsigned)kz_div_up(nb, 256), 256, 0, st>>>(ntasks, (uint32_t)nb, (uint32_t*)g_ws.buckets.p);
-  KZ_LAUNCHED();
   msm_reduce_kernel<Cfg><<<(unsigned)kz_div_up((size_t)cpw * Wb, 128), 128, 0, st>>>((uint32_t*)g_ws.buckets.p, B, CH, cpw, Wb,
                                                                                     (uint32_t*)g_ws.partials.p);
   KZ_LAUNCHED();
@@ -913,7 +945,7 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   }
   msm_final_kernel<Cfg><<<1, 32, 0, st>>>(lvl_in, Wb, c, mode, d_out);
   KZ_LAUNCHED();
-  prof_red.stop(3, (double)nb);
+  prof_red.stop(1, (double)nb);
   uint32_t hflag = 0;
   KZ_CUDA(cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, st));
   KZ_CUDA(cudaStreamSynchronize(st));
@@ -922,11 +954,12 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
 }
 
 template <class Cfg>
-int msm_affine(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, uint64_t* out_xy, int* is_inf) {
+int msm_affine(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, uint64_t* out_xy, int* is_inf,
+               const uint64_t* h_scalars = nullptr) {
   using P = typename Cfg::Fp;
   int rc;
   if ((rc = g_ws.result.ensure((2 * P::N + 1) * 4))) return rc;
-  if ((rc = msm_core<Cfg>(srs, first, d_scalars, n, 1, (uint32_t*)g_ws.result.p))) return rc;
+  if ((rc = msm_core<Cfg>(srs, first, d_scalars, n, 1, (uint32_t*)g_ws.result.p, h_scalars))) return rc;
   uint32_t h[2 * 12 + 1];
   KZ_CUDA(cudaMemcpy(h, g_ws.result.p, (2 * P::N + 1) * 4, cudaMemcpyDeviceToHost));
   memcpy(out_xy, h, 2 * P::N * 4);
@@ -1061,15 +1094,16 @@ void kz_msm_release() {
 }
 
 // used by poly.cu (open): MSM of device-resident scalars against a handle
-int kz_msm_dev_internal(uint64_t handle, size_t first, const uint32_t* d_scalars, size_t n, uint64_t* out_xy, int* is_inf) {
+int kz_msm_dev_internal(uint64_t handle, size_t first, const uint32_t* d_scalars, size_t n, uint64_t* out_xy, int* is_inf,
+                        const uint64_t* h_scalars) {
   const Srs* s = find_srs(handle);
   if (!s) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle %llu", (unsigned long long)handle);
   if (first + n > s->n)
     return kz_fail(KZGPU_ERANGE, "Polynomial degree %zu exceeds maximum allowed degree %zu", first + n - 1, s->n - 1);
   int rc = set_smem_attrs();
   if (rc) return rc;
-  if (s->curve == KZGPU_BN254) return msm_affine<BN254Cfg>(*s, first, d_scalars, n, out_xy, is_inf);
-  return msm_affine<BLS381Cfg>(*s, first, d_scalars, n, out_xy, is_inf);
+  if (s->curve == KZGPU_BN254) return msm_affine<BN254Cfg>(*s, first, d_scalars, n, out_xy, is_inf, h_scalars);
+  return msm_affine<BLS381Cfg>(*s, first, d_scalars, n, out_xy, is_inf, h_scalars);
 }
 
 int kz_srs_curve(uint64_t handle) {
@@ -1151,16 +1185,16 @@ int kzgpu_srs_read(uint64_t handle, size_t first, size_t count, uint64_t* affine
 int kzgpu_msm_dev(uint64_t handle, size_t first, const uint64_t* d_scalars, size_t n, uint64_t* out_affine_xy, int* is_inf) {
   KZ_REQUIRE_INIT();
   if (!out_affine_xy || (n && !d_scalars)) return kz_fail(KZGPU_EINVAL, "null pointer");
-  return kz_msm_dev_internal(handle, first, (const uint32_t*)d_scalars, n, out_affine_xy, is_inf);
+  return kz_msm_dev_internal(handle, first, (const uint32_t*)d_scalars, n, out_affine_xy, is_inf, nullptr);
 }
 
 int kzgpu_msm(uint64_t handle, size_t first, const uint64_t* scalars, size_t n, uint64_t* out_affine_xy, int* is_inf) {
   KZ_REQUIRE_INIT();
   if (!out_affine_xy || (n && !scalars)) return kz_fail(KZGPU_EINVAL, "null pointer");
-  uint32_t* d = nullptr;
-  int rc = upload_scalars(scalars, n, &d);
+  // the upload happens inside the MSM, chunked and overlapped with the compute
+  int rc = g_ws.scal.ensure(n * 32 + 32);
   if (rc) return rc;
-  return kz_msm_dev_internal(handle, first, d, n, out_affine_xy, is_inf);
+  return kz_msm_dev_internal(handle, first, (const uint32_t*)g_ws.scal.p, n, out_affine_xy, is_inf, scalars);
 }
 
 int kzgpu_msm_batch(uint64_t handle, const uint64_t* scalars, const size_t* lens, size_t k, uint64_t* out_affine_xy, int* is_inf) {
@@ -1176,7 +1210,7 @@ int kzgpu_msm_batch(uint64_t handle, const uint64_t* scalars, const size_t* lens
   if (rc) return rc;
   size_t off = 0;
   for (size_t j = 0; j < k; j++) {
-    rc = kz_msm_dev_internal(handle, 0, d + off * 8, lens[j], out_affine_xy + j * 2 * L, is_inf ? is_inf + j : nullptr);
+    rc = kz_msm_dev_internal(handle, 0, d + off * 8, lens[j], out_affine_xy + j * 2 * L, is_inf ? is_inf + j : nullptr, nullptr);
     if (rc) return rc;
     off += lens[j];
   }

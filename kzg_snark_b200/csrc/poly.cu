@@ -13,7 +13,8 @@
 #include <vector>
 #include <cstring>
 
-int kz_msm_dev_internal(uint64_t handle, size_t first, const uint32_t* d_scalars, size_t n, uint64_t* out_xy, int* is_inf);
+int kz_msm_dev_internal(uint64_t handle, size_t first, const uint32_t* d_scalars, size_t n, uint64_t* out_xy, int* is_inf,
+                        const uint64_t* h_scalars);
 int kz_srs_curve(uint64_t handle);
 
 namespace {
@@ -138,7 +139,7 @@ int open_impl(uint64_t handle, bool do_msm, const uint64_t* polys, const size_t*
   }
   if (maxlen == 0) {           // all-zero combination: witness is the zero polynomial -> Z1 (kzg.py:109)
     if (do_msm) {
-      int rc = kz_msm_dev_internal(handle, 0, nullptr, 0, out_xy, is_inf);
+      int rc = kz_msm_dev_internal(handle, 0, nullptr, 0, out_xy, is_inf, nullptr);
       if (rc) return rc;
     }
     if (quot_len) *quot_len = 0;
@@ -168,7 +169,7 @@ int open_impl(uint64_t handle, bool do_msm, const uint64_t* polys, const size_t*
   if (quotient && maxlen > 1) KZ_CUDA(cudaMemcpyAsync(quotient, d_T + P::N, (maxlen - 1) * 32, cudaMemcpyDeviceToHost, cx.stream));
   if (quot_len) *quot_len = maxlen - 1;
   KZ_CUDA(cudaStreamSynchronize(cx.stream));
-  if (do_msm) return kz_msm_dev_internal(handle, 0, d_T + P::N, maxlen - 1, out_xy, is_inf);
+  if (do_msm) return kz_msm_dev_internal(handle, 0, d_T + P::N, maxlen - 1, out_xy, is_inf, nullptr);
   return 0;
 }
 

@@ -246,6 +246,32 @@ def test_srs_generate_and_tau_identity(dev, curve):
     srs.destroy()
 
 
+def test_msm_full_size_chunked_upload_and_heavy_buckets(dev):
+    """Sizes at which the two-level sort runs its full geometry and the host-scalar entry point
+    uploads in four overlapped chunks that accumulate into the same buckets: tau-identity
+    (kzg.py:108) for uniform, all-equal (one huge bucket per window, split + merged across
+    chunks) and witness-like scalars; host-buffer and device-resident calls agree."""
+    from kzg_snark_b200 import _ffi
+    from kzg_snark_b200.limbs import random_scalars, ints_to_limbs
+    cv = get_curve("bn254")
+    tau = 0x1D2C3B4A5F6E7D8C9BA % cv.r
+    n = (1 << 20) + 77
+    srs = dev.Srs.generate("bn254", tau, n)
+    rng = random.Random(5)
+    uniform = random_scalars(n, cv.r, seed=21)
+    same = np.tile(ints_to_limbs([rng.randrange(cv.r)], cv.r), (n, 1))
+    skew = uniform.copy(); skew[::2] = 0; skew[1::4, 1:] = 0; skew[1::4, 0] &= np.uint64(0xFFFF)
+    for sc in (uniform, same, skew):
+        exp = cv.normalize(cv.multiply(cv.G1, poly_eval(I(sc), tau, cv.r)))
+        out, inf = dev.msm(srs, sc)                                   # chunked H2D inside
+        assert point_of(cv, out, inf, 4) == exp
+        d = _ffi.DeviceBuffer(n * 32).upload(np.ascontiguousarray(sc))
+        out2, inf2 = dev.msm_dev(srs, d, n)                           # single pass, resident
+        d.free()
+        assert point_of(cv, out2, inf2, 4) == exp
+    srs.destroy()
+
+
 # ------------------------------------------------------------------ open
 @pytest.mark.parametrize("curve", CURVE_NAMES)
 @pytest.mark.parametrize("lens", [[5], [1], [4, 9, 2], [70, 64, 65, 1, 130], [5000, 4097]])
