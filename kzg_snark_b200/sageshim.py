@@ -16,6 +16,13 @@ Semantics follow Sage where the reference relies on them:
 
 import random as _random
 
+_rng = _random.Random()
+
+
+def seed(s):
+    """Re-seed the generator behind GF(q).random_element() (set_random_seed in Sage)."""
+    _rng.seed(s)
+
 
 class FieldElement:
     __slots__ = ("n", "F")
@@ -162,7 +169,7 @@ class GFShim:
     characteristic = order
 
     def random_element(self):
-        return FieldElement(_random.randrange(self.q), self)
+        return FieldElement(_rng.randrange(self.q), self)
 
     def _factors(self):
         if self.q in _KNOWN:
@@ -580,3 +587,144 @@ class PolyRingShim:
 
 def PolynomialRing(F, name="X"):
     return PolyRingShim(F, name)
+
+
+# --------------------------------------------------------------------------- vector / matrix / prod
+def prod(items, start=1):
+    """sage.all.prod: product of an iterable (marlin/prover.py:63-64, marlin/encoder.py:158)."""
+    out = start
+    for it in items:
+        out = out * it
+    return out
+
+
+class Vector:
+    """vector(F, entries): only what marlin/encoder.py:202-207 needs (A * z, indexing, len)."""
+
+    def __init__(self, F, entries):
+        self.F = F
+        self.v = [F(e) for e in entries]
+
+    def __len__(self):
+        return len(self.v)
+
+    def __getitem__(self, i):
+        return self.v[i]
+
+    def __iter__(self):
+        return iter(self.v)
+
+    def list(self):
+        return list(self.v)
+
+    def __repr__(self):
+        return "(" + ", ".join(repr(e) for e in self.v) + ")"
+
+
+def vector(F, entries=None):
+    if entries is None:
+        F, entries = entries, F
+        F = entries[0].parent()
+    return Vector(F, entries)
+
+
+class Matrix:
+    """Dense matrix over GF(q) with the methods the Marlin indexer/encoder call: nrows, ncols,
+    [i, j] / [i][j] access, .T, * vector, rows(), columns() (marlin/indexer.py:48-52,
+    marlin/encoder.py:37,98-125,205-207)."""
+
+    def __init__(self, F, rows):
+        self.F = F
+        self.r = [[F(e) for e in row] for row in rows]
+
+    def nrows(self):
+        return len(self.r)
+
+    def ncols(self):
+        return len(self.r[0]) if self.r else 0
+
+    def dimensions(self):
+        return (self.nrows(), self.ncols())
+
+    def nonzero_positions(self):
+        """(i, j) of non-zero entries in row-major order, as Sage returns them (marlin/encoder.py:40,101)."""
+        return [(i, j) for i, row in enumerate(self.r) for j, e in enumerate(row) if e.n]
+
+    def base_ring(self):
+        return self.F
+
+    def __getitem__(self, idx):
+        if isinstance(idx, tuple):
+            i, j = idx
+            if isinstance(i, slice) or isinstance(j, slice):
+                rows = self.r[i] if isinstance(i, slice) else [self.r[i]]
+                sub = [row[j] if isinstance(j, slice) else [row[j]] for row in rows]
+                return Matrix(self.F, sub)
+            return self.r[i][j]
+        return self.r[idx]
+
+    def __setitem__(self, idx, val):
+        if isinstance(idx, tuple):
+            i, j = idx
+            if isinstance(i, slice) and not isinstance(j, slice):      # M[:, j] = column
+                col = val.column(0) if isinstance(val, Matrix) else list(val)
+                for k, row in enumerate(self.r[i]):
+                    row[j] = self.F(col[k])
+                return
+            self.r[i][j] = self.F(val)
+        else:
+            self.r[idx] = [self.F(e) for e in val]
+
+    @property
+    def T(self):
+        return self.transpose()
+
+    def transpose(self):
+        return Matrix(self.F, [list(c) for c in zip(*self.r)]) if self.r else Matrix(self.F, [])
+
+    def rows(self):
+        return [list(r) for r in self.r]
+
+    def row(self, i):
+        return list(self.r[i])
+
+    def columns(self):
+        return [list(c) for c in zip(*self.r)]
+
+    def column(self, j):
+        return [row[j] for row in self.r]
+
+    def __copy__(self):
+        return Matrix(self.F, self.r)
+
+    def __mul__(self, o):
+        if isinstance(o, Vector):
+            q = self.F.q
+            ov = [e.n for e in o.v]
+            return Vector(self.F, [sum(a.n * b for a, b in zip(row, ov) if a.n) % q for row in self.r])
+        if isinstance(o, Matrix):
+            q = self.F.q
+            cols = o.columns()
+            return Matrix(self.F, [[sum(a.n * b.n for a, b in zip(row, col)) % q for col in cols] for row in self.r])
+        return Matrix(self.F, [[e * o for e in row] for row in self.r])
+
+    __rmul__ = __mul__
+
+    def __eq__(self, o):
+        return isinstance(o, Matrix) and self.r == o.r
+
+    def __hash__(self):
+        return id(self)
+
+    def __repr__(self):
+        return "\n".join("[" + " ".join(repr(e) for e in row) + "]" for row in self.r)
+
+
+def matrix(F, *args):
+    """matrix(F, rows) / matrix(F, nrows, ncols, flat_or_rows)."""
+    if len(args) == 1:
+        return Matrix(F, args[0])
+    nr, nc, data = args
+    if data and not isinstance(data[0], (list, tuple)):
+        data = [data[i * nc:(i + 1) * nc] for i in range(nr)]
+    return Matrix(F, data)

@@ -1,0 +1,237 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/ref_trace_*.json by running the REFERENCE'S OWN code here.
+
+Run in the BUILD container (where /root/reference is mounted):
+    python tests/golden/make_traces.py
+
+The reference's kzg.py, fft_ff.py, transcript.py, plonk/*.py and marlin/*.py are imported
+unmodified from /root/reference by oracle/refrun.py (SageMath and py_ecc replaced by the
+stand-ins described there) and every outermost call that crosses the hot-path boundary
+(KZG.commit, KZG.open, fft_ff, ifft_ff, fft_ff_interpolation) is recorded with its inputs and the
+reference's outputs (points normalised to affine):
+
+  ref_trace_kzg.json     configs[0]: setup(2^10) -> commit -> open -> check of a random degree-2^10
+                         polynomial, the main.py:17-36 demo, and kzg.py's edge behaviour (zero
+                         polynomial, zero coefficients, list inputs, multi-poly open, degree
+                         overflow message)
+  ref_trace_fft.json     fft_ff / ifft_ff / fft_ff_interpolation from fft_ff.py on n = 1 .. 2^8 (fft_ff also 2^10)
+  ref_trace_plonk.json   main.py:64-94: Indexer.preprocess, Prover.prove, Verifier.verify (accepts)
+  ref_trace_marlin.json  main.py:39-61 likewise
+  ref_plonk_normalized.json
+                         the reference PLONK prover run once more with commitments NORMALISED to
+                         (x, y, 1) before they reach the transcript -- what any drop-in returning
+                         canonical affine points produces -- with the blinding scalars, challenges'
+                         inputs and the full proof, for the bit-exact check of kzg_snark_b200.plonk
+
+All fixtures are deterministic (seeded) and small (< 1 MB together).
+"""
+import json
+import os
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import fixtures, refrun                 # noqa: E402
+from kzg_snark_b200 import sageshim                 # noqa: E402
+
+REF_CS = "/root/reference/constraint-system"
+SEED = 20261018
+
+
+def dump(name, obj):
+    path = os.path.join(HERE, name)
+    with open(path, "w") as f:
+        json.dump(obj, f, separators=(",", ":"))
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB, {len(obj.get('calls', []))} calls")
+
+
+def trace_kzg():
+    with refrun.ReferenceRun(seed=SEED) as rr:
+        kzg = rr.kzg.KZG(curve_type="bn254")
+        Fq, R, X = kzg.Fq, kzg.R, kzg.X
+        notes = {}
+        # main.py:17-36
+        ck, rk = kzg.setup(max_degree=10)
+        polys = [1 + 2 * X + 3 * X**2, 4 + 5 * X**3]
+        comm = kzg.commit(ck, polys)
+        proof = kzg.open(ck, polys, 7, 42)
+        notes["demo_check"] = bool(kzg.check(rk, comm, 7, [p(7) for p in polys], proof, 42))
+        notes["demo_check_wrong_eval"] = bool(kzg.check(rk, comm, 7, [polys[0](7) + 1, polys[1](7)], proof, 42))
+        # edge behaviour on the same key
+        edge = [R(0), R([0, 0, 5, 0, Fq(-1)]), R([Fq.random_element() for _ in range(11)]), R(3)]
+        kzg.commit(ck, edge)
+        kzg.commit(ck, [[1, 2, 3], [0, 0, 0, 7]])                       # coefficient lists (kzg.py:94-95)
+        kzg.commit(ck, [])
+        kzg.open(ck, edge, Fq.random_element(), Fq.random_element())
+        kzg.open(ck, [edge[3]], 5, 9)                                   # constant polynomial -> quotient 0 -> Z1
+        try:
+            kzg.commit(ck, [X**11])
+            notes["overflow"] = None
+        except ValueError as e:
+            notes["overflow"] = str(e)
+        notes["batch_check"] = bool(kzg.batch_check(
+            rk, [comm, comm[:1]], [7, 3], [[p(7) for p in polys], [polys[0](3)]],
+            [proof, kzg.open(ck, polys[:1], 3, 11)], [42, 11]))
+        # configs[0]: degree 2^10
+        t0 = time.time()
+        ck2, rk2 = kzg.setup(max_degree=1 << 10)
+        big = R([Fq.random_element() for _ in range((1 << 10) + 1)])
+        z, xi = Fq.random_element(), Fq.random_element()
+        c2 = kzg.commit(ck2, [big])
+        pr2 = kzg.open(ck2, [big], z, xi)
+        notes["config0_check"] = bool(kzg.check(rk2, c2, z, [big(z)], pr2, xi))
+        notes["config0_seconds"] = round(time.time() - t0, 2)
+        assert notes["demo_check"] and notes["config0_check"] and notes["batch_check"] and not notes["demo_check_wrong_eval"]
+        dump("ref_trace_kzg.json", {"source": "reference kzg.py run by oracle/refrun.py", "seed": SEED, "curve": "bn254",
+                                    "notes": notes, "keys": rr.keys, "calls": rr.trace})
+
+
+def trace_fft():
+    with refrun.ReferenceRun(seed=SEED + 1) as rr:
+        kzg = rr.kzg.KZG(curve_type="bn254")
+        Fq = kzg.Fq
+        q = Fq.order()
+        notes = {}
+        for logn in (0, 1, 2, 3, 4, 5, 6, 7, 8, 10):
+            n = 1 << logn
+            w = Fq(5) ** ((q - 1) // n)
+            vals = [Fq.random_element() for _ in range(n)]
+            rr.fft_ff.fft_ff(vals, w, Fq)
+            if logn > 8:
+                continue
+            rr.fft_ff.ifft_ff(vals, w, Fq)
+            if n >= 2:
+                sparse = [Fq(0)] * n
+                sparse[1] = Fq(1)
+                rr.fft_ff.fft_ff(sparse, w, Fq)                          # delta_1 -> [w^k]
+                rr.fft_ff.fft_ff_interpolation(vals, w, Fq)
+        one = [Fq(7)]
+        notes["n1_returns_same_object"] = rr.fft_ff.fft_ff(one, Fq(1), Fq) is one       # fft_ff.py:16-17
+        for bad, key in (([Fq(1)] * 3, "assert_not_pow2"), ([Fq(1)] * 8, "assert_short_order")):
+            try:
+                rr.fft_ff.fft_ff_interpolation(bad, Fq(5) ** ((q - 1) // 4), Fq)
+                notes[key] = None
+            except AssertionError as e:
+                notes[key] = str(e)
+        dump("ref_trace_fft.json", {"source": "reference fft_ff.py run by oracle/refrun.py", "seed": SEED + 1,
+                                    "field": "bn254_r", "notes": notes, "calls": rr.trace})
+
+
+def _plonk_inputs(Fq):
+    inst = fixtures.load_plonk_instance(os.path.join(REF_CS, "PLONK_ARITHMETIZATION_INSTANCE.pkl"))
+    f = lambda v: [Fq(x) for x in v]                                     # noqa: E731
+    w = f(inst["w"])
+    return [f(inst[k]) for k in ("qM", "qL", "qR", "qO", "qC")], list(inst["perm"]), w[:5], w[5:]
+
+
+def enc_proof(rr, proof):
+    out = {}
+    for sec, d in proof.items():
+        out[sec] = {k: (rr.enc_point(v) if isinstance(v, tuple) else rr.enc_scalar(v)) for k, v in d.items()}
+    return out
+
+
+def trace_plonk():
+    with refrun.ReferenceRun(seed=SEED + 2) as rr:
+        Fq = rr.kzg.KZG("bn254").Fq
+        sel, perm, x, wit = _plonk_inputs(Fq)
+        n = len(sel[0])
+        t0 = time.time()
+        ipk, ivk = rr.load("plonk.indexer").Indexer(curve_type="bn254").preprocess(*sel, perm, max_degree=n + 5)
+        t1 = time.time()
+        proof = rr.load("plonk.prover").Prover(curve_type="bn254").prove(ipk, x, wit)
+        t2 = time.time()
+        V = rr.load("plonk.verifier").Verifier
+        ok = V(curve_type="bn254").verify(ivk, x, proof)
+        bad = {**proof, "evaluations": {**proof["evaluations"], "a": proof["evaluations"]["a"] + 1}}
+        rejected = not V(curve_type="bn254").verify(ivk, x, bad)
+        assert ok and rejected
+        dump("ref_trace_plonk.json", {
+            "source": "reference plonk/{indexer,prover,verifier}.py + kzg.py + fft_ff.py run by oracle/refrun.py",
+            "seed": SEED + 2, "curve": "bn254",
+            "notes": {"verify": bool(ok), "tampered_rejected": bool(rejected),
+                      "index_seconds": round(t1 - t0, 3), "prove_seconds": round(t2 - t1, 3)},
+            "keys": rr.keys, "calls": rr.trace, "proof": enc_proof(rr, proof)})
+
+
+def trace_marlin():
+    with refrun.ReferenceRun(seed=SEED + 3) as rr:
+        Fq = rr.kzg.KZG("bn254").Fq
+        inst = fixtures.load_r1cs_instance(os.path.join(REF_CS, "R1CS_INSTANCE.pkl"))
+        A, B, C = (sageshim.matrix(Fq, inst[k]) for k in "ABC")
+        z = [Fq(v) for v in inst["z"]]
+        x, w = z[:5], z[5:]
+        t0 = time.time()
+        ipk, ivk = rr.load("marlin.indexer").Indexer(curve_type="bn254").preprocess(A, B, C, max_degree=200)
+        t1 = time.time()
+        proof = rr.load("marlin.prover").Prover(curve_type="bn254").prove(ipk, x, w)
+        t2 = time.time()
+        ok = rr.load("marlin.verifier").Verifier(curve_type="bn254").verify(ivk, x, proof)
+        assert ok
+        dump("ref_trace_marlin.json", {
+            "source": "reference marlin/{indexer,prover,verifier}.py + kzg.py + fft_ff.py run by oracle/refrun.py",
+            "seed": SEED + 3, "curve": "bn254",
+            "notes": {"verify": bool(ok), "index_seconds": round(t1 - t0, 3), "prove_seconds": round(t2 - t1, 3)},
+            "keys": rr.keys, "calls": rr.trace})
+
+
+def trace_plonk_normalized():
+    """Reference prover + indexer with KZG.commit / KZG.open outputs normalised to (x, y, 1): the
+    transcript then hashes what a canonical-affine drop-in returns, so kzg_snark_b200.plonk can be
+    compared bit for bit (commitments, evaluations, opening proofs)."""
+    from oracle import pyecc_standin as E
+    with refrun.ReferenceRun(seed=SEED + 4) as rr:
+        KZG = rr.kzg.KZG
+
+        def norm(pt):
+            if E.is_inf(pt):
+                return E.Z1
+            x, y = E.normalize(pt)
+            return (E.FQ(x.n), E.FQ(y.n), E.FQ(1))
+
+        traced_commit, traced_open = KZG.commit, KZG.open
+        KZG.commit = lambda s, ck, polys: [norm(c) for c in traced_commit(s, ck, polys)]
+        KZG.open = lambda s, ck, polys, z, xi: norm(traced_open(s, ck, polys, z, xi))
+        draws = []
+        orig_rand = sageshim.GFShim.random_element
+
+        def rand(self):
+            v = orig_rand(self)
+            draws.append(hex(int(v)))
+            return v
+
+        sageshim.GFShim.random_element = rand
+        try:
+            Fq = KZG("bn254").Fq
+            sel, perm, x, wit = _plonk_inputs(Fq)
+            n = len(sel[0])
+            ipk, ivk = rr.load("plonk.indexer").Indexer(curve_type="bn254").preprocess(*sel, perm, max_degree=n + 5)
+            n_index_draws = len(draws)
+            proof = rr.load("plonk.prover").Prover(curve_type="bn254").prove(ipk, x, wit)
+            ok = rr.load("plonk.verifier").Verifier(curve_type="bn254").verify(ivk, x, proof)
+        finally:
+            sageshim.GFShim.random_element = orig_rand
+        assert ok
+        sub = ipk["subgroups"]
+        dump("ref_plonk_normalized.json", {
+            "source": "reference plonk prover with commitments normalised to (x,y,1) before the transcript",
+            "seed": SEED + 4, "curve": "bn254", "n": n,
+            "index_draws": draws[:n_index_draws],                 # tau, k1, k2 ... (kzg.py:67, plonk/encoder.py:83-84)
+            "prover_draws": draws[n_index_draws:],                # b1..b9, b10, b11 (plonk/prover.py:72-75,346)
+            "g": rr.enc_scalar(sub["g"]), "k1": rr.enc_scalar(sub["k1"]), "k2": rr.enc_scalar(sub["k2"]),
+            "sigma_star": [rr.enc_scalar(s) for s in ipk["sigma_star"]],
+            "index_polys": {k: rr.enc_poly(v) for k, v in ipk["polynomials"].items()},
+            "keys": rr.keys, "x": [rr.enc_scalar(v) for v in x], "w": [rr.enc_scalar(v) for v in wit],
+            "proof": enc_proof(rr, proof), "notes": {"verify": bool(ok)}})
+
+
+if __name__ == "__main__":
+    assert refrun.available(), "/root/reference not mounted"
+    trace_kzg()
+    trace_fft()
+    trace_plonk()
+    trace_marlin()
+    trace_plonk_normalized()

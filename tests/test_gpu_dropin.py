@@ -165,3 +165,31 @@ def test_tau_identity_large(logn):
     assert tuple(limbs_to_ints(out2.reshape(2, 4))) == exp
     for s in (srs, s0, s1):
         s.destroy()
+
+
+@pytest.mark.parametrize("name", ["ref_trace_kzg.json", "ref_trace_fft.json", "ref_trace_plonk.json", "ref_trace_marlin.json"])
+def test_dropin_reproduces_reference_trace(name):
+    """Every commit / open / fft_ff / ifft_ff / fft_ff_interpolation call the reference's own
+    kzg.py, plonk and marlin provers made (recorded in the build container by
+    tests/golden/make_traces.py) replayed through the GPU drop-in: identical affine points and
+    identical residues, call by call (configs[0], configs[3] and configs[4] call sites)."""
+    from trace_replay import load, replay
+    from kzg_snark_b200.kzg import KZG
+    from kzg_snark_b200.fft_ff import fft_ff, ifft_ff, fft_ff_interpolation
+    cv = get_curve("bn254")
+    kzg = KZG("bn254")
+    F, fq = kzg.Fq, kzg._codec.fq
+
+    def poly_ints(p):
+        return [int(c) for c in (p.list() if hasattr(p, "list") else p)]
+
+    trace = load(name)
+    n = replay(
+        trace,
+        make_key=lambda pts: [kzg.Z1 if p is None else (fq(p[0]), fq(p[1]), fq(1)) for p in pts],
+        commit=kzg.commit, open_=kzg.open,
+        fft=lambda v, w: fft_ff([F(x) for x in v], F(w), F),
+        ifft=lambda v, w: ifft_ff([F(x) for x in v], F(w), F),
+        interp=lambda v, w: fft_ff_interpolation([F(x) for x in v], F(w), F),
+        to_affine=lambda pt: aff(cv, pt), to_ints=poly_ints)
+    assert n == len(trace["calls"]) > 0
