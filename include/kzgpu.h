@@ -52,6 +52,9 @@ int kzgpu_alloc(void** d_ptr, size_t bytes);
 int kzgpu_free(void* d_ptr);
 int kzgpu_h2d(void* d_dst, const void* src, size_t bytes);
 int kzgpu_d2h(void* dst, const void* d_src, size_t bytes);
+/* stream-ordered device->device copy and fill (zero padding of coefficient vectors before an NTT) */
+int kzgpu_d2d(void* d_dst, const void* d_src, size_t bytes);
+int kzgpu_memset(void* d_dst, int byte, size_t bytes);
 int kzgpu_sync(void);
 /* page-locked host memory (cudaHostAlloc) so that host<->device copies of the timed e2e
  * path run at PCIe rate */
@@ -135,6 +138,41 @@ int kzgpu_open(uint64_t handle, const uint64_t* polys, const size_t* lens, size_
 int kzgpu_open_quotient(int field, const uint64_t* polys, const size_t* lens, size_t k,
                         const uint64_t* z, const uint64_t* xi, uint64_t* quotient,
                         size_t* quot_len, uint64_t* eval_out);
+
+/* same with the k polynomials already on the device: d_polys[j] -> lens[j] canonical coefficients */
+int kzgpu_open_dev(uint64_t handle, const uint64_t* const* d_polys, const size_t* lens, size_t k,
+                   const uint64_t* z, const uint64_t* xi, uint64_t* out_affine_xy, int* is_inf,
+                   uint64_t* eval_out);
+
+/* ---- polynomial kernels for the callers of commit / open ----------------- */
+/* The reference's PLONK prover does this work with Sage polynomial arithmetic between its
+ * kzg.commit / kzg.open / fft_ff_interpolation calls; these keep it on the device so that the
+ * polynomials never cross PCIe.  All vectors are canonical residues, 4 limbs per element. */
+/* out = p(x): poly(zeta) in round 4 (plonk/prover.py:161-166) */
+int kzgpu_poly_eval_dev(int field, const uint64_t* d_poly, size_t len, const uint64_t* x, uint64_t* out);
+/* d_out[i] = constant*[i == 0] + sum_j scalars[j] * d_polys[j][i] for i < out_len (coefficients
+ * beyond lens[j] read as 0): blinding terms (plonk/prover.py:84-86), the split of t(X) (:336-351)
+ * and the linearisation polynomial r(X) (:383-407).  constant may be NULL. */
+int kzgpu_poly_lincomb_dev(int field, uint64_t* d_out, size_t out_len, const uint64_t* const* d_polys,
+                           const size_t* lens, const uint64_t* scalars, size_t k, const uint64_t* constant);
+/* d_out[i] = scale * base^i, i < n (the subgroup H of plonk/encoder.py:45 and the evaluation coset);
+ * scale may be NULL (= 1) */
+int kzgpu_powers_dev(int field, uint64_t* d_out, size_t n, const uint64_t* base, const uint64_t* scale);
+/* Permutation grand product (plonk/prover.py:245-258): d_z[0] = 1,
+ * d_z[i+1] = d_z[i] * num_i / den_i over the wire values d_a/d_b/d_c (n each), the 3n permutation
+ * images d_sigma_star (plonk/encoder.py:137) and d_H[i] = g^i.  *zero_den = 1 if some den_i was 0
+ * (the reference raises ValueError at :254-255). */
+int kzgpu_plonk_permutation_dev(int field, size_t n, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_c,
+                                const uint64_t* d_sigma_star, const uint64_t* d_H, const uint64_t* k1,
+                                const uint64_t* k2, const uint64_t* beta, const uint64_t* gamma,
+                                uint64_t* d_z, int* zero_den);
+/* Quotient numerator over v_H on the evaluation coset {s * w_4n^i} (plonk/prover.py:297-310):
+ * d_evals = 15 device vectors of n4 = 4n evaluations in the order a, b, c, z, qM, qL, qR, qO, qC,
+ * S_sigma1, S_sigma2, S_sigma3, PI, L1, X (the coset points themselves); params = 9 elements
+ * alpha, beta, gamma, k1, k2, 1/v_H(x_0..3) (v_H has period 4 on the coset).  d_t receives
+ * t(x_i); one inverse coset NTT of it gives t's coefficients. */
+int kzgpu_plonk_quotient_dev(int field, size_t n4, const uint64_t* const* d_evals, const uint64_t* params,
+                             uint64_t* d_t);
 
 /* ---- diagnostics used by the parity tests and bench.py ---------------------------------- */
 /* elementwise Montgomery-core check: out[i] = a[i] op b[i] in the chosen field.

@@ -45,6 +45,8 @@ SIGNATURES = {
     "kzgpu_free": (ctypes.c_int, [ctypes.c_void_p]),
     "kzgpu_h2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "kzgpu_d2h": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "kzgpu_d2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "kzgpu_memset": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t]),
     "kzgpu_sync": (ctypes.c_int, []),
     "kzgpu_host_alloc": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]),
     "kzgpu_host_free": (ctypes.c_int, [ctypes.c_void_p]),
@@ -69,6 +71,12 @@ SIGNATURES = {
     "kzgpu_ntt_batch_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "kzgpu_open": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_void_p, _szp, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _intp, ctypes.c_void_p]),
     "kzgpu_open_quotient": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, _szp, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _szp, ctypes.c_void_p]),
+    "kzgpu_open_dev": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_void_p, _szp, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _intp, ctypes.c_void_p]),
+    "kzgpu_poly_eval_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
+    "kzgpu_poly_lincomb_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, _szp, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "kzgpu_powers_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
+    "kzgpu_plonk_permutation_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t] + [ctypes.c_void_p] * 10 + [_intp]),
+    "kzgpu_plonk_quotient_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "kzgpu_field_op": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "kzgpu_microbench": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]),
     "kzgpu_profile_enable": (ctypes.c_int, [ctypes.c_int]),

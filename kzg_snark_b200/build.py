@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libkzgpu.so")
-SOURCES = ["context.cu", "ntt.cu", "msm.cu", "poly.cu"]
+SOURCES = ["context.cu", "ntt.cu", "msm.cu", "poly.cu", "plonk.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

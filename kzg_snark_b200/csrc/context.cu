@@ -8,6 +8,7 @@
 void kz_ntt_release();
 void kz_msm_release();
 void kz_poly_release();
+void kz_plonk_release();
 
 KzgpuCtx& kz_ctx() {
   static KzgpuCtx ctx;
@@ -237,6 +238,7 @@ int kzgpu_shutdown(void) {
   kz_ntt_release();
   kz_msm_release();
   kz_poly_release();
+  kz_plonk_release();
   cudaEventDestroy(cx.ev0);
   cudaEventDestroy(cx.ev1);
   cudaStreamDestroy(cx.own_stream);
@@ -295,6 +297,18 @@ int kzgpu_d2h(void* dst, const void* d_src, size_t bytes) {
   KZ_REQUIRE_INIT();
   KZ_CUDA(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, kz_ctx().stream));
   KZ_CUDA(cudaStreamSynchronize(kz_ctx().stream));
+  return 0;
+}
+
+int kzgpu_d2d(void* d_dst, const void* d_src, size_t bytes) {
+  KZ_REQUIRE_INIT();
+  KZ_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, kz_ctx().stream));
+  return 0;
+}
+
+int kzgpu_memset(void* d_dst, int byte, size_t bytes) {
+  KZ_REQUIRE_INIT();
+  KZ_CUDA(cudaMemsetAsync(d_dst, byte, bytes, kz_ctx().stream));
   return 0;
 }
 

@@ -40,18 +40,39 @@ template <class P> __device__ __forceinline__ void stc_fe(uint32_t* p, const Fe<
   for (int i = 0; i < P::N / 4; i++) q[i] = make_uint4(a.v[4 * i], a.v[4 * i + 1], a.v[4 * i + 2], a.v[4 * i + 3]);
 }
 
-// out[i] = sum_j xipow[j] * poly_j[i]; meta = {offset_j, len_j} pairs (in elements)
+// out[i] = addend*[i==0] + sum_j mult[j] * poly_j[i]; meta = {device address of poly_j, len_j} pairs;
+// mult in Montgomery form, coefficients and addend canonical
 template <class P>
-__global__ void poly_combine_kernel(const uint32_t* polys, const uint64_t* meta, const uint32_t* xipow, uint32_t k, size_t maxlen,
+__global__ void poly_combine_kernel(const uint64_t* meta, const uint32_t* mult, uint32_t k, size_t outlen, const uint32_t* addend,
                                     uint32_t* out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= maxlen) return;
-  Fe<P> acc = fe_zero<P>();
+  if (i >= outlen) return;
+  Fe<P> acc = (addend && i == 0) ? ldc_fe<P>(addend) : fe_zero<P>();
   for (uint32_t j = 0; j < k; j++) {
-    uint64_t off = meta[2 * j], len = meta[2 * j + 1];
-    if (i < len) acc = fe_add<P>(acc, fe_mul<P>(ldc_fe<P>(polys + (off + i) * P::N), ldc_fe<P>(xipow + (size_t)j * P::N)));
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(meta[2 * j]);
+    uint64_t len = meta[2 * j + 1];
+    if (i < len) acc = fe_add<P>(acc, fe_mul<P>(ldc_fe<P>(base + i * P::N), ldc_fe<P>(mult + (size_t)j * P::N)));
   }
   stc_fe<P>(out + i * P::N, acc);
+}
+
+// out[i] = scale * base^i: thread t owns PCH consecutive exponents, seeded by square-and-multiply
+constexpr size_t PCH = 16;
+template <class P>
+__global__ void powers_kernel(uint32_t* out, size_t n, Fe<P> base_m, Fe<P> scale) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t lo = t * PCH;
+  if (lo >= n) return;
+  Fe<P> acc = scale, b = base_m;            // scale canonical, base Montgomery -> products stay canonical
+  for (size_t e = lo; e; e >>= 1) {
+    if (e & 1) acc = fe_mul<P>(acc, b);
+    b = fe_sqr<P>(b);
+  }
+  size_t hi = lo + PCH < n ? lo + PCH : n;
+  for (size_t i = lo; i < hi; i++) {
+    stc_fe<P>(out + i * P::N, acc);
+    acc = fe_mul<P>(acc, base_m);
+  }
 }
 
 // S[t] = sum_{i in chunk t} in[i] * z^(i - 64 t)
@@ -125,8 +146,9 @@ int suffix_horner(const uint32_t* d_c, size_t len, const Fe<P>& z_mont, uint32_t
 }
 
 template <class P>
-int open_impl(uint64_t handle, bool do_msm, const uint64_t* polys, const size_t* lens, size_t k, const uint64_t* z, const uint64_t* xi,
-              uint64_t* out_xy, int* is_inf, uint64_t* quotient, size_t* quot_len, uint64_t* eval_out) {
+int open_impl(uint64_t handle, bool do_msm, const uint64_t* polys, const uint64_t* const* d_polys, const size_t* lens, size_t k,
+              const uint64_t* z, const uint64_t* xi, uint64_t* out_xy, int* is_inf, uint64_t* quotient, size_t* quot_len,
+              uint64_t* eval_out) {
   KzgpuCtx& cx = kz_ctx();
   Fe<P> zc = kz_fe_from_u64<P>(z), xc = kz_fe_from_u64<P>(xi);
   if (!kz_fe_reduced<P>(zc) || !kz_fe_reduced<P>(xc)) return kz_fail(KZGPU_ERANGE, "z / xi must be canonical field elements");
@@ -151,16 +173,18 @@ int open_impl(uint64_t handle, bool do_msm, const uint64_t* polys, const size_t*
   Fe<P> xm = fe_to_mont<P>(xc), cur = xm;
   for (size_t j = 0; j < k; j++) { memcpy(&xip[j * P::N], cur.v, P::N * 4); cur = fe_mul<P>(cur, xm); }
   int rc;
-  if ((rc = g_pw.polys.ensure(total * 32))) return rc;
+  if (!d_polys && (rc = g_pw.polys.ensure(total * 32))) return rc;
+  for (size_t j = 0; j < k; j++)       // element offsets -> device addresses
+    meta[2 * j] = d_polys ? (uint64_t)(uintptr_t)d_polys[j] : (uint64_t)(uintptr_t)g_pw.polys.p + meta[2 * j] * 32;
   if ((rc = g_pw.meta.ensure(meta.size() * 8 + xip.size() * 4 + 64))) return rc;
   if ((rc = g_pw.comb.ensure(maxlen * 32))) return rc;
   if ((rc = g_pw.t.ensure(maxlen * 32 + 32))) return rc;
   uint64_t* d_meta = (uint64_t*)g_pw.meta.p;
   uint32_t* d_xip = (uint32_t*)(d_meta + meta.size());
-  KZ_CUDA(cudaMemcpyAsync(g_pw.polys.p, polys, total * 32, cudaMemcpyHostToDevice, cx.stream));
+  if (!d_polys) KZ_CUDA(cudaMemcpyAsync(g_pw.polys.p, polys, total * 32, cudaMemcpyHostToDevice, cx.stream));
   KZ_CUDA(cudaMemcpyAsync(d_meta, meta.data(), meta.size() * 8, cudaMemcpyHostToDevice, cx.stream));
   KZ_CUDA(cudaMemcpyAsync(d_xip, xip.data(), xip.size() * 4, cudaMemcpyHostToDevice, cx.stream));
-  poly_combine_kernel<P><<<(unsigned)kz_div_up(maxlen, 128), 128, 0, cx.stream>>>((uint32_t*)g_pw.polys.p, d_meta, d_xip, (uint32_t)k, maxlen,
+  poly_combine_kernel<P><<<(unsigned)kz_div_up(maxlen, 128), 128, 0, cx.stream>>>(d_meta, d_xip, (uint32_t)k, maxlen, nullptr,
                                                                                (uint32_t*)g_pw.comb.p);
   KZ_LAUNCHED();
   if ((rc = suffix_horner<P>((uint32_t*)g_pw.comb.p, maxlen, fe_to_mont<P>(zc), (uint32_t*)g_pw.t.p))) return rc;
@@ -170,6 +194,79 @@ int open_impl(uint64_t handle, bool do_msm, const uint64_t* polys, const size_t*
   if (quot_len) *quot_len = maxlen - 1;
   KZ_CUDA(cudaStreamSynchronize(cx.stream));
   if (do_msm) return kz_msm_dev_internal(handle, 0, d_T + P::N, maxlen - 1, out_xy, is_inf, nullptr);
+  return 0;
+}
+
+// p(x) = T_0 of the suffix Horner recurrence: upward sweep only
+template <class P>
+int eval_impl(const uint32_t* d_c, size_t len, const uint64_t* x, uint64_t* out) {
+  KzgpuCtx& cx = kz_ctx();
+  Fe<P> xc = kz_fe_from_u64<P>(x);
+  if (!kz_fe_reduced<P>(xc)) return kz_fail(KZGPU_ERANGE, "evaluation point must be a canonical field element");
+  if (len == 0) { memset(out, 0, 32); return 0; }
+  std::vector<size_t> lens{len};
+  while (lens.back() > 1) lens.push_back(kz_div_up(lens.back(), CHL));
+  size_t total = 0;
+  for (size_t l = 1; l < lens.size(); l++) total += lens[l];
+  int rc = g_pw.levels.ensure((total + 1) * P::N * 4);
+  if (rc) return rc;
+  uint32_t* p = (uint32_t*)g_pw.levels.p;
+  Fe<P> zl = fe_to_mont<P>(xc);
+  const uint32_t* cur = d_c;
+  for (size_t l = 1; l < lens.size(); l++) {
+    horner_chunks_kernel<P><<<(unsigned)kz_div_up(lens[l], 128), 128, 0, cx.stream>>>(cur, lens[l - 1], zl, p, lens[l]);
+    KZ_LAUNCHED();
+    cur = p; p += lens[l] * P::N;
+    zl = hpow<P>(zl, CHL);
+  }
+  KZ_CUDA(cudaMemcpyAsync(out, cur, 32, cudaMemcpyDeviceToHost, cx.stream));
+  KZ_CUDA(cudaStreamSynchronize(cx.stream));
+  return 0;
+}
+
+template <class P>
+int lincomb_impl(uint32_t* d_out, size_t out_len, const uint64_t* const* d_polys, const size_t* lens, const uint64_t* scalars, size_t k,
+                 const uint64_t* constant) {
+  KzgpuCtx& cx = kz_ctx();
+  if (out_len == 0) return 0;
+  std::vector<uint64_t> meta(2 * k + 2);
+  std::vector<uint32_t> mult((k + 1) * P::N);
+  for (size_t j = 0; j < k; j++) {
+    meta[2 * j] = (uint64_t)(uintptr_t)d_polys[j]; meta[2 * j + 1] = lens[j];
+    Fe<P> sc = kz_fe_from_u64<P>(scalars + 4 * j);
+    if (!kz_fe_reduced<P>(sc)) return kz_fail(KZGPU_ERANGE, "scalar %zu is not a canonical field element", j);
+    Fe<P> sm = fe_to_mont<P>(sc);
+    memcpy(&mult[j * P::N], sm.v, P::N * 4);
+  }
+  if (constant) {
+    Fe<P> cc = kz_fe_from_u64<P>(constant);
+    if (!kz_fe_reduced<P>(cc)) return kz_fail(KZGPU_ERANGE, "constant is not a canonical field element");
+    memcpy(&mult[k * P::N], cc.v, P::N * 4);
+  }
+  int rc;
+  if ((rc = g_pw.meta.ensure(meta.size() * 8 + mult.size() * 4 + 64))) return rc;
+  uint64_t* d_meta = (uint64_t*)g_pw.meta.p;
+  uint32_t* d_mult = (uint32_t*)(d_meta + meta.size());
+  KZ_CUDA(cudaMemcpyAsync(d_meta, meta.data(), meta.size() * 8, cudaMemcpyHostToDevice, cx.stream));
+  KZ_CUDA(cudaMemcpyAsync(d_mult, mult.data(), mult.size() * 4, cudaMemcpyHostToDevice, cx.stream));
+  poly_combine_kernel<P><<<(unsigned)kz_div_up(out_len, 128), 128, 0, cx.stream>>>(d_meta, d_mult, (uint32_t)k, out_len,
+                                                                                constant ? d_mult + k * P::N : nullptr, d_out);
+  KZ_LAUNCHED();
+  KZ_CUDA(cudaStreamSynchronize(cx.stream));     // meta/mult are host vectors: keep them alive until consumed
+  return 0;
+}
+
+template <class P>
+int powers_impl(uint32_t* d_out, size_t n, const uint64_t* base, const uint64_t* scale) {
+  KzgpuCtx& cx = kz_ctx();
+  Fe<P> b = kz_fe_from_u64<P>(base), sc = fe_zero<P>();
+  sc.v[0] = 1;
+  if (scale) sc = kz_fe_from_u64<P>(scale);
+  if (!kz_fe_reduced<P>(b) || !kz_fe_reduced<P>(sc)) return kz_fail(KZGPU_ERANGE, "base / scale must be canonical field elements");
+  if (n == 0) return 0;
+  size_t threads = kz_div_up(n, PCH);
+  powers_kernel<P><<<(unsigned)kz_div_up(threads, 128), 128, 0, cx.stream>>>(d_out, n, fe_to_mont<P>(b), sc);
+  KZ_LAUNCHED();
   return 0;
 }
 
@@ -188,16 +285,52 @@ int kzgpu_open(uint64_t handle, const uint64_t* polys, const size_t* lens, size_
   if ((k && (!polys || !lens)) || !z || !xi || !out_affine_xy) return kz_fail(KZGPU_EINVAL, "null pointer");
   int curve = kz_srs_curve(handle);
   if (curve < 0) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle %llu", (unsigned long long)handle);
-  if (curve == KZGPU_BN254) return open_impl<FrBN254>(handle, true, polys, lens, k, z, xi, out_affine_xy, is_inf, nullptr, nullptr, eval_out);
-  return open_impl<FrBLS381>(handle, true, polys, lens, k, z, xi, out_affine_xy, is_inf, nullptr, nullptr, eval_out);
+  if (curve == KZGPU_BN254) return open_impl<FrBN254>(handle, true, polys, nullptr, lens, k, z, xi, out_affine_xy, is_inf, nullptr, nullptr, eval_out);
+  return open_impl<FrBLS381>(handle, true, polys, nullptr, lens, k, z, xi, out_affine_xy, is_inf, nullptr, nullptr, eval_out);
 }
 
 int kzgpu_open_quotient(int field, const uint64_t* polys, const size_t* lens, size_t k, const uint64_t* z, const uint64_t* xi,
                         uint64_t* quotient, size_t* quot_len, uint64_t* eval_out) {
   KZ_REQUIRE_INIT();
   if ((k && (!polys || !lens)) || !z || !xi) return kz_fail(KZGPU_EINVAL, "null pointer");
-  if (field == KZGPU_BN254) return open_impl<FrBN254>(0, false, polys, lens, k, z, xi, nullptr, nullptr, quotient, quot_len, eval_out);
-  if (field == KZGPU_BLS12_381) return open_impl<FrBLS381>(0, false, polys, lens, k, z, xi, nullptr, nullptr, quotient, quot_len, eval_out);
+  if (field == KZGPU_BN254) return open_impl<FrBN254>(0, false, polys, nullptr, lens, k, z, xi, nullptr, nullptr, quotient, quot_len, eval_out);
+  if (field == KZGPU_BLS12_381) return open_impl<FrBLS381>(0, false, polys, nullptr, lens, k, z, xi, nullptr, nullptr, quotient, quot_len, eval_out);
+  return kz_fail(KZGPU_EINVAL, "unknown field id %d", field);
+}
+
+int kzgpu_open_dev(uint64_t handle, const uint64_t* const* d_polys, const size_t* lens, size_t k, const uint64_t* z, const uint64_t* xi,
+                   uint64_t* out_affine_xy, int* is_inf, uint64_t* eval_out) {
+  KZ_REQUIRE_INIT();
+  if ((k && (!d_polys || !lens)) || !z || !xi || !out_affine_xy) return kz_fail(KZGPU_EINVAL, "null pointer");
+  int curve = kz_srs_curve(handle);
+  if (curve < 0) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle %llu", (unsigned long long)handle);
+  if (curve == KZGPU_BN254)
+    return open_impl<FrBN254>(handle, true, nullptr, d_polys, lens, k, z, xi, out_affine_xy, is_inf, nullptr, nullptr, eval_out);
+  return open_impl<FrBLS381>(handle, true, nullptr, d_polys, lens, k, z, xi, out_affine_xy, is_inf, nullptr, nullptr, eval_out);
+}
+
+int kzgpu_poly_eval_dev(int field, const uint64_t* d_poly, size_t len, const uint64_t* x, uint64_t* out) {
+  KZ_REQUIRE_INIT();
+  if ((len && !d_poly) || !x || !out) return kz_fail(KZGPU_EINVAL, "null pointer");
+  if (field == KZGPU_BN254) return eval_impl<FrBN254>((const uint32_t*)d_poly, len, x, out);
+  if (field == KZGPU_BLS12_381) return eval_impl<FrBLS381>((const uint32_t*)d_poly, len, x, out);
+  return kz_fail(KZGPU_EINVAL, "unknown field id %d", field);
+}
+
+int kzgpu_poly_lincomb_dev(int field, uint64_t* d_out, size_t out_len, const uint64_t* const* d_polys, const size_t* lens,
+                           const uint64_t* scalars, size_t k, const uint64_t* constant) {
+  KZ_REQUIRE_INIT();
+  if ((out_len && !d_out) || (k && (!d_polys || !lens || !scalars))) return kz_fail(KZGPU_EINVAL, "null pointer");
+  if (field == KZGPU_BN254) return lincomb_impl<FrBN254>((uint32_t*)d_out, out_len, d_polys, lens, scalars, k, constant);
+  if (field == KZGPU_BLS12_381) return lincomb_impl<FrBLS381>((uint32_t*)d_out, out_len, d_polys, lens, scalars, k, constant);
+  return kz_fail(KZGPU_EINVAL, "unknown field id %d", field);
+}
+
+int kzgpu_powers_dev(int field, uint64_t* d_out, size_t n, const uint64_t* base, const uint64_t* scale) {
+  KZ_REQUIRE_INIT();
+  if ((n && !d_out) || !base) return kz_fail(KZGPU_EINVAL, "null pointer");
+  if (field == KZGPU_BN254) return powers_impl<FrBN254>((uint32_t*)d_out, n, base, scale);
+  if (field == KZGPU_BLS12_381) return powers_impl<FrBLS381>((uint32_t*)d_out, n, base, scale);
   return kz_fail(KZGPU_EINVAL, "unknown field id %d", field);
 }
 

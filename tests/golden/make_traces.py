@@ -211,6 +211,7 @@ def trace_plonk_normalized():
             ipk, ivk = rr.load("plonk.indexer").Indexer(curve_type="bn254").preprocess(*sel, perm, max_degree=n + 5)
             n_index_draws = len(draws)
             proof = rr.load("plonk.prover").Prover(curve_type="bn254").prove(ipk, x, wit)
+            n_prove_draws = len(draws)
             ok = rr.load("plonk.verifier").Verifier(curve_type="bn254").verify(ivk, x, proof)
         finally:
             sageshim.GFShim.random_element = orig_rand
@@ -220,7 +221,9 @@ def trace_plonk_normalized():
             "source": "reference plonk prover with commitments normalised to (x,y,1) before the transcript",
             "seed": SEED + 4, "curve": "bn254", "n": n,
             "index_draws": draws[:n_index_draws],                 # tau, k1, k2 ... (kzg.py:67, plonk/encoder.py:83-84)
-            "prover_draws": draws[n_index_draws:],                # b1..b9, b10, b11 (plonk/prover.py:72-75,346)
+            # the prover's Encoder.update_state draws a throw-away k1, k2 first (plonk/prover.py:63,
+            # plonk/encoder.py:80-91); the last 11 draws are b1..b9 (:72-75) and b10, b11 (:346)
+            "prover_draws": draws[n_index_draws:n_prove_draws],
             "g": rr.enc_scalar(sub["g"]), "k1": rr.enc_scalar(sub["k1"]), "k2": rr.enc_scalar(sub["k2"]),
             "sigma_star": [rr.enc_scalar(s) for s in ipk["sigma_star"]],
             "index_polys": {k: rr.enc_poly(v) for k, v in ipk["polynomials"].items()},

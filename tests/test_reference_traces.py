@@ -94,3 +94,29 @@ def test_live_reference_run_matches_committed_plonk_trace():
     gold = load("ref_trace_plonk.json")
     assert live["notes"]["verify"] and live["notes"]["tampered_rejected"]
     assert live["calls"] == gold["calls"] and live["proof"] == gold["proof"] and live["keys"] == gold["keys"]
+
+
+def _normalized_fixture():
+    d = load("ref_plonk_normalized.json")
+    ko = KZGOracle("bn254")
+    cv = get_curve("bn254")
+    ck = [(H(p[0]), H(p[1]), 1) for p in d["keys"][0]]
+    names = ["qM", "qL", "qR", "qO", "qC", "S_sigma1", "S_sigma2", "S_sigma3"]
+    comm = ko.commit(ck, [[H(c) for c in d["index_polys"][k]] for k in names])
+    ivk = {"commitments": {k: cv.normalize(c) for k, c in zip(names, comm)}, "n": d["n"], "g": H(d["g"]),
+           "k1": H(d["k1"]), "k2": H(d["k2"]), "tau": H(d["index_draws"][0])}
+    proof = {sec: {k: (None if v is None else (tuple(H(t) for t in v) if isinstance(v, list) else H(v)))
+                   for k, v in body.items()} for sec, body in d["proof"].items()}
+    return d, ivk, proof
+
+
+def test_test_verifier_accepts_the_reference_provers_proof():
+    """tests/plonk_verifier.py (used to judge the GPU prover at sizes the fixture does not cover)
+    must agree with the reference: accept the proof plonk/prover.py produced, reject a tampered one."""
+    import plonk_verifier
+    d, ivk, proof = _normalized_fixture()
+    x = [H(v) for v in d["x"]]
+    assert d["notes"]["verify"] and plonk_verifier.verify(ivk, x, proof)
+    bad = {**proof, "evaluations": {**proof["evaluations"], "a": proof["evaluations"]["a"] + 1}}
+    assert not plonk_verifier.verify(ivk, x, bad)
+    assert not plonk_verifier.verify(ivk, [x[0] + 1] + x[1:], proof)
