@@ -40,6 +40,16 @@ IMAD32_PER_MODMUL = 272
 MODMUL_PER_MADD = 10
 
 
+def load_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture
+    (profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            return json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -147,6 +157,28 @@ def cpu_ntt_rate(logn, cores):
         with mp.get_context("fork").Pool(cores) as pool:
             wall = max(pool.map(_cpu_ntt_chunk, jobs))
     return (1 << logn) * cores / wall, wall
+
+
+def cpu_plonk_hotpath():
+    """Seconds the restated oracle needs for the hot-path calls the reference's PLONK prover made on
+    the bundled instance (the kzg.commit / kzg.open / fft_ff_interpolation records of
+    tests/golden/ref_trace_plonk.json after the indexer's), 1 core."""
+    from oracle import fft_ff as off
+    from oracle.field import GFp
+    from oracle.kzg import KZGOracle
+    tr = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_trace_plonk.json")))
+    H = lambda v: int(v, 16)                                          # noqa: E731
+    ko, F = KZGOracle("bn254"), GFp(R_BN254)
+    keys = [[(H(p[0]), H(p[1]), 1) for p in k] for k in tr["keys"]]
+    t0 = time.perf_counter()
+    for rec in tr["calls"][tr["notes"]["index_calls"]:]:
+        if rec["fn"] == "commit":
+            ko.commit(keys[rec["ck_id"]], [[H(c) for c in p] for p in rec["polys"]])
+        elif rec["fn"] == "open":
+            ko.open(keys[rec["ck_id"]], [[H(c) for c in p] for p in rec["polys"]], H(rec["z"]), H(rec["xi"]))
+        else:
+            off.fft_ff_interpolation([F(H(v)) for v in rec["in"]], F(H(rec["w"])), F)
+    return time.perf_counter() - t0
 
 
 def run_reference(args):
@@ -326,7 +358,7 @@ def run_gpu(args):
                 "achieved": (n / (acc_ms * 1e-3)) * MODEL_IMAD_PER_POINT / 1e9,
                 "peak": imad32_peak / 1e9, "unit": "G IMAD32/s",
                 "frac": (n / (acc_ms * 1e-3)) * MODEL_IMAD_PER_POINT / imad32_peak,
-                "traffic": None,
+                "traffic": load_traffic("msm_accumulate_kernel") if args.logn == 24 else None,
                 "model": "SURVEY 8(d): 43,520 32-bit IMAD per point (16 windows x 10 modmul x 272); "
                          "peak = live IMAD.WIDE.U32 microbenchmark x 2",
                 "executed_frac": madds * MODMUL_PER_MADD * IMAD32_PER_MODMUL / (acc_ms * 1e-3) / imad32_peak,
@@ -388,7 +420,7 @@ def run_gpu(args):
             "roofline": {
                 "bound": "hbm", "kernel": "ntt_pass_kernel (all passes of one transform)",
                 "achieved": hbm, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": hbm / peaks.get("hbm_gbs"),
-                "traffic": None, "peak_source": peak_src,
+                "traffic": load_traffic("ntt_pass_kernel") if args.logn == 24 else None, "peak_source": peak_src,
                 "model": "SURVEY 8(d): algorithmic bytes = 2 x 32 B x n (twiddles not counted)",
                 "passes": pr["launches"] // K, "kernel_ms": ntt_ms,
                 "imad_frac": modmuls * IMAD32_PER_MODMUL / (ntt_ms * 1e-3) / imad32_peak,
@@ -398,10 +430,87 @@ def run_gpu(args):
         d.free(); pinned.free()
         return res
 
-    primary = bench_msm() if args.workload == "msm" else bench_ntt()
+    # ------------------------------------------------------------------ PLONK prove (configs[3])
+    def bench_plonk():
+        """End-to-end `Prover.prove` (kzg_snark_b200/plonk.py, the device-resident counterpart of
+        plonk/prover.py:24) on (a) the reference's bundled 16-gate instance, checked bit for bit
+        against the proof the reference's own prover produced in the build container, and (b) a
+        synthetic circuit of 2^plonk_logn gates.  Wall-clock seconds, host lists / arrays in,
+        proof (9 points + 6 scalars) out."""
+        from kzg_snark_b200.plonk import Indexer, Prover
+        from kzg_snark_b200.plonk_synth import synthetic_circuit
+        gold = os.path.join(ROOT, "tests", "golden")
+        H = lambda v: int(v, 16)                                      # noqa: E731
+        d = json.load(open(os.path.join(gold, "ref_plonk_normalized.json")))
+        inst = json.load(open(os.path.join(gold, "plonk_instance.json")))
+        tr = json.load(open(os.path.join(gold, "ref_trace_plonk.json")))
+        sel = [[H(v) for v in inst[k]] for k in ("qM", "qL", "qR", "qO", "qC")]
+        nb = d["n"]
+        idx = Indexer("bn254")
+        ipk, _ = idx.preprocess(*sel, [H(v) for v in inst["perm"]], max_degree=nb + 5, tau=H(d["index_draws"][0]),
+                                k1=H(d["k1"]), k2=H(d["k2"]))
+        xs = [idx.kzg.Fq(H(v)) for v in d["x"]]
+        ws = [H(v) for v in d["w"]]
+        bl = [H(b) for b in d["prover_draws"][-11:]]
+        prover = Prover("bn254")
+        times = []
+        for i in range(Wm + K):
+            t0 = time.perf_counter()
+            proof = prover.prove(ipk, xs, ws, blinders=bl)
+            times.append(time.perf_counter() - t0)
+        times = sorted(times[Wm:])
+        same = all((int(proof[sec][k][0]), int(proof[sec][k][1])) == (H(v[0]), H(v[1])) if isinstance(v, list)
+                   else int(proof[sec][k]) == H(v) for sec, body in d["proof"].items() for k, v in body.items())
+        out = {"bundled": {"gates": nb, "prove_s": times[len(times) // 2], "proof_equals_reference_prover": bool(same),
+                           "reference_prove_s": tr["notes"]["prove_seconds"],
+                           "reference_note": "plonk/prover.py run unmodified in the build container on the Sage/py_ecc stand-ins "
+                                             "(oracle/refrun.py), 1 core; recorded in tests/golden/ref_trace_plonk.json"}}
+        n = 1 << args.plonk_logn
+        t0 = time.perf_counter()
+        qM, qL, qR, qO, qC, perm, w = synthetic_circuit(n, 16, R_BN254, seed=args.plonk_logn)
+        wpin = _ffi.PinnedArray((3 * n - 16, 4))                      # the witness lives in page-locked host memory
+        wpin.array[:] = ints_to_limbs(w[16:], R_BN254)
+        wl = wpin.array
+        t_gen = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ipk, _ = idx.preprocess(qM, qL, qR, qO, qC, perm, max_degree=n + 5, tau=TAU, k1=7, k2=13)
+        _ffi.check(_ffi._lib.kzgpu_sync())
+        t_index = time.perf_counter() - t0
+        xs = [idx.kzg.Fq(v) for v in w[:16]]
+        times, l0 = [], 0
+        for i in range(3 + 5):
+            if i == 3:
+                l0 = _ffi.launch_count()
+            t0 = time.perf_counter()
+            prover.prove(ipk, xs, wl)
+            times.append(time.perf_counter() - t0)
+        launches = (_ffi.launch_count() - l0) // 5
+        assert prover.last_r_zeta == 0 and not any(prover.last_t_top), "r(zeta) != 0: the proof would not verify"
+        times = sorted(times[3:])
+        out["synthetic"] = {"gates": n, "prove_s": times[len(times) // 2], "index_s": t_index, "circuit_generation_s": t_gen,
+                            "h2d_bytes": int(wl.nbytes), "host_buffers": "pinned (cudaHostAlloc)", "gpu_launches_per_prove": int(launches),
+                            "rounds_s": {k: round(v, 5) for k, v in prover.timings.items()},
+                            "checks": "r(zeta) == 0 and deg t <= 3n+5 asserted; verifier acceptance at this construction is "
+                                      "covered by tests/test_gpu_plonk.py up to 2^14 gates"}
+        wpin.free()
+        return out
+
+    primary = bench_msm() if args.workload == "msm" else (bench_ntt() if args.workload == "ntt" else None)
     secondary = None
     if args.workload == "msm" and not args.no_secondary:
         secondary = bench_ntt()
+    plonk = None
+    if world == 1 and (args.workload == "plonk" or not args.no_secondary):
+        plonk = bench_plonk()
+    if args.workload == "plonk":
+        if rank == 0:
+            print(json.dumps({"metric": "plonk_prove_s", "value": plonk["synthetic"]["prove_s"], "unit": "s", "n_gpus": 1,
+                              "steps": 5, "warmup": 3, "ms_per_step": 1e3 * plonk["synthetic"]["prove_s"],
+                              "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+                              "dtype": "u32x8 (256-bit modular integers, Montgomery)", "data": "synthetic",
+                              "config": {"workload": f"PLONK prove, synthetic circuit of 2^{args.plonk_logn} gates, BN254"},
+                              "plonk": plonk, "device": info["name"]}))
+        return 0
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
     cpu = None
@@ -420,6 +529,10 @@ def run_gpu(args):
             cpu = {"value": v, "unit": "elements/s", "cores": 1, "kind": "port",
                    "sample": f"2^18-element recursive fft_ff (fft_ff.py:3-37 on CPython ints), {wall:.1f} s",
                    "host_cpus": os.cpu_count()}
+
+    cpu_plonk = None
+    if rank == 0 and world == 1 and not args.no_cpu and plonk is not None:
+        cpu_plonk = cpu_plonk_hotpath()
 
     if rank == 0:
         if args.workload == "msm":
@@ -446,6 +559,10 @@ def run_gpu(args):
         }
         if "profile_ms_per_step" in primary:
             line["profile_ms_per_step"] = primary["profile_ms_per_step"]
+        if plonk is not None:
+            if cpu_plonk is not None:
+                plonk["bundled"]["cpu_port_hotpath_s"] = cpu_plonk
+            line["plonk"] = plonk
         if secondary is not None:
             line["ntt"] = {"metric": "ntt_elements_per_s", "value": secondary["value"], "unit": "elements/s",
                            "ms_per_step": secondary["ms"] / K, "e2e": secondary["e2e"], "roofline": secondary["roofline"],
@@ -465,7 +582,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="msm", choices=["msm", "ntt"])
+    ap.add_argument("--workload", default="msm", choices=["msm", "ntt", "plonk"])
+    ap.add_argument("--plonk-logn", type=int, default=20, help="gates of the synthetic PLONK circuit (log2)")
     ap.add_argument("--logn", type=int, default=24)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -26,6 +26,7 @@ import ctypes
 import hashlib
 import random
 import struct
+import time
 
 import numpy as np
 
@@ -283,15 +284,24 @@ class Prover:
             out, inf = device.msm_dev(srs, vec, length)
             return kzg._codec.from_device(out, inf)
 
+        self.timings = tm = {}
+        clock = [time.perf_counter()]
+
+        def lap(name):
+            check(lib.kzgpu_sync())
+            now = time.perf_counter()
+            tm[name] = tm.get(name, 0.0) + now - clock[0]
+            clock[0] = now
+
         transcript = Transcript("plonk-proof", Fq)
         transcript.append_message("public-inputs", x)                   # plonk/prover.py:57
 
-        if isinstance(w, np.ndarray):
-            full = np.concatenate([ints_to_limbs(x, r), w.reshape(-1, 4)], axis=0)
-        else:
-            full = ints_to_limbs(list(x) + list(w), r)
-        assert full.shape[0] == 3 * n, "x + w must hold 3n wire values"
-        wires = DVec.from_limbs(full)                                   # a | b | c values on H
+        wires = DVec(3 * n)                                             # a | b | c values on H
+        xl = ints_to_limbs(x, r)
+        wl = w.reshape(-1, 4) if isinstance(w, np.ndarray) else ints_to_limbs(w, r)   # a (pinned) limb array is copied as is
+        assert xl.shape[0] + wl.shape[0] == 3 * n, "x + w must hold 3n wire values"
+        check(lib.kzgpu_h2d(wires.at(0), ptr(xl), xl.nbytes))
+        check(lib.kzgpu_h2d(wires.at(xl.shape[0]), ptr(np.ascontiguousarray(wl, dtype=np.uint64)), wl.nbytes))
 
         # PI(X) = -sum x_i L_i(X): values -x_i on the first len(x) points of H (plonk/encoder.py:218-223)
         pi = DVec.from_limbs(ints_to_limbs([-int(v) for v in x], r), n)
@@ -308,7 +318,9 @@ class Prover:
             p.write(n, [bl, bh], r)
             wire_polys.append(p)
         a_poly, b_poly, c_poly = wire_polys
+        lap("round1_upload_intt")
         wire_commitments = [commit(p, n + 2) for p in wire_polys]
+        lap("round1_msm")
         transcript.append_message("round1-commitments", wire_commitments)
         beta = transcript.get_challenge("beta")
         gamma = transcript.get_challenge("gamma")
@@ -325,7 +337,9 @@ class Prover:
         lo = z_poly.read_ints(0, 3)                                     # (b7 X^2 + b8 X + b9)(X^n - 1) + interp
         z_poly.write(0, [lo[0] - b9, lo[1] - b8, lo[2] - b7], r)
         z_poly.write(n, [b9, b8, b7], r)
+        lap("round2_grand_product_intt")
         z_commit = commit(z_poly, n + 3)
+        lap("round2_msm")
         transcript.append_message("round2-commitment", z_commit)
         alpha = transcript.get_challenge("alpha")
 
@@ -353,7 +367,9 @@ class Prover:
         t_mid.write(n, [b11], r)
         f.lincomb(t_hi, n + 6, [(t.at(2 * n), n + 6, 1)], constant=-b11)  # t_hi - b11
         t_polys = [(t_lo, n + 1), (t_mid, n + 1), (t_hi, n + 6)]
+        lap("round3_quotient")
         t_commitments = [commit(v, length) for v, length in t_polys]
+        lap("round3_msm")
         transcript.append_message("round3-commitments", t_commitments)
         zeta = transcript.get_challenge("zeta")
 
@@ -363,6 +379,7 @@ class Prover:
         s1_z, s2_z = f.eval(P["S_sigma1"], n, zi), f.eval(P["S_sigma2"], n, zi)
         zw_z = f.eval(z_poly, n + 3, zi * g % r)
         evaluations = [Fq(v) for v in (a_z, b_z, c_z, s1_z, s2_z, zw_z)]
+        lap("round4_evaluations")
         transcript.append_message("round4-evaluations", evaluations)
         v = transcript.get_challenge("v")
 
@@ -398,8 +415,10 @@ class Prover:
             check(rc)
             return kzg._codec.from_device(out, bool(inf.value))
 
+        lap("round5_linearisation")
         W_z = open_dev([(r_poly, n + 6), (a_poly, n + 2), (b_poly, n + 2), (c_poly, n + 2), (P["S_sigma1"], n), (P["S_sigma2"], n)], zi)
         W_zw = open_dev([(z_poly, n + 3)], zi * g % r)
+        lap("round5_openings")
         self.last_r_zeta = f.eval(r_poly, n + 6, zi)                    # plonk/prover.py:171 asserts this is 0
         self.last_t_top = t.read_ints(3 * n + 6, min(8, n4 - 3 * n - 6))   # deg t <= 3n+5: must be zeros
 

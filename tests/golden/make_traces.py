@@ -142,6 +142,7 @@ def trace_plonk():
         t0 = time.time()
         ipk, ivk = rr.load("plonk.indexer").Indexer(curve_type="bn254").preprocess(*sel, perm, max_degree=n + 5)
         t1 = time.time()
+        index_calls = len(rr.trace)
         proof = rr.load("plonk.prover").Prover(curve_type="bn254").prove(ipk, x, wit)
         t2 = time.time()
         V = rr.load("plonk.verifier").Verifier
@@ -152,7 +153,7 @@ def trace_plonk():
         dump("ref_trace_plonk.json", {
             "source": "reference plonk/{indexer,prover,verifier}.py + kzg.py + fft_ff.py run by oracle/refrun.py",
             "seed": SEED + 2, "curve": "bn254",
-            "notes": {"verify": bool(ok), "tampered_rejected": bool(rejected),
+            "notes": {"verify": bool(ok), "tampered_rejected": bool(rejected), "index_calls": index_calls,
                       "index_seconds": round(t1 - t0, 3), "prove_seconds": round(t2 - t1, 3)},
             "keys": rr.keys, "calls": rr.trace, "proof": enc_proof(rr, proof)})
 

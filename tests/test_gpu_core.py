@@ -296,3 +296,35 @@ def test_open_matches_oracle(dev, curve, lens):
     exp = cv.normalize(cv.multiply(cv.G1, poly_eval(wit, tau, cv.r)))
     assert point_of(cv, out, inf, nl) == exp
     srs.destroy()
+
+
+def test_msm_tau_identity_at_baseline_size(dev):
+    """BASELINE.json's size: a 2^24-point BN254 MSM with uniform scalars must equal p(tau)*G1
+    (kzg.py:108).  p(tau) comes from the device Horner kernel (kzgpu_poly_eval_dev), which is
+    checked here against CPython on a 2^16 slice and by the split p = p_lo + tau^(n/2) p_hi."""
+    import ctypes
+    from kzg_snark_b200 import _ffi
+    from kzg_snark_b200.limbs import random_scalars, int_to_limbs, limbs_to_int
+    cv = get_curve("bn254")
+    tau = 0x5A17C0FFEE5EED1234567 % cv.r
+    n = 1 << 24
+    srs = dev.Srs.generate("bn254", tau, n)
+    sc = random_scalars(n, cv.r, seed=24)
+    d = _ffi.DeviceBuffer(n * 32).upload(sc)
+    lib = _ffi.load_library()
+
+    def horner(offset, count):
+        out = np.zeros(4, dtype=np.uint64)
+        _ffi.check(lib.kzgpu_poly_eval_dev(_ffi.BN254, ctypes.c_void_p(d.ptr.value + 32 * offset), count,
+                                           _ffi.ptr(int_to_limbs(tau, cv.r)), _ffi.ptr(out)))
+        return limbs_to_int(out)
+
+    assert horner(12345, 1 << 16) == poly_eval(I(sc[12345:12345 + (1 << 16)]), tau, cv.r)
+    p_tau = horner(0, n)
+    assert p_tau == (horner(0, n // 2) + pow(tau, n // 2, cv.r) * horner(n // 2, n // 2)) % cv.r
+    exp = cv.normalize(cv.multiply(cv.G1, p_tau))
+    out, inf = dev.msm_dev(srs, d, n)
+    assert point_of(cv, out, inf, 4) == exp
+    out, inf = dev.msm(srs, sc)                                        # host scalars, chunked upload
+    assert point_of(cv, out, inf, 4) == exp
+    d.free(); srs.destroy()
