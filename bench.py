@@ -495,6 +495,78 @@ def run_gpu(args):
         wpin.free()
         return out
 
+    # ------------------------------------------------------------------ Marlin kernel workload (configs[4])
+    def bench_marlin():
+        """The commit / open / NTT calls a Marlin proof over a 2^marlin_logn-constraint R1CS implies
+        (call sites marlin/prover.py:106,142,176,226-227,439-449,469 and
+        marlin/encoder.py:123-125 with |H| = n, |K| = m = 2n, b = 2).  The reference prover itself cannot
+        run at this size (dense Sage matrices).  Items are independent: item j runs on rank j % world
+        with the full SRS replicated on every GPU; no data-path collective."""
+        import ctypes
+        n_ = 1 << args.marlin_logn
+        m_ = 2 * n_
+        commits = [n_ + 2] * 4 + [n_ + 4, 2 * n_ + 1] + [n_, n_ - 1, n_ + 2] + [m_ - 1, 6 * m_ - 6]
+        ntts = [(m_, True)] * 9 + [(n_, True)] * 4 + [(m_, False)] * 9 + [(m_, True)]
+        opens = [[2 * n_ + 2, m_ - 1, n_ + 2, n_], [6 * m_ - 6] + [m_] * 6]
+        srs_n = 6 * m_
+        srs = device.Srs.generate("bn254", TAU, srs_n)
+        lib = _ffi._lib
+        from kzg_snark_b200.parallel import round_robin
+        L = lambda v: _ffi.ptr(ints_to_limbs([v], R_BN254)[0])           # noqa: E731
+
+        def rand_dev(cnt, seed):
+            return _ffi.DeviceBuffer(cnt * 32).upload(random_scalars(cnt, R_BN254, seed=seed))
+
+        my_c = [(j, rand_dev(commits[j], 500 + j)) for j in round_robin(len(commits), world, rank)]
+        my_n = [(j, rand_dev(ntts[j][0], 600 + j)) for j in round_robin(len(ntts), world, rank)]
+        my_o = [(j, [rand_dev(c, 700 + 10 * j + i) for i, c in enumerate(opens[j])]) for j in round_robin(len(opens), world, rank)]
+        w_of = {sz: ints_to_limbs([pow(5, (R_BN254 - 1) // sz, R_BN254)], R_BN254)[0] for sz in (n_, m_)}
+        zl, xil = 0x1234567 % R_BN254, 0x7654321 % R_BN254
+
+        def step():
+            for j, d in my_c:
+                device.msm_dev(srs, d, commits[j])
+            for j, d in my_n:
+                device.ntt_dev("bn254", d, ntts[j][0], w_of[ntts[j][0]], inverse=ntts[j][1])
+            for j, ds in my_o:
+                k = len(ds)
+                out = np.zeros(8, dtype=np.uint64)
+                fl = ctypes.c_int(0)
+                ptrs = (ctypes.c_void_p * k)(*[d.ptr.value for d in ds])
+                lens = (ctypes.c_size_t * k)(*opens[j])
+                _ffi.check(lib.kzgpu_open_dev(srs.handle, ptrs, lens, k, L(zl), L(xil), _ffi.ptr(out), ctypes.byref(fl), None))
+
+        for _ in range(Wm):
+            step()
+        sampler = ClockSampler(local)
+        barrier()
+        l0 = _ffi.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            step()
+        barrier()
+        ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        return {"ms": ms, "launches": _ffi.launch_count() - l0, "clocks": sampler.stop(),
+                "items": {"commits": commits, "ntts": [[a, "inverse" if b else "forward"] for a, b in ntts], "opens": opens},
+                "srs_points": srs_n, "srs": srs.info()}
+
+    if args.workload == "marlin":
+        res = bench_marlin()
+        if rank == 0:
+            print(json.dumps({"metric": "marlin_kernel_workload_s", "value": res["ms"] / K / 1e3, "unit": "s", "n_gpus": world,
+                              "steps": K, "warmup": Wm, "ms_per_step": res["ms"] / K, "higher_is_better": False,
+                              "scaling": "strong", "vs_baseline": None,
+                              "dtype": "u32x8 (256-bit modular integers, Montgomery)", "data": "synthetic",
+                              "config": {"workload": f"commit/open/NTT calls of one Marlin proof, 2^{args.marlin_logn} constraints "
+                                                     f"(|H|=2^{args.marlin_logn}, |K|=2^{args.marlin_logn + 1}), items round-robin over {world} GPUs, "
+                                                     "SRS replicated", "items": res["items"], "srs_points": res["srs_points"],
+                                         "srs_layout": res["srs"]},
+                              "clocks": res["clocks"], "gpu_launches": res["launches"], "device": info["name"]}))
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
     primary = bench_msm() if args.workload == "msm" else (bench_ntt() if args.workload == "ntt" else None)
     secondary = None
     if args.workload == "msm" and not args.no_secondary:
@@ -582,7 +654,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="msm", choices=["msm", "ntt", "plonk"])
+    ap.add_argument("--workload", default="msm", choices=["msm", "ntt", "plonk", "marlin"])
+    ap.add_argument("--marlin-logn", type=int, default=20, help="constraints of the Marlin kernel workload (log2)")
     ap.add_argument("--plonk-logn", type=int, default=20, help="gates of the synthetic PLONK circuit (log2)")
     ap.add_argument("--logn", type=int, default=24)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])

@@ -73,12 +73,27 @@ class Transcript:
         return c
 
 
+_POOL = {}          # capacity in bytes -> idle DeviceBuffers (cudaMalloc / cudaFree stay out of the prove loop)
+
+
+def release_pool():
+    """Return every pooled device buffer to the driver."""
+    for bufs in _POOL.values():
+        for b in bufs:
+            b.free()
+    _POOL.clear()
+
+
 class DVec:
-    """A vector of scalar-field elements in HBM (canonical limbs, 32 B each)."""
+    """A vector of scalar-field elements in HBM (canonical limbs, 32 B each).  Buffers are
+    recycled through a size-keyed pool: `free()` parks the allocation, the next vector of the
+    same size reuses it."""
 
     def __init__(self, n, zero=False):
         self.n = int(n)
-        self.buf = _ffi.DeviceBuffer(max(self.n, 1) * 32)
+        cap = max(self.n, 1) * 32
+        idle = _POOL.get(cap)
+        self.buf = idle.pop() if idle else _ffi.DeviceBuffer(cap)
         if zero:
             check(_ffi._lib.kzgpu_memset(self.buf.ptr, 0, self.n * 32))
 
@@ -115,7 +130,12 @@ class DVec:
         check(_ffi._lib.kzgpu_d2d(self.at(dst_off), src.at(src_off), count * 32))
 
     def free(self):
-        self.buf.free()
+        if self.buf is not None:
+            _POOL.setdefault(self.buf.nbytes, []).append(self.buf)
+            self.buf = None
+
+    def __del__(self):
+        self.free()
 
 
 def _voidp_array(ptrs):

@@ -15,15 +15,23 @@ vendored in /root/reference:
     SageMath (un-pinned: README.md:14)  GF(r) elements and PolynomialRing
         arithmetic used by kzg.py:144-154    -> oracle/field.py, oracle/poly.py
 
-PARITY STATUS: "parity unpinned".  The reference holds no golden vectors or
-known-answer tests for this path and neither SageMath
-nor py_ecc can be imported in this image, so the oracle cannot be checked
-against the reference's own outputs.  It is pinned instead by
-  (i)   the mathematical definitions (DFT definition; group law on the fixed
-        curves -> the normalised affine result is canonical),
+PARITY STATUS: pinned against the reference's own code, run here.  oracle/refrun.py imports
+the UNMODIFIED kzg.py, fft_ff.py, transcript.py, plonk/*.py and marlin/*.py from
+/root/reference (with stand-ins for the two uninstallable third-party packages:
+kzg_snark_b200/sageshim.py for `sage.all`, oracle/pyecc_standin.py -- restated G1/G2 arithmetic
+and BN254 ate pairing -- for `py_ecc.optimized_bn128`), runs main.py's three demos (both
+verifiers accept, tampered proofs are rejected) and configs[0], and records every boundary call
+(KZG.commit / open, fft_ff / ifft_ff / fft_ff_interpolation) with the reference's outputs in
+tests/golden/ref_trace_*.json (generator: tests/golden/make_traces.py).  The oracle reproduces
+all of them bit for bit (tests/test_reference_traces.py), and so does the CUDA path
+(tests/test_gpu_dropin.py).  What stays restated rather than pinned is the inside of py_ecc and
+SageMath (exact integer arithmetic with canonical results); for it the oracle relies on
+  (i)   the mathematical definitions (DFT definition; group law on the fixed curves),
   (ii)  public curve constants / known multiples of the generators
-        (tests/golden/public_kat.json, see tests/test_oracle.py),
+        (tests/golden/public_kat.json), bilinearity of the restated pairing,
   (iii) the tau-identity  commit(ck, p) == p(tau)*G1  (kzg.py:108).
+BLS12-381 has no reference run (the reference's demos and fixtures are BN254 only): there the
+oracle is pinned by (i)-(iii) alone.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 reference legs may import this package.  The product (kzg_snark_b200/) never

@@ -9,9 +9,11 @@ this image.  The reference binds its callables at kzg.py:27-35,40-49 and calls
 them at kzg.py:72,115-116.  Restated from the library's published algorithm
 (optimized_curve.py): homogeneous projective points (x, y, z) over FQ,
 Z1 = (1, 1, 0), G1 = (Gx, Gy, 1), `double`, `add`, recursive binary `multiply`,
-`neg`, cross-multiplied `eq`, `normalize` = (x/z, y/z).  "parity unpinned" in the
-sense of SURVEY.md section 8c; pinned by the group law (canonical affine result)
-and the public known-answer multiples in tests/golden/public_kat.json.
+`neg`, cross-multiplied `eq`, `normalize` = (x/z, y/z).  The library's internals
+cannot be run here; these formulas are pinned by the group law (canonical affine
+result), the public known-answer multiples in tests/golden/public_kat.json and by
+the reference's own verifiers accepting proofs computed with them (pairing check,
+tests/golden/ref_trace_*.json via oracle/refrun.py).
 
 Points are tuples of plain ints (mod p) for speed; `FQ` is the presentation
 type with py_ecc's `.n` attribute used at the drop-in boundary.
