@@ -733,7 +733,8 @@ uint32_t choose_c(size_t n, int bits) {
 }
 
 // window size of the precomputed tables for a key of n points: minimise
-//   10 * n * W(c)  (mixed additions, 10 modmul each)  +  28 * 2^(c-1)  (bucket reduction, 2 full adds per bucket)
+//   10 * n * W(c)  (mixed additions, 10 modmul each)  +  56 * 2^(c-1)  (bucket reduction: 2 full adds per bucket
+//   plus the per-chunk fix-up and the tree sums; calibrated with scripts/c_sweep.py, profiles/r1_c_sweep.txt)
 // subject to the memory cap and to 31-bit point indices.  Returns 0 when tables are disabled.
 uint32_t choose_table_c(size_t n, int bits, size_t point_bytes) {
   const char* env = getenv("KZGPU_SRS_TABLES");
@@ -754,7 +755,7 @@ uint32_t choose_table_c(size_t n, int bits, size_t point_bytes) {
     uint32_t W = (bits + 1 + c - 1) / c;
     double mem = (double)W * (double)n * (double)point_bytes;
     if (mem > cap || (double)W * (double)n >= 2147483648.0) continue;
-    double cost = 10.0 * (double)(n ? n : 1) * W + 28.0 * (double)(1ull << (c - 1));
+    double cost = 10.0 * (double)(n ? n : 1) * W + 56.0 * (double)(1ull << (c - 1));
     if (cost < best) { best = cost; best_c = c; }
   }
   return best_c;
@@ -762,7 +763,7 @@ uint32_t choose_table_c(size_t n, int bits, size_t point_bytes) {
 
 template <class Cfg>
 int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, int mode, uint32_t* d_out,
-             const uint64_t* h_scalars = nullptr) {
+             const uint64_t* h_scalars = nullptr, uint32_t* h_out_xyzz = nullptr) {
   using P = typename Cfg::Fp;
   using R = typename Cfg::Fr;
   KzgpuCtx& cx = kz_ctx();
@@ -806,7 +807,11 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   if ((rc = g_ws.flag.ensure(4))) return rc;
   const size_t nblk = kz_div_up(nb, 1024);
   if ((rc = g_ws.blocksums.ensure(nblk * 4))) return rc;
+  // buckets per reduce thread: each thread walks a chain of 2*CH dependent XYZZ additions (~7 us each when a
+  // warp runs alone), so small bucket sets get short chunks -- enough threads to fill the SMs matters more than
+  // the ~20-addition fix-up (lo * running) every chunk pays
   uint32_t CH = 64;
+  while (CH > 8 && (nb / CH) < 65536) CH >>= 1;
   if (CH > B) CH = B;
   const uint32_t cpw = (B + CH - 1) / CH;
   if ((rc = g_ws.partials.ensure((size_t)cpw * Wb * 4 * P::N * 4))) return rc;
@@ -943,14 +948,58 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
     KZ_LAUNCHED();
     lvl_in = lvl_out; count = blocks; lvl_launches++;
   }
-  msm_final_kernel<Cfg><<<1, 32, 0, st>>>(lvl_in, Wb, c, mode, d_out);
+  // mode 2: the caller normalises on the host (one 256/384-bit inversion is ~20 us of CPU but ~200 us for a lone
+  // GPU thread); only the window fold stays on the device
+  msm_final_kernel<Cfg><<<1, 32, 0, st>>>(lvl_in, Wb, c, mode == 2 ? 0 : mode, d_out);
   KZ_LAUNCHED();
   prof_red.stop(1, (double)nb);
   uint32_t hflag = 0;
   KZ_CUDA(cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, st));
+  if (mode == 2 && h_out_xyzz) KZ_CUDA(cudaMemcpyAsync(h_out_xyzz, d_out, 4 * P::N * 4, cudaMemcpyDeviceToHost, st));
   KZ_CUDA(cudaStreamSynchronize(st));
   if (hflag) return kz_fail(KZGPU_ERANGE, "a scalar is not a canonical residue (>= 2^%d)", R::BITS);
   return 0;
+}
+
+// a^-1 mod p for a Montgomery-form element, on the host: binary extended Euclid on the raw limbs
+// (inverse of a*R is a^-1 R^-1), then two Montgomery multiplications by R^2 bring it back to a^-1 R.
+template <class P> Fe<P> host_fe_inv(const Fe<P>& a) {
+  constexpr int N = P::N;
+  auto is_one = [](const uint32_t* x) { for (int i = 1; i <= N; i++) if (x[i]) return false; return x[0] == 1; };
+  auto geq = [](const uint32_t* x, const uint32_t* y) { for (int i = N; i >= 0; i--) { if (x[i] != y[i]) return x[i] > y[i]; } return true; };
+  auto sub = [](uint32_t* x, const uint32_t* y) { uint64_t br = 0; for (int i = 0; i <= N; i++) { uint64_t d = (uint64_t)x[i] - y[i] - br; x[i] = (uint32_t)d; br = (d >> 63) & 1; } };
+  auto add = [](uint32_t* x, const uint32_t* y) { uint64_t c = 0; for (int i = 0; i <= N; i++) { c += (uint64_t)x[i] + y[i]; x[i] = (uint32_t)c; c >>= 32; } };
+  auto shr = [](uint32_t* x) { for (int i = 0; i < N; i++) x[i] = (x[i] >> 1) | (x[i + 1] << 31); x[N] >>= 1; };
+  uint32_t p[N + 1], u[N + 1], v[N + 1], x1[N + 1] = {0}, x2[N + 1] = {0};
+  for (int i = 0; i < N; i++) { p[i] = P::mod(i); u[i] = a.v[i]; v[i] = p[i]; }
+  p[N] = u[N] = v[N] = 0;
+  x1[0] = 1;
+  bool zero = true;
+  for (int i = 0; i < N; i++) zero = zero && !u[i];
+  if (zero) return a;
+  while (!is_one(u) && !is_one(v)) {
+    while (!(u[0] & 1)) { shr(u); if (x1[0] & 1) add(x1, p); shr(x1); }
+    while (!(v[0] & 1)) { shr(v); if (x2[0] & 1) add(x2, p); shr(x2); }
+    if (geq(u, v)) { sub(u, v); if (!geq(x1, x2)) add(x1, p); sub(x1, x2); }
+    else { sub(v, u); if (!geq(x2, x1)) add(x2, p); sub(x2, x1); }
+  }
+  const uint32_t* res = is_one(u) ? x1 : x2;
+  Fe<P> r;
+  for (int i = 0; i < N; i++) r.v[i] = res[i];
+  return fe_to_mont<P>(fe_to_mont<P>(r));
+}
+
+// XYZZ (Montgomery) -> canonical affine limbs + infinity flag, on the host
+template <class P> void host_xyzz_to_canonical(const uint32_t* h, uint32_t* out_xy, int* is_inf) {
+  XYZZ<P> a;
+  memcpy(a.x.v, h, 4 * P::N * 4);
+  if (xyzz_is_inf<P>(a)) { memset(out_xy, 0, 2 * P::N * 4); if (is_inf) *is_inf = 1; return; }
+  Fe<P> t = host_fe_inv<P>(fe_mul<P>(a.zz, a.zzz));
+  Fe<P> x = fe_from_mont<P>(fe_mul<P>(a.x, fe_mul<P>(t, a.zzz)));
+  Fe<P> y = fe_from_mont<P>(fe_mul<P>(a.y, fe_mul<P>(t, a.zz)));
+  memcpy(out_xy, x.v, P::N * 4);
+  memcpy(out_xy + P::N, y.v, P::N * 4);
+  if (is_inf) *is_inf = 0;
 }
 
 template <class Cfg>
@@ -958,12 +1007,10 @@ int msm_affine(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n
                const uint64_t* h_scalars = nullptr) {
   using P = typename Cfg::Fp;
   int rc;
-  if ((rc = g_ws.result.ensure((2 * P::N + 1) * 4))) return rc;
-  if ((rc = msm_core<Cfg>(srs, first, d_scalars, n, 1, (uint32_t*)g_ws.result.p, h_scalars))) return rc;
-  uint32_t h[2 * 12 + 1];
-  KZ_CUDA(cudaMemcpy(h, g_ws.result.p, (2 * P::N + 1) * 4, cudaMemcpyDeviceToHost));
-  memcpy(out_xy, h, 2 * P::N * 4);
-  if (is_inf) *is_inf = (int)h[2 * P::N];
+  if ((rc = g_ws.result.ensure((4 * P::N + 1) * 4))) return rc;
+  uint32_t h[4 * 12];
+  if ((rc = msm_core<Cfg>(srs, first, d_scalars, n, 2, (uint32_t*)g_ws.result.p, h_scalars, h))) return rc;
+  host_xyzz_to_canonical<P>(h, (uint32_t*)out_xy, is_inf);
   return 0;
 }
 

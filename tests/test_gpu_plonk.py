@@ -97,6 +97,31 @@ def test_synthetic_circuit_proof_is_accepted_and_tamper_rejected(logn, n_pub):
     assert not plonk_verifier.verify(vk, x, pf2)
 
 
+@pytest.mark.parametrize("logn", [4, 11])
+def test_bls12_381_prover_accepted_by_the_trapdoor_verifier(logn):
+    """The second curve of KZG.__init__ (kzg.py:31-35): same prover, BLS12-381 scalar field and G1;
+    checked with the trapdoor form of the reference's verifier equation."""
+    import plonk_verifier
+    from kzg_snark_b200.plonk import Indexer, Prover
+    from kzg_snark_b200.plonk_synth import synthetic_circuit
+    rq = CURVES["bls12_381"]["r"]
+    n, n_pub = 1 << logn, 3
+    qM, qL, qR, qO, qC, perm, w = synthetic_circuit(n, n_pub, rq, seed=40 + logn)
+    idx = Indexer("bls12_381")
+    ipk, ivk = idx.preprocess(qM, qL, qR, qO, qC, perm, max_degree=n + 5, rng=random.Random(7 + logn))
+    prover = Prover("bls12_381")
+    proof = prover.prove(ipk, [idx.kzg.Fq(v) for v in w[:n_pub]], w[n_pub:])
+    assert prover.last_r_zeta == 0 and not any(prover.last_t_top)
+    vk = {"commitments": {k: aff(c) for k, c in ivk["commitments"].items()}, "n": n, "g": int(ivk["subgroups"]["g"]),
+          "k1": int(ivk["subgroups"]["k1"]), "k2": int(ivk["subgroups"]["k2"]), "tau": ivk["tau"]}
+    pf = {"commitments": {k: aff(c) for k, c in proof["commitments"].items()},
+          "evaluations": {k: int(v) for k, v in proof["evaluations"].items()},
+          "kzg_proofs": {k: aff(c) for k, c in proof["kzg_proofs"].items()}}
+    assert plonk_verifier.verify_trapdoor(vk, w[:n_pub], pf, "bls12_381")
+    bad = {**pf, "evaluations": {**pf["evaluations"], "z_omega": (pf["evaluations"]["z_omega"] + 1) % rq}}
+    assert not plonk_verifier.verify_trapdoor(vk, w[:n_pub], bad, "bls12_381")
+
+
 # ----------------------------------------------------------------------------- kernels
 def _vec(ints):
     from kzg_snark_b200.plonk import DVec

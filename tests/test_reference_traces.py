@@ -120,3 +120,6 @@ def test_test_verifier_accepts_the_reference_provers_proof():
     bad = {**proof, "evaluations": {**proof["evaluations"], "a": proof["evaluations"]["a"] + 1}}
     assert not plonk_verifier.verify(ivk, x, bad)
     assert not plonk_verifier.verify(ivk, [x[0] + 1] + x[1:], proof)
+    # the trapdoor form of the same equation (used for BLS12-381, which has no pairing stand-in) agrees
+    assert plonk_verifier.verify_trapdoor(ivk, x, proof, "bn254")
+    assert not plonk_verifier.verify_trapdoor(ivk, x, bad, "bn254")
