@@ -135,7 +135,10 @@ class DVec:
             self.buf = None
 
     def __del__(self):
-        self.free()
+        try:
+            self.free()
+        except Exception:                      # interpreter shutdown: module globals may be gone
+            pass
 
 
 def _voidp_array(ptrs):

@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_$TAG.log
 tail -3 gpurun_out/pytest_$TAG.log
 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_$TAG.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py > gpurun_out/ncu_bench_$TAG.log 2>&1
 cat gpurun_out/bench_$TAG.json
 python scripts/prof_target.py 24 > gpurun_out/prof_plain_$TAG.log 2>&1 && \
