@@ -100,6 +100,10 @@ int kzgpu_msm_dev(uint64_t handle, size_t first, const uint64_t* d_scalars, size
 /* k polynomials of one commit() call (kzg.py:102): scalars concatenated, lens[j] limbs-of-4 counts */
 int kzgpu_msm_batch(uint64_t handle, const uint64_t* scalars, const size_t* lens, size_t k,
                     uint64_t* out_affine_xy, int* is_inf);
+/* same with the polynomials on the device: k vectors of poly_len scalars each, back to back (pad shorter ones with
+ * zeros: zero coefficients are skipped, kzg.py:113).  All k MSMs share one sort / accumulate / reduce pass. */
+int kzgpu_msm_batch_dev(uint64_t handle, const uint64_t* d_scalars, size_t poly_len, size_t k,
+                        uint64_t* out_affine_xy, int* is_inf);
 /* Partial sum for point-sharded multi-GPU MSM: result left un-normalised as XYZZ in
  * Montgomery form (4 * fp_limbs64 limbs), to be all-gathered and folded by kzgpu_g1_fold. */
 int kzgpu_msm_partial_dev(uint64_t handle, size_t first, const uint64_t* d_scalars, size_t n,

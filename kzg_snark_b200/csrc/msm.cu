@@ -119,15 +119,18 @@ constexpr uint32_t kSortStage = 11264;      // records staged per block in the p
 constexpr uint32_t kSortChunk = 16384;      // records per block in pass 2 (64 KB staged)
 constexpr uint32_t kMaxCoarse = 4096;
 
-struct SortGeom { uint32_t c, W, B, f, ncoarse, tabled, first, n_srs, top_bits; };
+struct SortGeom { uint32_t c, W, B, f, ncoarse, tabled, first, n_srs, top_bits, batch_len; };   // batch_len: scalars per polynomial of a batched pass (0 = one MSM)
 
 __device__ __forceinline__ bool digit_entry(const uint32_t* s, uint32_t w, const SortGeom& g, uint32_t i, uint32_t& key, uint32_t& val) {
   int d = signed_digit(s, w, g.c, g.W);
   if (d == 0) return false;
   uint32_t neg = d < 0 ? 1u : 0u;
   uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
-  if (g.tabled) { key = mag - 1; val = (w * g.n_srs + g.first + i) | (neg << 31); }
-  else { key = w * g.B + (mag - 1); val = (g.first + i) | (neg << 31); }
+  // batched pass: scalar i belongs to polynomial j = i / batch_len, whose buckets form their own set(s)
+  uint32_t j = 0;
+  if (g.batch_len) { j = i / g.batch_len; i -= j * g.batch_len; }
+  if (g.tabled) { key = j * g.B + (mag - 1); val = (w * g.n_srs + g.first + i) | (neg << 31); }
+  else { key = (j * g.W + w) * g.B + (mag - 1); val = (g.first + i) | (neg << 31); }
   return true;
 }
 
@@ -600,14 +603,15 @@ __global__ void __launch_bounds__(128) msm_window_kernel(const uint32_t* __restr
 template <class Cfg>
 __global__ void msm_final_kernel(const uint32_t* __restrict__ winsums, uint32_t W, uint32_t c, int mode, uint32_t* __restrict__ out) {
   using P = typename Cfg::Fp;
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (threadIdx.x != 0) return;
+  winsums += (size_t)blockIdx.x * W * 4 * P::N;        // block j: polynomial j of a batched pass
   XYZZ<P> acc = xyzz_inf<P>();
   for (uint32_t w = W; w-- > 0;) {
     if (!xyzz_is_inf<P>(acc))
       for (uint32_t k = 0; k < c; k++) acc = xyzz_dbl<P>(acc);
     acc = xyzz_add<P>(acc, ld_xyzz<P>(winsums, w));
   }
-  if (mode == 0) { st_xyzz<P>(out, 0, acc); return; }
+  if (mode == 0) { st_xyzz<P>(out, blockIdx.x, acc); return; }
   Affine<P> a = xyzz_to_affine<P>(acc);
   Fe<P> x = fe_from_mont<P>(a.x), y = fe_from_mont<P>(a.y);
   for (int i = 0; i < P::N; i++) { out[i] = x.v[i]; out[P::N + i] = y.v[i]; }
@@ -763,7 +767,10 @@ uint32_t choose_table_c(size_t n, int bits, size_t point_bytes) {
 
 template <class Cfg>
 int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, int mode, uint32_t* d_out,
-             const uint64_t* h_scalars = nullptr, uint32_t* h_out_xyzz = nullptr) {
+             const uint64_t* h_scalars = nullptr, uint32_t* h_out_xyzz = nullptr, uint32_t batch = 1) {
+  // batch > 1: d_scalars holds `batch` polynomials of n / batch scalars each (zero padded to equal length); they
+  // share one sort / accumulate / reduce pass, every polynomial owning its own bucket set(s), and d_out receives
+  // `batch` XYZZ results (mode 0 / 2 only)
   using P = typename Cfg::Fp;
   using R = typename Cfg::Fr;
   KzgpuCtx& cx = kz_ctx();
@@ -783,7 +790,8 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   const bool tabled = srs.c_tab != 0;
   const uint32_t c = tabled ? srs.c_tab : choose_c(n, R::BITS);
   const uint32_t W = (R::BITS + 1 + c - 1) / c;          // digits per scalar
-  const uint32_t Wb = tabled ? 1u : W;                   // bucket sets
+  const uint32_t Wp = tabled ? 1u : W;                   // bucket sets per polynomial
+  const uint32_t Wb = Wp * batch;                        // bucket sets of the pass
   const uint32_t B = 1u << (c - 1);
   const size_t nb = (size_t)Wb * B;                     // buckets = sort keys
   if (first + n > 0x7fffffffull) return kz_fail(KZGPU_EINVAL, "MSM index range exceeds 2^31");
@@ -834,6 +842,7 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   geo.c = c; geo.W = W; geo.B = B; geo.f = f; geo.ncoarse = ncoarse; geo.tabled = tabled ? 1u : 0u;
   geo.first = (uint32_t)first; geo.n_srs = (uint32_t)srs.n;
   geo.top_bits = R::BITS - 224;                  // bits allowed in the top 32-bit word
+  geo.batch_len = batch > 1 ? (uint32_t)(n / batch) : 0u;
   DigitOffset doff;
   for (int k = 0; k < 8; k++) doff.w[k] = 0;
   for (uint32_t w = 0; w + 1 < W; w++) {
@@ -880,7 +889,7 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   }
   const uint32_t ostride = 1u;                          // offsets[] entries per bucket
   // tasks: split heavy buckets, sort by length
-  uint32_t mean = (uint32_t)(((size_t)n * (tabled ? W : 1u)) / B) + 1;
+  uint32_t mean = (uint32_t)((((size_t)n / batch) * (tabled ? W : 1u)) / B) + 1;
   uint32_t T = 32;
   while (T < 2 * mean && T < 1024) T <<= 1;
   const size_t max_tasks = nb + ((size_t)n * W) / T + 1;
@@ -950,12 +959,12 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   }
   // mode 2: the caller normalises on the host (one 256/384-bit inversion is ~20 us of CPU but ~200 us for a lone
   // GPU thread); only the window fold stays on the device
-  msm_final_kernel<Cfg><<<1, 32, 0, st>>>(lvl_in, Wb, c, mode == 2 ? 0 : mode, d_out);
+  msm_final_kernel<Cfg><<<batch, 32, 0, st>>>(lvl_in, Wp, c, mode == 2 ? 0 : mode, d_out);
   KZ_LAUNCHED();
   prof_red.stop(1, (double)nb);
   uint32_t hflag = 0;
   KZ_CUDA(cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, st));
-  if (mode == 2 && h_out_xyzz) KZ_CUDA(cudaMemcpyAsync(h_out_xyzz, d_out, 4 * P::N * 4, cudaMemcpyDeviceToHost, st));
+  if (mode == 2 && h_out_xyzz) KZ_CUDA(cudaMemcpyAsync(h_out_xyzz, d_out, (size_t)batch * 4 * P::N * 4, cudaMemcpyDeviceToHost, st));
   KZ_CUDA(cudaStreamSynchronize(st));
   if (hflag) return kz_fail(KZGPU_ERANGE, "a scalar is not a canonical residue (>= 2^%d)", R::BITS);
   return 0;
@@ -1011,6 +1020,19 @@ int msm_affine(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n
   uint32_t h[4 * 12];
   if ((rc = msm_core<Cfg>(srs, first, d_scalars, n, 2, (uint32_t*)g_ws.result.p, h_scalars, h))) return rc;
   host_xyzz_to_canonical<P>(h, (uint32_t*)out_xy, is_inf);
+  return 0;
+}
+
+// k equal-length polynomials in one pass -> k canonical affine points
+template <class Cfg>
+int msm_affine_batch(const Srs& srs, const uint32_t* d_scalars, size_t poly_len, size_t k, uint64_t* out_xy, int* is_inf) {
+  using P = typename Cfg::Fp;
+  int rc;
+  if ((rc = g_ws.result.ensure(k * 4 * P::N * 4 + 4))) return rc;
+  std::vector<uint32_t> h(k * 4 * P::N);
+  if ((rc = msm_core<Cfg>(srs, 0, d_scalars, poly_len * k, 2, (uint32_t*)g_ws.result.p, nullptr, h.data(), (uint32_t)k))) return rc;
+  for (size_t j = 0; j < k; j++)
+    host_xyzz_to_canonical<P>(&h[j * 4 * P::N], (uint32_t*)out_xy + j * 2 * P::N, is_inf ? is_inf + j : nullptr);
   return 0;
 }
 
@@ -1244,24 +1266,72 @@ int kzgpu_msm(uint64_t handle, size_t first, const uint64_t* scalars, size_t n, 
   return kz_msm_dev_internal(handle, first, (const uint32_t*)g_ws.scal.p, n, out_affine_xy, is_inf, scalars);
 }
 
+// can the k polynomials share one pass?  (bucket sets and digit entries must fit the sort's key and index ranges)
+static bool batch_fits(const Srs& s, size_t poly_len, size_t k) {
+  if (k < 2 || k > 64 || poly_len == 0) return false;
+  const int bits = s.curve == KZGPU_BN254 ? FrBN254::BITS : FrBLS381::BITS;
+  const uint32_t c = s.c_tab ? s.c_tab : choose_c(poly_len, bits);
+  const uint32_t W = (bits + 1 + c - 1) / c;
+  const size_t nb = (size_t)(s.c_tab ? 1u : W) * k << (c - 1);
+  return nb <= ((size_t)kMaxCoarse << 13) && (size_t)poly_len * k * W < 0xffffffffull && poly_len * k < 0x7fffffffull;
+}
+
+int kz_msm_batch_dev_internal(uint64_t handle, const uint32_t* d_scalars, size_t poly_len, size_t k, uint64_t* out_xy, int* is_inf) {
+  const Srs* s = find_srs(handle);
+  if (!s) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle %llu", (unsigned long long)handle);
+  if (poly_len > s->n)
+    return kz_fail(KZGPU_ERANGE, "Polynomial degree %zu exceeds maximum allowed degree %zu", poly_len - 1, s->n - 1);
+  const int L = kzgpu_fp_limbs64(s->curve);
+  int rc = set_smem_attrs();
+  if (rc) return rc;
+  if (!batch_fits(*s, poly_len, k)) {                 // one pass per polynomial
+    for (size_t j = 0; j < k; j++) {
+      rc = kz_msm_dev_internal(handle, 0, d_scalars + j * poly_len * 8, poly_len, out_xy + j * 2 * L, is_inf ? is_inf + j : nullptr, nullptr);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  if (s->curve == KZGPU_BN254) return msm_affine_batch<BN254Cfg>(*s, d_scalars, poly_len, k, out_xy, is_inf);
+  return msm_affine_batch<BLS381Cfg>(*s, d_scalars, poly_len, k, out_xy, is_inf);
+}
+
+int kzgpu_msm_batch_dev(uint64_t handle, const uint64_t* d_scalars, size_t poly_len, size_t k, uint64_t* out_affine_xy, int* is_inf) {
+  KZ_REQUIRE_INIT();
+  if (k && (!out_affine_xy || (poly_len && !d_scalars))) return kz_fail(KZGPU_EINVAL, "null pointer");
+  if (!k) return 0;
+  return kz_msm_batch_dev_internal(handle, (const uint32_t*)d_scalars, poly_len, k, out_affine_xy, is_inf);
+}
+
 int kzgpu_msm_batch(uint64_t handle, const uint64_t* scalars, const size_t* lens, size_t k, uint64_t* out_affine_xy, int* is_inf) {
   KZ_REQUIRE_INIT();
   if (k && (!lens || !out_affine_xy)) return kz_fail(KZGPU_EINVAL, "null pointer");
-  int curve = kz_srs_curve(handle);
-  if (curve < 0) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle %llu", (unsigned long long)handle);
-  const int L = kzgpu_fp_limbs64(curve);
-  size_t total = 0;
-  for (size_t j = 0; j < k; j++) total += lens[j];
-  uint32_t* d = nullptr;
-  int rc = upload_scalars(scalars, total, &d);
+  const Srs* s = find_srs(handle);
+  if (!s) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle %llu", (unsigned long long)handle);
+  if (!k) return 0;
+  size_t maxlen = 0, total = 0;
+  for (size_t j = 0; j < k; j++) { total += lens[j]; if (lens[j] > maxlen) maxlen = lens[j]; }
+  if (maxlen > s->n)                                   // the degree check of kzg.py:103-106, before any work
+    return kz_fail(KZGPU_ERANGE, "Polynomial degree %zu exceeds maximum allowed degree %zu", maxlen - 1, s->n - 1);
+  // the k polynomials of one commit() call, zero padded to a common length, share one pass (zero scalars emit no digits)
+  KzgpuCtx& cx = kz_ctx();
+  int rc = g_ws.scal.ensure(k * maxlen * 32 + 32);
   if (rc) return rc;
+  uint32_t* d = (uint32_t*)g_ws.scal.p;
+  if (total != k * maxlen) KZ_CUDA(cudaMemsetAsync(d, 0, k * maxlen * 32, cx.stream));
   size_t off = 0;
   for (size_t j = 0; j < k; j++) {
-    rc = kz_msm_dev_internal(handle, 0, d + off * 8, lens[j], out_affine_xy + j * 2 * L, is_inf ? is_inf + j : nullptr, nullptr);
-    if (rc) return rc;
+    if (lens[j]) KZ_CUDA(cudaMemcpyAsync(d + j * maxlen * 8, scalars + off * 4, lens[j] * 32, cudaMemcpyHostToDevice, cx.stream));
     off += lens[j];
   }
-  return 0;
+  if (maxlen == 0 || k == 1) {
+    const int L = kzgpu_fp_limbs64(s->curve);
+    for (size_t j = 0; j < k; j++) {
+      rc = kz_msm_dev_internal(handle, 0, d + j * maxlen * 8, maxlen, out_affine_xy + j * 2 * L, is_inf ? is_inf + j : nullptr, nullptr);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  return kz_msm_batch_dev_internal(handle, d, maxlen, k, out_affine_xy, is_inf);
 }
 
 int kzgpu_msm_partial_dev(uint64_t handle, size_t first, const uint64_t* d_scalars, size_t n, uint64_t* d_out_xyzz) {

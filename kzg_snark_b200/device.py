@@ -154,6 +154,19 @@ def msm_batch(srs, scalar_arrays):
     return out, [bool(x) for x in inf]
 
 
+def msm_batch_dev(srs, dbuf, poly_len, k):
+    """k polynomials of `poly_len` scalars each, back to back on the device (zero padded), in one
+    sort / accumulate / reduce pass -> ((k, 2*L) affine limbs, [is_inf])."""
+    lib = _ffi.init()
+    out = np.zeros((k, 2 * FP_LIMBS[srs.curve]), dtype=np.uint64)
+    inf = (ctypes.c_int * k)()
+    rc = lib.kzgpu_msm_batch_dev(srs.handle, dbuf.ptr, poly_len, k, ptr(out), inf)
+    if rc == _ffi.E_RANGE:
+        raise ValueError(_ffi.last_error())
+    check(rc)
+    return out, [bool(x) for x in inf]
+
+
 def msm_partial_dev(srs, dbuf, n, dout, first=0):
     """Un-normalised XYZZ partial sum left on the device (multi-GPU shard)."""
     check(_ffi.init().kzgpu_msm_partial_dev(srs.handle, first, dbuf.ptr, n, dout.ptr))

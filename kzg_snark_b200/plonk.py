@@ -141,6 +141,29 @@ class DVec:
             pass
 
 
+class _View:
+    """A window of a DVec starting at element `off` (same interface, no ownership)."""
+
+    def __init__(self, base, off):
+        self.base, self.off = base, off
+
+    @property
+    def ptr(self):
+        return self.base.at(self.off)
+
+    def at(self, i):
+        return self.base.at(self.off + i)
+
+    def write(self, i, ints, r):
+        self.base.write(self.off + i, ints, r)
+
+    def read_ints(self, i=0, count=None):
+        return self.base.read_ints(self.off + i, count)
+
+    def copy_from(self, src, count, dst_off=0, src_off=0):
+        self.base.copy_from(src, count, self.off + dst_off, src_off)
+
+
 def _voidp_array(ptrs):
     return (ctypes.c_void_p * len(ptrs))(*[p.value if isinstance(p, ctypes.c_void_p) else p for p in ptrs])
 
@@ -331,18 +354,19 @@ class Prover:
         f.intt(pi, n, g)
 
         # ---- round 1 (plonk/prover.py:78-93): wire polynomials with degree-1 blinding
-        wire_polys = []
+        wire_buf = DVec(3 * (n + 2), zero=True)                         # a | b | c coefficients, one batched MSM
+        wire_polys = [_View(wire_buf, j * (n + 2)) for j in range(3)]
         for j, (bh, bl) in enumerate(((b1, b2), (b3, b4), (b5, b6))):
-            p = DVec(n + 2, zero=True)
+            p = wire_polys[j]
             p.copy_from(wires, n, 0, j * n)
             f.intt(p, n, g)
             lo = p.read_ints(0, 2)                                      # (bh X + bl)(X^n - 1) + interp
             p.write(0, [lo[0] - bl, lo[1] - bh], r)
             p.write(n, [bl, bh], r)
-            wire_polys.append(p)
         a_poly, b_poly, c_poly = wire_polys
         lap("round1_upload_intt")
-        wire_commitments = [commit(p, n + 2) for p in wire_polys]
+        outs, infs = device.msm_batch_dev(srs, wire_buf, n + 2, 3)
+        wire_commitments = [kzg._codec.from_device(o, i) for o, i in zip(outs, infs)]
         lap("round1_msm")
         transcript.append_message("round1-commitments", wire_commitments)
         beta = transcript.get_challenge("beta")
@@ -383,15 +407,16 @@ class Prover:
         f.coset_ntt(t, n4, w4, shift, inverse=True)
         for e in ev.values():
             e.free()
-        t_lo, t_mid, t_hi = DVec(n + 1), DVec(n + 1), DVec(n + 6)
+        t_buf = DVec(3 * (n + 6), zero=True)                            # t_lo | t_mid | t_hi, padded to n + 6 each
+        t_lo, t_mid, t_hi = (_View(t_buf, j * (n + 6)) for j in range(3))
         f.lincomb(t_lo, n + 1, [(t.at(0), n, 1)])                       # t_lo + b10 X^n
         t_lo.write(n, [b10], r)
         f.lincomb(t_mid, n + 1, [(t.at(n), n, 1)], constant=-b10)       # t_mid - b10 + b11 X^n
         t_mid.write(n, [b11], r)
         f.lincomb(t_hi, n + 6, [(t.at(2 * n), n + 6, 1)], constant=-b11)  # t_hi - b11
-        t_polys = [(t_lo, n + 1), (t_mid, n + 1), (t_hi, n + 6)]
         lap("round3_quotient")
-        t_commitments = [commit(v, length) for v, length in t_polys]
+        outs, infs = device.msm_batch_dev(srs, t_buf, n + 6, 3)
+        t_commitments = [kzg._codec.from_device(o, i) for o, i in zip(outs, infs)]
         lap("round3_msm")
         transcript.append_message("round3-commitments", t_commitments)
         zeta = transcript.get_challenge("zeta")
@@ -445,7 +470,7 @@ class Prover:
         self.last_r_zeta = f.eval(r_poly, n + 6, zi)                    # plonk/prover.py:171 asserts this is 0
         self.last_t_top = t.read_ints(3 * n + 6, min(8, n4 - 3 * n - 6))   # deg t <= 3n+5: must be zeros
 
-        for vec in (wires, pi, t, r_poly, a_poly, b_poly, c_poly, z_poly, t_lo, t_mid, t_hi):
+        for vec in (wires, pi, t, r_poly, wire_buf, z_poly, t_buf):
             vec.free()
         return {
             "commitments": {"a": wire_commitments[0], "b": wire_commitments[1], "c": wire_commitments[2], "z": z_commit,

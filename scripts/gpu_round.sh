@@ -14,3 +14,11 @@ python scripts/prof_target.py 24 > gpurun_out/prof_plain_$TAG.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:'msm_accumulate|ntt_pass|msm_partition|msm_fine_scatter' -c 6 \
     -f -o gpurun_out/prof_$TAG python scripts/prof_target.py 24 > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -3 gpurun_out/ncu_full_$TAG.log
+# keep the raw-page CSV (what profiles/ summarises), not the 50 MB report: gpurun_out/ is capped at 64 MiB
+ncu -i gpurun_out/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_raw.csv 2>/dev/null && rm -f gpurun_out/prof_$TAG.ncu-rep
+python scripts/prof_plonk.py 20 > gpurun_out/prof_plonk_$TAG.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'quotient_kernel|batch_ratio_kernel|perm_ratio_kernel|msm_reduce_kernel' -c 4 \
+    -f -o gpurun_out/prof_plonk_$TAG python scripts/prof_plonk.py 20 > gpurun_out/ncu_full_plonk_$TAG.log 2>&1
+tail -3 gpurun_out/ncu_full_plonk_$TAG.log
+ncu -i gpurun_out/prof_plonk_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_plonk_${TAG}_raw.csv 2>/dev/null && rm -f gpurun_out/prof_plonk_$TAG.ncu-rep
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2

@@ -1,7 +1,8 @@
 """Condense an .ncu-rep (read here with `ncu -i`) into a small per-launch CSV for profiles/."""
 import csv, subprocess, sys
 rep, out = sys.argv[1], sys.argv[2]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = open(rep).read() if rep.endswith(".csv") else \
+    subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 h, units = rows[0], rows[1]
 want = ["ID", "Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",

@@ -328,3 +328,56 @@ def test_msm_tau_identity_at_baseline_size(dev):
     out, inf = dev.msm(srs, sc)                                        # host scalars, chunked upload
     assert point_of(cv, out, inf, 4) == exp
     d.free(); srs.destroy()
+
+
+@pytest.mark.parametrize("curve", CURVE_NAMES)
+@pytest.mark.parametrize("mode", ["auto", "0"])
+def test_msm_batch_single_pass_matches_per_polynomial(dev, curve, mode, monkeypatch):
+    """KZG.commit(ck, [k polys]) (kzg.py:102): the k MSMs share one sort/accumulate/reduce pass;
+    every result must equal the tau-identity of its own polynomial -- tabled and plain keys, ragged
+    lengths, a zero polynomial and an empty one, zero coefficients, device-resident equal-length form."""
+    from kzg_snark_b200 import _ffi
+    cv = get_curve(curve)
+    nl = CURVES[curve]["fp_limbs32"] // 2
+    if mode != "auto":
+        monkeypatch.setenv("KZGPU_SRS_TABLES", mode)
+    rng = random.Random(33)
+    tau = rng.randrange(1, cv.r)
+    n = 700
+    srs = dev.Srs.generate(curve, tau, n)
+    polys = [[rng.randrange(cv.r) for _ in range(m)] for m in (700, 1, 333, 64)]
+    polys += [[0] * 50, [], [0, 0, 5, 0, cv.r - 1], [rng.randrange(1 << 20) for _ in range(699)]]
+    out, infs = dev.msm_batch(srs, [L(p, cv.r) if p else np.zeros((0, 4), np.uint64) for p in polys])
+    for p, o, f in zip(polys, out, infs):
+        t = poly_eval(p, tau, cv.r)
+        exp = cv.normalize(cv.multiply(cv.G1, t)) if t else None
+        assert point_of(cv, o, f, nl) == exp
+    # device-resident, equal length (what the PLONK prover uses for a | b | c and t_lo | t_mid | t_hi)
+    m, k = 513, 5
+    eq = [[rng.randrange(cv.r) for _ in range(m)] for _ in range(k)]
+    eq[2] = [0] * m
+    d = _ffi.DeviceBuffer(k * m * 32).upload(np.concatenate([L(p, cv.r) for p in eq]))
+    out, infs = dev.msm_batch_dev(srs, d, m, k)
+    for p, o, f in zip(eq, out, infs):
+        t = poly_eval(p, tau, cv.r)
+        assert point_of(cv, o, f, nl) == (cv.normalize(cv.multiply(cv.G1, t)) if t else None)
+    with pytest.raises(ValueError, match="exceeds maximum allowed degree 699"):
+        dev.msm_batch_dev(srs, d, 701, 2)
+    d.free(); srs.destroy()
+
+
+def test_msm_batch_large_matches_single(dev):
+    """2^18-point polynomials: the batched pass and three single MSMs give identical points."""
+    from kzg_snark_b200 import _ffi
+    from kzg_snark_b200.limbs import random_scalars
+    cv = get_curve("bn254")
+    n, k = (1 << 18) + 6, 3
+    srs = dev.Srs.generate("bn254", 0xABCDEF123456789, n)
+    sc = random_scalars(n * k, cv.r, seed=77)
+    sc[n + 5:2 * n] = 0                                       # a mostly-zero polynomial (padding case)
+    d = _ffi.DeviceBuffer(n * k * 32).upload(sc)
+    out, infs = dev.msm_batch_dev(srs, d, n, k)
+    for j in range(k):
+        o1, f1 = dev.msm(srs, sc[j * n:(j + 1) * n])
+        assert f1 == infs[j] and (o1 == out[j]).all()
+    d.free(); srs.destroy()
