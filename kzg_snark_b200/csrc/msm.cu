@@ -778,11 +778,20 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   // Host scalars (the e2e entry point): the upload is split into chunks on the copy stream and the
   // MSM runs chunk by chunk into the same buckets, so that all but the first chunk's PCIe time
   // hides behind the sort + accumulate of the previous chunk.
+  // Chunk sizes grow (1/16, 3/16, 1/4, 1/2 of the scalars): only the first chunk's transfer is exposed, so it is
+  // the smallest; each later transfer has the previous chunk's (shorter or equal) compute to hide behind.
   const uint32_t nchunks = (h_scalars && n >= (1u << 20)) ? 4u : 1u;
-  const size_t chunk_n = kz_div_up(n, nchunks);
+  size_t chunk_lo[5] = {0, n, n, n, n};
+  if (nchunks == 4) {
+    const char* env = getenv("KZGPU_MSM_CHUNKS");      // "uniform": four equal chunks (A/B measurements)
+    if (env && env[0] == 'u') { chunk_lo[1] = n / 4; chunk_lo[2] = n / 2; chunk_lo[3] = 3 * (n / 4); }
+    else { chunk_lo[1] = n / 16; chunk_lo[2] = n / 4; chunk_lo[3] = n / 2; }
+  }
+  size_t chunk_n = 0;                                   // largest chunk: sizes the sort scratch
+  for (uint32_t k = 0; k < nchunks; k++) if (chunk_lo[k + 1] - chunk_lo[k] > chunk_n) chunk_n = chunk_lo[k + 1] - chunk_lo[k];
   if (h_scalars && n) {
     for (uint32_t k = 0; k < nchunks; k++) {
-      size_t lo = k * chunk_n, cnt = lo < n ? (n - lo < chunk_n ? n - lo : chunk_n) : 0;
+      size_t lo = chunk_lo[k], cnt = chunk_lo[k + 1] - chunk_lo[k];
       if (cnt) KZ_CUDA(cudaMemcpyAsync((void*)(d_scalars + lo * 8), h_scalars + lo * 4, cnt * 32, cudaMemcpyHostToDevice, cx.copy_stream));
       KZ_CUDA(cudaEventRecord(cx.copy_ev[k], cx.copy_stream));
     }
@@ -852,8 +861,8 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   const uint32_t* d_scalars_all = d_scalars;
   const size_t n_all = n, first_all = first;
   for (uint32_t chunk = 0; chunk < nchunks; chunk++) {
-  const size_t c_lo = chunk * chunk_n;
-  n = c_lo < n_all ? (n_all - c_lo < chunk_n ? n_all - c_lo : chunk_n) : 0;
+  const size_t c_lo = chunk_lo[chunk];
+  n = chunk_lo[chunk + 1] - c_lo;
   if (chunk && !n) break;
   d_scalars = d_scalars_all + c_lo * 8;
   first = first_all + c_lo;
