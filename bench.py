@@ -511,17 +511,40 @@ def run_gpu(args):
         srs_n = 6 * m_
         srs = device.Srs.generate("bn254", TAU, srs_n)
         lib = _ffi._lib
-        from kzg_snark_b200.parallel import round_robin
+        from kzg_snark_b200.parallel import lpt_assign, shard_range
         L = lambda v: _ffi.ptr(ints_to_limbs([v], R_BN254)[0])           # noqa: E731
+        SHARD_MIN = 1 << 22          # MSMs at least this long are point-sharded over all ranks instead of owned by one
 
         def rand_dev(cnt, seed):
             return _ffi.DeviceBuffer(cnt * 32).upload(random_scalars(cnt, R_BN254, seed=seed))
 
-        my_c = [(j, rand_dev(commits[j], 500 + j)) for j in round_robin(len(commits), world, rank)]
-        my_n = [(j, rand_dev(ntts[j][0], 600 + j)) for j in round_robin(len(ntts), world, rank)]
-        my_o = [(j, [rand_dev(c, 700 + 10 * j + i) for i, c in enumerate(opens[j])]) for j in round_robin(len(opens), world, rank)]
+        # work items: (kind, index, cost); big MSMs are split over every rank (cost / world each), the rest are
+        # assigned whole, longest first (parallel.lpt_assign)
+        sharded_c = [j for j, ln in enumerate(commits) if world > 1 and ln >= SHARD_MIN]
+        sharded_o = [j for j, ls in enumerate(opens) if world > 1 and max(ls) >= SHARD_MIN]
+        whole = [("c", j, commits[j]) for j in range(len(commits)) if j not in sharded_c]
+        whole += [("n", j, ntts[j][0] // 8) for j in range(len(ntts))]
+        whole += [("o", j, max(opens[j]) + sum(opens[j]) // 4) for j in range(len(opens)) if j not in sharded_o]
+        owner = lpt_assign([w[2] for w in whole], world)
+        mine = [w for w, o in zip(whole, owner) if o == rank]
+        my_c = [(j, rand_dev(commits[j], 500 + j)) for kind, j, _ in mine if kind == "c"]
+        my_n = [(j, rand_dev(ntts[j][0], 600 + j)) for kind, j, _ in mine if kind == "n"]
+        my_o = [(j, [rand_dev(c, 700 + 10 * j + i) for i, c in enumerate(opens[j])]) for kind, j, _ in mine if kind == "o"]
+        sh_c = []                                                        # (start, count, this rank's slice of the scalars)
+        for j in sharded_c:
+            s0, cnt = shard_range(commits[j], world, rank)
+            sh_c.append((s0, cnt, rand_dev(cnt, 800 + 16 * j + rank)))
+        sh_o = [(j, [rand_dev(c, 700 + 10 * j + i) for i, c in enumerate(opens[j])], _ffi.DeviceBuffer(max(opens[j]) * 32))
+                for j in sharded_o]                                      # polynomials replicated, quotient scratch
+        if world > 1:
+            partial = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            gathered = torch.zeros(128 * world, dtype=torch.uint8, device="cuda")
         w_of = {sz: ints_to_limbs([pow(5, (R_BN254 - 1) // sz, R_BN254)], R_BN254)[0] for sz in (n_, m_)}
         zl, xil = 0x1234567 % R_BN254, 0x7654321 % R_BN254
+
+        def gather_fold():
+            dist.all_gather_into_tensor(gathered, partial)
+            return device.g1_fold("bn254", RawPtr(gathered.data_ptr()), world)
 
         def step():
             for j, d in my_c:
@@ -535,6 +558,18 @@ def run_gpu(args):
                 ptrs = (ctypes.c_void_p * k)(*[d.ptr.value for d in ds])
                 lens = (ctypes.c_size_t * k)(*opens[j])
                 _ffi.check(lib.kzgpu_open_dev(srs.handle, ptrs, lens, k, L(zl), L(xil), _ffi.ptr(out), ctypes.byref(fl), None))
+            for s0, cnt, d in sh_c:                                      # point-sharded commit: partial -> all-gather -> fold
+                device.msm_partial_dev(srs, d, cnt, RawPtr(partial.data_ptr()), first=s0)
+                gather_fold()
+            for j, ds, dq in sh_o:                                       # point-sharded open: quotient everywhere, MSM by range
+                k = len(ds)
+                ptrs = (ctypes.c_void_p * k)(*[d.ptr.value for d in ds])
+                lens = (ctypes.c_size_t * k)(*opens[j])
+                ql = ctypes.c_size_t(0)
+                _ffi.check(lib.kzgpu_open_quotient_dev(_ffi.BN254, ptrs, lens, k, L(zl), L(xil), dq.ptr, ctypes.byref(ql), None))
+                s0, cnt = shard_range(ql.value, world, rank)
+                device.msm_partial_dev(srs, RawPtr(dq.ptr.value + 32 * s0), cnt, RawPtr(partial.data_ptr()), first=s0)
+                gather_fold()
 
         for _ in range(Wm):
             step()
@@ -558,8 +593,8 @@ def run_gpu(args):
                               "scaling": "strong", "vs_baseline": None,
                               "dtype": "u32x8 (256-bit modular integers, Montgomery)", "data": "synthetic",
                               "config": {"workload": f"commit/open/NTT calls of one Marlin proof, 2^{args.marlin_logn} constraints "
-                                                     f"(|H|=2^{args.marlin_logn}, |K|=2^{args.marlin_logn + 1}), items round-robin over {world} GPUs, "
-                                                     "SRS replicated", "items": res["items"], "srs_points": res["srs_points"],
+                                                     f"(|H|=2^{args.marlin_logn}, |K|=2^{args.marlin_logn + 1}) on {world} GPUs: MSMs of >= 2^22 points point-sharded over all ranks, "
+                                                     "the rest assigned longest-first, SRS replicated", "items": res["items"], "srs_points": res["srs_points"],
                                          "srs_layout": res["srs"]},
                               "clocks": res["clocks"], "gpu_launches": res["launches"], "device": info["name"]}))
         if dist is not None:

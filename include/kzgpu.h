@@ -148,6 +148,12 @@ int kzgpu_open_dev(uint64_t handle, const uint64_t* const* d_polys, const size_t
                    const uint64_t* z, const uint64_t* xi, uint64_t* out_affine_xy, int* is_inf,
                    uint64_t* eval_out);
 
+/* the polynomial half with device-resident inputs, quotient left on the device (max(lens) - 1 coefficients): lets a
+ * multi-GPU host MSM index ranges of the quotient with kzgpu_msm_partial_dev (point-sharded open) */
+int kzgpu_open_quotient_dev(int field, const uint64_t* const* d_polys, const size_t* lens, size_t k,
+                            const uint64_t* z, const uint64_t* xi, uint64_t* d_quotient, size_t* quot_len,
+                            uint64_t* eval_out);
+
 /* ---- polynomial kernels for the callers of commit / open ----------------- */
 /* The reference's PLONK prover does this work with Sage polynomial arithmetic between its
  * kzg.commit / kzg.open / fft_ff_interpolation calls; these keep it on the device so that the

@@ -73,6 +73,7 @@ SIGNATURES = {
     "kzgpu_open": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_void_p, _szp, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _intp, ctypes.c_void_p]),
     "kzgpu_open_quotient": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, _szp, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _szp, ctypes.c_void_p]),
     "kzgpu_open_dev": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_void_p, _szp, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _intp, ctypes.c_void_p]),
+    "kzgpu_open_quotient_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, _szp, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _szp, ctypes.c_void_p]),
     "kzgpu_poly_eval_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
     "kzgpu_poly_lincomb_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, _szp, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "kzgpu_powers_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),

@@ -190,7 +190,7 @@ int open_impl(uint64_t handle, bool do_msm, const uint64_t* polys, const uint64_
   if ((rc = suffix_horner<P>((uint32_t*)g_pw.comb.p, maxlen, fe_to_mont<P>(zc), (uint32_t*)g_pw.t.p))) return rc;
   uint32_t* d_T = (uint32_t*)g_pw.t.p;
   if (eval_out) KZ_CUDA(cudaMemcpyAsync(eval_out, d_T, 32, cudaMemcpyDeviceToHost, cx.stream));
-  if (quotient && maxlen > 1) KZ_CUDA(cudaMemcpyAsync(quotient, d_T + P::N, (maxlen - 1) * 32, cudaMemcpyDeviceToHost, cx.stream));
+  if (quotient && maxlen > 1) KZ_CUDA(cudaMemcpyAsync(quotient, d_T + P::N, (maxlen - 1) * 32, cudaMemcpyDefault, cx.stream));   // host or device destination
   if (quot_len) *quot_len = maxlen - 1;
   KZ_CUDA(cudaStreamSynchronize(cx.stream));
   if (do_msm) return kz_msm_dev_internal(handle, 0, d_T + P::N, maxlen - 1, out_xy, is_inf, nullptr);
@@ -307,6 +307,17 @@ int kzgpu_open_dev(uint64_t handle, const uint64_t* const* d_polys, const size_t
   if (curve == KZGPU_BN254)
     return open_impl<FrBN254>(handle, true, nullptr, d_polys, lens, k, z, xi, out_affine_xy, is_inf, nullptr, nullptr, eval_out);
   return open_impl<FrBLS381>(handle, true, nullptr, d_polys, lens, k, z, xi, out_affine_xy, is_inf, nullptr, nullptr, eval_out);
+}
+
+int kzgpu_open_quotient_dev(int field, const uint64_t* const* d_polys, const size_t* lens, size_t k, const uint64_t* z, const uint64_t* xi,
+                            uint64_t* d_quotient, size_t* quot_len, uint64_t* eval_out) {
+  KZ_REQUIRE_INIT();
+  if ((k && (!d_polys || !lens)) || !z || !xi || !d_quotient) return kz_fail(KZGPU_EINVAL, "null pointer");
+  if (field == KZGPU_BN254)
+    return open_impl<FrBN254>(0, false, nullptr, d_polys, lens, k, z, xi, nullptr, nullptr, d_quotient, quot_len, eval_out);
+  if (field == KZGPU_BLS12_381)
+    return open_impl<FrBLS381>(0, false, nullptr, d_polys, lens, k, z, xi, nullptr, nullptr, d_quotient, quot_len, eval_out);
+  return kz_fail(KZGPU_EINVAL, "unknown field id %d", field);
 }
 
 int kzgpu_poly_eval_dev(int field, const uint64_t* d_poly, size_t len, const uint64_t* x, uint64_t* out) {

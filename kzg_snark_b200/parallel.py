@@ -36,6 +36,20 @@ def round_robin(n_items, world, rank):
     return list(range(rank, n_items, world))
 
 
+def lpt_assign(costs, world):
+    """Longest-processing-time-first assignment of independent batch items to ranks: items sorted by
+    cost (descending, ties by index) go to the currently least-loaded rank.  Returns owner[i].
+    Used where the items of a batch differ widely in size (the commits of one Marlin proof range
+    from 2^20 to 12 * 2^20 coefficients); plain round-robin is the special case of equal costs."""
+    owner = [0] * len(costs)
+    load = [0.0] * world
+    for i in sorted(range(len(costs)), key=lambda j: (-costs[j], j)):
+        r = min(range(world), key=lambda q: (load[q], q))
+        owner[i] = r
+        load[r] += costs[i]
+    return owner
+
+
 class _Raw:
     """Adapter: a raw device address as the `.ptr` the device.* helpers expect."""
 

@@ -114,10 +114,13 @@ def test_ntt_rejects_non_power_of_two(dev):
         dev.ntt("bn254", L([1, 2, 3], r), L([5], r)[0])
 
 
-@pytest.mark.parametrize("logn", [16, 18, 20, 22])
+@pytest.mark.parametrize("logn", [16, 18, 20, 22, 24])
 def test_ntt_large_properties(dev, logn):
-    """Full-size checks that need no O(n log n) CPU work: Horner spot checks, round trip, delta."""
-    from kzg_snark_b200.limbs import random_scalars
+    """Full-size checks (up to BASELINE.json's 2^24) that need no O(n log n) CPU work: Horner spot
+    checks (on the host up to 2^18, by the device Horner kernel above), round trip, delta."""
+    import ctypes
+    from kzg_snark_b200 import _ffi
+    from kzg_snark_b200.limbs import random_scalars, int_to_limbs, limbs_to_int
     cv = CURVES["bn254"]; r = cv["r"]
     n = 1 << logn
     w = root_of_unity(cv, n); wl = L([w], r)[0]
@@ -128,6 +131,14 @@ def test_ntt_large_properties(dev, logn):
         ks = [0, 1, 2, n // 2, n - 1, 12345 % n]
         yi = I(y[ks])
         assert yi == off.dft_definition(xi, w, r, ks)
+    else:
+        dx = _ffi.DeviceBuffer(n * 32).upload(x)
+        for k in (0, 1, n // 2, n - 1, 987654321 % n):            # y[k] = x(w^k), fft_ff.py:32-35
+            out = np.zeros(4, dtype=np.uint64)
+            _ffi.check(_ffi.load_library().kzgpu_poly_eval_dev(_ffi.BN254, dx.ptr, n, _ffi.ptr(int_to_limbs(pow(w, k, r), r)),
+                                                               _ffi.ptr(out)))
+            assert limbs_to_int(out) == I(y[k:k + 1])[0]
+        dx.free()
     back = dev.ntt("bn254", y.copy(), wl, inverse=True)
     assert np.array_equal(back, x)
     d = np.zeros((n, 4), dtype=np.uint64); d[1, 0] = 1          # delta_1 -> [w^k]
@@ -381,3 +392,46 @@ def test_msm_batch_large_matches_single(dev):
         o1, f1 = dev.msm(srs, sc[j * n:(j + 1) * n])
         assert f1 == infs[j] and (o1 == out[j]).all()
     d.free(); srs.destroy()
+
+
+def test_point_sharded_open_equals_single_open(dev):
+    """The multi-GPU form of KZG.open: the quotient is formed on the device
+    (kzgpu_open_quotient_dev), index ranges of it go through kzgpu_msm_partial_dev, and the XYZZ
+    partials are folded -- here the 3 'ranks' run one after another on one GPU.  Must equal
+    kzgpu_open and the oracle."""
+    import ctypes
+    from kzg_snark_b200 import _ffi
+    from kzg_snark_b200.parallel import shard_range
+    cv = get_curve("bn254"); ko = KZGOracle("bn254")
+    rng = random.Random(8)
+    tau = rng.randrange(1, cv.r)
+    lens = [3000, 2999, 1, 1500]
+    polys = [[rng.randrange(cv.r) for _ in range(m)] for m in lens]
+    z, xi = rng.randrange(cv.r), rng.randrange(cv.r)
+    srs = dev.Srs.generate("bn254", tau, 3000)
+    ref, inf = dev.open_proof(srs, [L(p, cv.r) for p in polys], L([z], cv.r)[0], L([xi], cv.r)[0])
+    bufs = [_ffi.DeviceBuffer(max(m, 1) * 32).upload(L(p, cv.r)) for p, m in zip(polys, lens)]
+    dq = _ffi.DeviceBuffer(3000 * 32)
+    ptrs = (ctypes.c_void_p * 4)(*[b.ptr.value for b in bufs])
+    ls = (ctypes.c_size_t * 4)(*lens)
+    ql = ctypes.c_size_t(0)
+    ev = np.zeros(4, dtype=np.uint64)
+    lib = _ffi.load_library()
+    _ffi.check(lib.kzgpu_open_quotient_dev(_ffi.BN254, ptrs, ls, 4, _ffi.ptr(L([z], cv.r)[0]), _ffi.ptr(L([xi], cv.r)[0]),
+                                           dq.ptr, ctypes.byref(ql), _ffi.ptr(ev)))
+    assert ql.value == 2999 and I(ev)[0] == poly_eval(ko.combine(polys, xi), z, cv.r)
+    world = 3
+    parts = _ffi.DeviceBuffer(128 * world)
+
+    class At:
+        def __init__(self, base, off):
+            self.ptr = ctypes.c_void_p(base.ptr.value + off)
+
+    for rank in range(world):
+        s0, cnt = shard_range(ql.value, world, rank)
+        dev.msm_partial_dev(srs, At(dq, 32 * s0), cnt, At(parts, 128 * rank), first=s0)
+    out, finf = dev.g1_fold("bn254", parts, world)
+    assert not inf and not finf and (out == ref).all()
+    wit = ko.witness(polys, z, xi)
+    assert point_of(cv, out, finf, 4) == cv.normalize(cv.multiply(cv.G1, poly_eval(wit, tau, cv.r)))
+    srs.destroy()

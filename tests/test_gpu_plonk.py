@@ -65,7 +65,7 @@ def test_prover_matches_the_reference_prover_bit_for_bit():
         assert aff(proof["kzg_proofs"][k]) == (H(v[0]), H(v[1])), k
 
 
-@pytest.mark.parametrize("logn,n_pub", [(3, 2), (6, 5), (10, 7), (14, 16)])
+@pytest.mark.parametrize("logn,n_pub", [(3, 2), (6, 5), (10, 7), (14, 16), (20, 16)])
 def test_synthetic_circuit_proof_is_accepted_and_tamper_rejected(logn, n_pub):
     import plonk_verifier
     from kzg_snark_b200.plonk import Indexer, Prover

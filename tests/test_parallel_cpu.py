@@ -77,6 +77,16 @@ def test_shard_range_partitions_exactly():
     assert sorted(sum((round_robin(11, 4, r) for r in range(4)), [])) == list(range(11))
 
 
+def test_lpt_assignment_balances_unequal_items():
+    from kzg_snark_b200.parallel import lpt_assign
+    costs = [1, 1, 1, 1, 1, 2, 1, 1, 1, 2, 12]
+    owner = lpt_assign(costs, 4)
+    load = [sum(c for c, o in zip(costs, owner) if o == r) for r in range(4)]
+    assert sorted(set(owner)) == [0, 1, 2, 3] and max(load) == 12 and sum(load) == sum(costs)
+    assert lpt_assign([3, 3, 3, 3], 4) == [0, 1, 2, 3] and lpt_assign([5], 8) == [0] and lpt_assign([], 2) == []
+    assert lpt_assign(costs, 1) == [0] * len(costs)
+
+
 @pytest.mark.parametrize("n_total", [9, 32])
 def test_point_sharded_commit_over_gloo(n_total):
     world = 2
