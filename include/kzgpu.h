@@ -112,6 +112,12 @@ int kzgpu_msm_partial_dev(uint64_t handle, size_t first, const uint64_t* d_scala
 int kzgpu_g1_fold(int curve, const uint64_t* d_xyzz, size_t count,
                   uint64_t* out_affine_xy, int* is_inf);
 
+/* Verifier-side combinations: sum_i scalars[i] * P_i over `count` ARBITRARY affine points given on
+ * the host (commitments, proofs, G1) -- the loops of KZG.check / batch_check, kzg.py:183-205 and :252-281, and of the
+ * PLONK / Marlin verifiers (plonk/verifier.py:117-157).  Small counts only (<= 65536); the pairing stays with the caller. */
+int kzgpu_g1_lincomb(int curve, const uint64_t* affine_xy, const uint64_t* scalars, size_t count,
+                     uint64_t* out_affine_xy, int* is_inf);
+
 /* ---- NTT: fft_ff / ifft_ff (fft_ff.py:3-58) and the coset variant ---------------------- */
 /* In place, natural order in and out:  out[k] = sum_j data[j] * (shift^j) * w^(j k)
  * inverse != 0: uses w^-1 and scales by n^-1 (fft_ff.py:53-58); with a shift, output j is

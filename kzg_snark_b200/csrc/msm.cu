@@ -643,6 +643,43 @@ __global__ void __launch_bounds__(128) g1_fold_kernel(const uint32_t* __restrict
   }
 }
 
+// Variable-base linear combination sum_i s_i * P_i of a handful of arbitrary points (the verifier-side combinations
+// of kzg.py:183-205, 252-281): thread i runs an MSB-first double-and-add over its scalar, then the block folds the
+// XYZZ partials exactly like g1_fold_kernel.  points: canonical affine ((0,0) = identity); scalars: canonical limbs.
+template <class Cfg>
+__global__ void __launch_bounds__(128) g1_lincomb_kernel(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ scalars,
+                                                        uint32_t count, uint32_t* __restrict__ out) {
+  using P = typename Cfg::Fp;
+  extern __shared__ uint32_t shw[];
+  XYZZ<P> acc = xyzz_inf<P>();
+  for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) {
+    Affine<P> a;
+    for (int k = 0; k < P::N; k++) { a.x.v[k] = pts[(size_t)i * 2 * P::N + k]; a.y.v[k] = pts[(size_t)i * 2 * P::N + P::N + k]; }
+    if (aff_is_inf<P>(a)) continue;
+    a.x = fe_to_mont<P>(a.x); a.y = fe_to_mont<P>(a.y);
+    XYZZ<P> r = xyzz_inf<P>();
+    bool started = false;
+    for (int w = 7; w >= 0; w--) {
+      uint32_t word = scalars[(size_t)i * 8 + w];
+      for (int b = 31; b >= 0; b--) {
+        if (started) r = xyzz_dbl<P>(r);
+        if ((word >> b) & 1) { xyzz_madd<P>(r, a); started = true; }
+      }
+    }
+    acc = xyzz_add<P>(acc, r);
+  }
+  st_xyzz<P>(shw, threadIdx.x, acc);
+  __syncthreads();
+  for (uint32_t off = blockDim.x / 2; off > 0; off >>= 1) {
+    if (threadIdx.x < off) {
+      XYZZ<P> a = ld_xyzz<P>(shw, threadIdx.x), b = ld_xyzz<P>(shw, threadIdx.x + off);
+      st_xyzz<P>(shw, threadIdx.x, xyzz_add<P>(a, b));
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) st_xyzz<P>(out, 0, ld_xyzz<P>(shw, 0));
+}
+
 // canonical affine -> Montgomery affine (in place); (0,0) stays (0,0)
 template <class Cfg> __global__ void srs_to_mont_kernel(uint32_t* pts, size_t n) {
   using P = typename Cfg::Fp;
@@ -1374,6 +1411,36 @@ int kzgpu_g1_fold(int curve, const uint64_t* d_xyzz, size_t count, uint64_t* out
   KZ_CUDA(cudaStreamSynchronize(cx.stream));
   memcpy(out_affine_xy, h, 2 * N * 4);
   if (is_inf) *is_inf = (int)h[2 * N];
+  return 0;
+}
+
+int kzgpu_g1_lincomb(int curve, const uint64_t* affine_xy, const uint64_t* scalars, size_t count, uint64_t* out_affine_xy, int* is_inf) {
+  KZ_REQUIRE_INIT();
+  if (!out_affine_xy || (count && (!affine_xy || !scalars))) return kz_fail(KZGPU_EINVAL, "null pointer");
+  if (curve != KZGPU_BN254 && curve != KZGPU_BLS12_381) return kz_fail(KZGPU_EINVAL, "Unsupported curve type: %d", curve);
+  if (count > 65536) return kz_fail(KZGPU_EINVAL, "kzgpu_g1_lincomb is for verifier-sized combinations (<= 65536 terms); use an SRS handle and kzgpu_msm");
+  KzgpuCtx& cx = kz_ctx();
+  int rc = set_smem_attrs();
+  if (rc) return rc;
+  const int N = curve == KZGPU_BN254 ? 8 : 12;
+  const size_t pb = count * 2 * N * 4, sb = count * 32;
+  if ((rc = g_ws.scal.ensure(pb + sb + 64)) || (rc = g_ws.result.ensure(4 * N * 4 + 4))) return rc;
+  uint32_t* d_pts = (uint32_t*)g_ws.scal.p;
+  uint32_t* d_sc = d_pts + count * 2 * N;
+  if (count) {
+    KZ_CUDA(cudaMemcpyAsync(d_pts, affine_xy, pb, cudaMemcpyHostToDevice, cx.stream));
+    KZ_CUDA(cudaMemcpyAsync(d_sc, scalars, sb, cudaMemcpyHostToDevice, cx.stream));
+  }
+  if (curve == KZGPU_BN254)
+    g1_lincomb_kernel<BN254Cfg><<<1, 128, 128 * 4 * N * 4, cx.stream>>>(d_pts, d_sc, (uint32_t)count, (uint32_t*)g_ws.result.p);
+  else
+    g1_lincomb_kernel<BLS381Cfg><<<1, 128, 128 * 4 * N * 4, cx.stream>>>(d_pts, d_sc, (uint32_t)count, (uint32_t*)g_ws.result.p);
+  KZ_LAUNCHED();
+  uint32_t h[4 * 12];
+  KZ_CUDA(cudaMemcpyAsync(h, g_ws.result.p, 4 * N * 4, cudaMemcpyDeviceToHost, cx.stream));
+  KZ_CUDA(cudaStreamSynchronize(cx.stream));
+  if (curve == KZGPU_BN254) host_xyzz_to_canonical<FpBN254>(h, (uint32_t*)out_affine_xy, is_inf);
+  else host_xyzz_to_canonical<FpBLS381>(h, (uint32_t*)out_affine_xy, is_inf);
   return 0;
 }
 

@@ -180,6 +180,19 @@ def g1_fold(curve, dbuf, count):
     return out, bool(inf.value)
 
 
+def g1_lincomb(curve, affine_xy, scalars):
+    """sum_i scalars[i] * P_i over a few arbitrary points (verifier-side combinations, kzg.py:183-205):
+    affine_xy (k, 2*L) canonical limbs ((0,0) rows = identity), scalars (k, 4) -> (affine limbs, is_inf)."""
+    cid = curve_id(curve)
+    a = np.ascontiguousarray(affine_xy, dtype=np.uint64).reshape(-1, 2 * FP_LIMBS[cid])
+    s = _scalars(scalars)
+    assert a.shape[0] == s.shape[0]
+    out = _point_out(cid)
+    inf = ctypes.c_int(0)
+    check(_ffi.init().kzgpu_g1_lincomb(cid, ptr(a), ptr(s), a.shape[0], ptr(out), ctypes.byref(inf)))
+    return out, bool(inf.value)
+
+
 # ---------------------------------------------------------------------------- open
 def open_proof(srs, poly_arrays, z_limbs, xi_limbs, want_eval=False):
     lib = _ffi.init()

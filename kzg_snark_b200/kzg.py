@@ -3,9 +3,10 @@ methods and attributes (kzg.py:18-288), whose prover-side hot path -- `commit` (
 `open` (xi-combination, synthetic division, MSM) -- runs on the sm_100a kernels behind
 libkzgpu.so.  `setup` builds the G1 powers on the device as well.
 
-What is NOT accelerated, by design: `check` and
-`batch_check` are verifier-side, O(#polynomials) group operations plus two pairings; as in the
-reference they run on py_ecc, and raise ImportError when py_ecc is not installed.
+Verifier side: the G1 linear combinations inside `check` / `batch_check`
+(kzg.py:183-205, 252-281) and the `multiply` / `add` / `neg` / `eq` attributes the verifiers read run
+on the device too (`kzgpu_g1_lincomb`); the two pairings and G2 stay on py_ecc as in the reference, so
+`check` / `batch_check` raise ImportError at the pairing when py_ecc is not installed.
 
 The GPU context is a process-wide singleton (six KZG instances exist in one PLONK run,
 SURVEY.md section 8b); device copies of commitment keys are cached per `ck` list.
@@ -40,7 +41,8 @@ class CommitmentKey(list):
 def _needs_py_ecc(name):
     def stub(*a, **k):
         raise ImportError(f"py_ecc is required for the verifier-side operation `{name}` "
-                          "(KZG.check / batch_check are not part of the accelerated path)")
+                          "(the pairing and G2 arithmetic of KZG.check / batch_check stay on py_ecc)")
+    stub.missing = True
     return stub
 
 
@@ -71,8 +73,9 @@ class KZG:
             G1 = (self._codec.fq(gx), self._codec.fq(gy), self._codec.fq(1))
             Z1 = self._codec.Z1
             G2 = Z2 = None
-            multiply, add, neg, pairing, eq = (_needs_py_ecc(n) for n in
-                                               ("multiply", "add", "neg", "pairing", "eq"))
+            # G1 group operations without py_ecc: device-backed (kzgpu_g1_lincomb); G2 and the pairing stay py_ecc's
+            multiply, add, neg, eq = self._g1_multiply, self._g1_add, self._g1_neg, self._g1_eq
+            pairing = _needs_py_ecc("pairing")
         self.G1, self.G2, self.Z1, self.Z2 = G1, G2, Z1, Z2                    # kzg.py:40-49
         self.multiply, self.add, self.neg = multiply, add, neg
         self.pairing, self.eq = pairing, eq
@@ -80,6 +83,32 @@ class KZG:
         self.Fq = GF(curve_order)                                              # kzg.py:52-54
         self.R = PolynomialRing(self.Fq, "X")
         self.X = self.R.gen()
+
+    # ------------------------------------------------------------------ G1 on the device
+    def g1_lincomb(self, points, scalars):
+        """sum_i scalars[i] * points[i] for a few arbitrary G1 points (py_ecc-shaped triples): the
+        verifier-side combinations of kzg.py:183-205 and :252-281 as one kernel launch."""
+        q = self.curve_order
+        if not points:
+            return self.Z1
+        out, inf = device.g1_lincomb(self._cid, self._codec.points_to_limbs(points), ints_to_limbs([int(s) % q for s in scalars], q))
+        return self._codec.from_device(out, inf)
+
+    def _g1_multiply(self, pt, n):
+        return self.g1_lincomb([pt], [n])
+
+    def _g1_add(self, p1, p2):
+        return self.g1_lincomb([p1, p2], [1, 1])
+
+    def _g1_neg(self, pt):
+        x, y, z = pt
+        return (x, self._codec.fq(-int(y)), z)
+
+    def _g1_eq(self, p1, p2):
+        p = self._codec.p
+        x1, y1, z1 = (int(c) for c in p1)
+        x2, y2, z2 = (int(c) for c in p2)
+        return (x1 * z2 - x2 * z1) % p == 0 and (y1 * z2 - y2 * z1) % p == 0
 
     # ------------------------------------------------------------------ helpers
     def _coeff_limbs(self, poly):
@@ -166,38 +195,41 @@ class KZG:
     def check(self, rk, commitments, z, evaluations, proof, xi):
         """e(C - v*G1, G2) == e(proof, tau*G2 - z*G2) with C, v the xi-combinations
         (kzg.py:161-211).  Runs on py_ecc like the reference."""
+        if getattr(self.pairing, "missing", False):
+            self.pairing()                              # ImportError before any device work
         z = self.Fq(z)
         xi = self.Fq(xi)
-        C = self.Z1
         v = self.Fq(0)
-        for i, comm in enumerate(commitments):
-            C = self.add(C, self.multiply(comm, int(xi ** (i + 1))))
         for i, e in enumerate(evaluations):
             v += xi ** (i + 1) * self.Fq(e)
-        lhs_pt = self.add(C, self.neg(self.multiply(self.G1, int(v))))
+        # C - v*G1 = sum_i xi^(i+1) C_i - v G1: one device combination (kzg.py:183-201)
+        lhs_pt = self.g1_lincomb(list(commitments) + [self.G1], [int(xi ** (i + 1)) for i in range(len(commitments))] + [-int(v)])
         rhs_g2 = self.add(rk, self.neg(self.multiply(self.G2, int(z))))
         return self.pairing(self.G2, lhs_pt) == self.pairing(rhs_g2, proof)
 
     def batch_check(self, rk, commitments_list, z_list, evaluations_list, proof_list, xi_list, r=None):
         """One pairing equation for several openings (kzg.py:213-288):
         e(sum r^i (C_i - v_i G1 + z_i pi_i), G2) == e(sum r^i pi_i, tau G2)."""
+        if getattr(self.pairing, "missing", False):
+            self.pairing()
         if r is None:
             r = self.Fq.random_element()
-        left = self.Z1
-        right = self.Z1
+        r = self.Fq(r)
+        # left = sum_i r^(i+1) (sum_j xi_i^(j+1) C_ij - v_i G1 + z_i pi_i), right = sum_i r^(i+1) pi_i  (kzg.py:252-281):
+        # every term is scalar * point, so each side is one device combination
+        lp, ls, rp_, rs = [], [], [], []
         for i, (commitments, z, evaluations, proof, xi) in enumerate(
                 zip(commitments_list, z_list, evaluations_list, proof_list, xi_list)):
             z = self.Fq(z)
             xi = self.Fq(xi)
-            C = self.Z1
+            rp = r ** (i + 1)
             v = self.Fq(0)
             for j, comm in enumerate(commitments):
                 xp = xi ** (j + 1)
-                C = self.add(C, self.multiply(comm, int(xp)))
+                lp.append(comm); ls.append(int(rp * xp))
                 v += xp * self.Fq(evaluations[j])
-            term = self.add(C, self.neg(self.multiply(self.G1, int(v))))
-            term = self.add(term, self.multiply(proof, int(z)))
-            rp = int(r ** (i + 1))
-            left = self.add(left, self.multiply(term, rp))
-            right = self.add(right, self.multiply(proof, rp))
+            lp += [self.G1, proof]; ls += [-int(rp * v), int(rp * z)]
+            rp_.append(proof); rs.append(int(rp))
+        left = self.g1_lincomb(lp, ls)
+        right = self.g1_lincomb(rp_, rs)
         return self.pairing(self.G2, left) == self.pairing(rk, right)

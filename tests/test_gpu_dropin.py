@@ -5,6 +5,7 @@ import json
 import os
 import random
 
+import numpy as np
 import pytest
 
 from oracle.curve import get_curve
@@ -193,3 +194,74 @@ def test_dropin_reproduces_reference_trace(name):
         interp=lambda v, w: fft_ff_interpolation([F(x) for x in v], F(w), F),
         to_affine=lambda pt: aff(cv, pt), to_ints=poly_ints)
     assert n == len(trace["calls"]) > 0
+
+
+@pytest.mark.parametrize("curve", CURVE_NAMES)
+def test_g1_lincomb_matches_oracle(curve):
+    """kzgpu_g1_lincomb: sum_i s_i * P_i over arbitrary points, incl. the identity,
+    repeated points, P + (-P), scalars 0 / 1 / r-1, and the empty sum."""
+    from kzg_snark_b200 import device
+    from kzg_snark_b200.limbs import ints_to_limbs, limbs_to_ints
+    cv = get_curve(curve)
+    nl = CURVES[curve]["fp_limbs32"] // 2
+    rng = random.Random(12)
+    base = [cv.multiply(cv.G1, rng.randrange(1, cv.r)) for _ in range(9)]
+    cases = [([], []), ([base[0]], [0]), ([base[0]], [1]), ([base[1]], [cv.r - 1]), ([cv.Z1, base[2]], [5, 7]),
+             ([base[3], base[3]], [3, 4]), ([base[4], cv.neg(base[4])], [11, 11]),
+             (base, [rng.randrange(cv.r) for _ in base]),
+             ([base[i % 9] for i in range(150)], [rng.randrange(cv.r) for _ in range(150)])]
+    for pts, sc in cases:
+        flat = []
+        for p in pts:
+            a = cv.normalize(p)
+            flat += [0, 0] if a is None else [a[0], a[1]]
+        arr = ints_to_limbs(flat, cv.p, nl).reshape(len(pts), 2 * nl) if pts else np.zeros((0, 2 * nl), np.uint64)
+        out, inf = device.g1_lincomb(curve, arr, ints_to_limbs(sc, cv.r) if sc else np.zeros((0, 4), np.uint64))
+        acc = cv.Z1
+        for p, k in zip(pts, sc):
+            acc = cv.add(acc, cv.multiply(p, k))
+        exp = cv.normalize(acc)
+        assert (None if inf else tuple(limbs_to_ints(out.reshape(2, nl)))) == exp
+
+
+def test_check_and_batch_check_with_device_combinations():
+    """KZG.check / batch_check (kzg.py:161-288) with their G1 combinations on the device; the pairing
+    and G2 arithmetic -- py_ecc's in the reference, absent here -- are supplied by the oracle's
+    stand-in, exactly the role py_ecc plays for the drop-in.  Accepts honest openings, rejects
+    tampered ones, like the reference's self-test (kzg.py:337-380)."""
+    from kzg_snark_b200.kzg import KZG
+    from oracle import pyecc_standin as E
+    kzg = KZG("bn254")
+    if kzg.have_py_ecc:
+        pytest.skip("py_ecc present: the drop-in already uses it")
+    g1 = lambda P: tuple(E.FQ(int(c)) for c in P)                              # noqa: E731
+    is_g2 = lambda P: isinstance(P[0], E.FQ2)                                  # noqa: E731
+    kzg.G2 = E.G2
+    kzg.pairing = lambda Q, P: E.pairing(Q, g1(P))
+    dev_mul, dev_add, dev_neg = kzg.multiply, kzg.add, kzg.neg
+    kzg.multiply = lambda P, n: E.multiply(P, n) if is_g2(P) else dev_mul(P, n)
+    kzg.add = lambda P, Q: E.add(P, Q) if is_g2(P) else dev_add(P, Q)
+    kzg.neg = lambda P: E.neg(P) if is_g2(P) else dev_neg(P)
+    rng = random.Random(21)
+    r = kzg.curve_order
+    tau = rng.randrange(1, r)
+    ck, _ = kzg.setup(40, tau=tau)
+    rk = E.multiply(E.G2, tau)
+    polys = [kzg.R([rng.randrange(r) for _ in range(m)]) for m in (41, 17, 1)]
+    comm = kzg.commit(ck, polys)
+    z, xi = rng.randrange(r), rng.randrange(r)
+    proof = kzg.open(ck, polys, z, xi)
+    evals = [p(z) for p in polys]
+    assert kzg.check(rk, comm, z, evals, proof, xi)
+    assert not kzg.check(rk, comm, z, [evals[0] + 1] + evals[1:], proof, xi)
+    z2, xi2 = rng.randrange(r), rng.randrange(r)
+    proof2 = kzg.open(ck, polys[:2], z2, xi2)
+    ok = kzg.batch_check(rk, [comm, comm[:2]], [z, z2], [evals, [p(z2) for p in polys[:2]]], [proof, proof2], [xi, xi2], r=rng.randrange(r))
+    assert ok
+    bad = kzg.batch_check(rk, [comm, comm[:2]], [z, z2], [evals, [polys[0](z2) + 1, polys[1](z2)]], [proof, proof2], [xi, xi2], r=rng.randrange(r))
+    assert not bad
+    # the group-operation attributes the verifiers read (plonk/verifier.py:117-157) agree with the oracle
+    cv = get_curve("bn254")
+    P = kzg.multiply(kzg.G1, 12345)
+    assert aff(cv, P) == cv.normalize(cv.multiply(cv.G1, 12345))
+    assert aff(cv, kzg.add(P, kzg.neg(P))) is None and kzg.eq(kzg.add(P, P), kzg.multiply(P, 2))
