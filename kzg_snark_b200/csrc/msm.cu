@@ -865,7 +865,7 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   // warp runs alone), so small bucket sets get short chunks -- enough threads to fill the SMs matters more than
   // the ~20-addition fix-up (lo * running) every chunk pays
   uint32_t CH = 64;
-  while (CH > 8 && (nb / CH) < 65536) CH >>= 1;
+  while (CH > 8 && (nb / CH) < 32768) CH >>= 1;        // 2^21 buckets keep CH = 64 (work-bound there), 2^19 get 16
   if (CH > B) CH = B;
   const uint32_t cpw = (B + CH - 1) / CH;
   if ((rc = g_ws.partials.ensure((size_t)cpw * Wb * 4 * P::N * 4))) return rc;

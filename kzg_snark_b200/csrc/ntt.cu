@@ -40,6 +40,7 @@ struct NttPassArgs {
   uint32_t b, logC, logK, logQ;
   uint32_t nd;
   uint32_t dpack;         // layer widths, 2 bits each (kept out of an array: no local-memory indexing)
+  uint32_t blk0;          // first column tile of this launch (column-slab launches of the host-buffer entry point)
 };
 
 __device__ __forceinline__ uint32_t layer_width(uint32_t dpack, uint32_t s) { return (dpack >> (2 * s)) & 3u; }
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, 4) ntt_pass_kernel(NttPassArgs a, Nt
   }
   const uint32_t Cmask = (1u << a.logC) - 1, Kmask = (1u << a.logK) - 1, Rmask = (1u << a.b) - 1;
   const size_t boff = (size_t)blockIdx.y * a.n;
-  const size_t q0 = (size_t)blockIdx.x << a.logC;
+  const size_t q0 = ((size_t)blockIdx.x + a.blk0) << a.logC;
 
   // load phase, four elements (and their boundary twiddles) in flight per thread
   for (uint32_t o0 = threadIdx.x; o0 < tile; o0 += 4 * blockDim.x) {
@@ -376,8 +377,15 @@ int build_plan(NttPlan& pl, uint32_t logn, const Fe<P>& w_canon, int inverse, co
   return 0;
 }
 
+// Host-buffer entry point (kzgpu_ntt): the first executed pass reads its input as a [R][Q] matrix by column tiles and the
+// last one writes a [R][Q] matrix by column tiles, so both can run slab by slab (kSlabs column ranges): slab s of the input
+// is uploaded with one 2-D copy and transformed while slab s+1 is in flight, and slab s of the result goes back to the host
+// while slab s+1 is computed.  Only one slab of each transfer and the middle passes are not hidden behind PCIe.
+struct NttHostIo { const uint64_t* h_in; uint64_t* h_out; };
+constexpr uint32_t kSlabs = 4;
+
 template <class P>
-int run_plan(const NttPlan& pl, uint32_t* d_data, size_t batch) {
+int run_plan(const NttPlan& pl, uint32_t* d_data, size_t batch, const NttHostIo* io = nullptr) {
   KzgpuCtx& cx = kz_ctx();
   const uint64_t n = 1ull << pl.logn;
   const size_t bytes = n * batch * 32;
@@ -406,21 +414,59 @@ int run_plan(const NttPlan& pl, uint32_t* d_data, size_t batch) {
     a.n = n; a.b = pp.b; a.logC = pp.logC; a.logK = pp.logK; a.logQ = pp.logQ; a.nd = pp.nd;
     a.dpack = 0;
     for (uint32_t k = 0; k < pp.nd; k++) a.dpack |= pp.d[k] << (2 * k);
+    a.blk0 = 0;
     uint32_t tile = 1u << (pp.b + pp.logC);
     uint32_t threads = tile / 8 < 32 ? 32 : (tile / 8 > (uint32_t)kThreads ? kThreads : tile / 8);
-    dim3 grid((unsigned)(1ull << (pp.logQ - pp.logC)), (unsigned)batch);
+    const uint32_t tiles = (uint32_t)(1ull << (pp.logQ - pp.logC));
+    const size_t smem = (size_t)tile * 32 + (pp.nd > 1 ? (32u << pp.b) : 0u);
+    const bool slab_in = io && m >= 2 && i == 0, slab_out = io && m >= 2 && i == m - 1 && pp.logK == pp.logQ;
+    if (slab_in || slab_out) {
+      // [R][Q] matrix, slab = tiles/kSlabs column tiles = (Q / kSlabs) columns of every row
+      static cudaEvent_t done_ev[kSlabs] = {nullptr};
+      if (!done_ev[0]) for (uint32_t k = 0; k < kSlabs; k++) KZ_CUDA(cudaEventCreateWithFlags(&done_ev[k], cudaEventDisableTiming));
+      const size_t R = 1ull << pp.b, Q = 1ull << pp.logQ, pitch = Q * 32, width = pitch / kSlabs;
+      if (slab_in)
+        for (uint32_t k = 0; k < kSlabs; k++) {
+          KZ_CUDA(cudaMemcpy2DAsync((char*)src + k * width, pitch, (const char*)io->h_in + k * width, pitch, width, R,
+                                    cudaMemcpyHostToDevice, cx.copy_stream));
+          KZ_CUDA(cudaEventRecord(cx.copy_ev[k], cx.copy_stream));
+        }
+      for (uint32_t k = 0; k < kSlabs; k++) {
+        if (slab_in) KZ_CUDA(cudaStreamWaitEvent(cx.stream, cx.copy_ev[k], 0));
+        a.blk0 = k * (tiles / kSlabs);
+        KzProf prof(1);
+        ntt_pass_kernel<P><<<dim3(tiles / kSlabs, 1), threads, smem, cx.stream>>>(a, c);
+        KZ_LAUNCHED();
+        prof.stop(k == 0 ? 1 : 0, k == 0 ? (double)n : 0.0);
+        if (slab_out) {
+          KZ_CUDA(cudaEventRecord(done_ev[k], cx.stream));
+          KZ_CUDA(cudaStreamWaitEvent(cx.copy_stream, done_ev[k], 0));
+          KZ_CUDA(cudaMemcpy2DAsync((char*)io->h_out + k * width, pitch, (const char*)dst + k * width, pitch, width, R,
+                                    cudaMemcpyDeviceToHost, cx.copy_stream));
+        }
+      }
+      if (slab_out) KZ_CUDA(cudaStreamSynchronize(cx.copy_stream));
+      src = dst;
+      continue;
+    }
+    dim3 grid((unsigned)tiles, (unsigned)batch);
     KzProf prof(1);
-    ntt_pass_kernel<P><<<grid, threads, (size_t)tile * 32 + (pp.nd > 1 ? (32u << pp.b) : 0u), cx.stream>>>(a, c);
+    ntt_pass_kernel<P><<<grid, threads, smem, cx.stream>>>(a, c);
     KZ_LAUNCHED();
     prof.stop(1, (double)n * (double)batch);
     src = dst;
   }
   if (m == 1) KZ_CUDA(cudaMemcpyAsync(d_data, src, bytes, cudaMemcpyDeviceToDevice, cx.stream));
+  if (io && !(m >= 2 && pl.passes[m - 1].logK == pl.passes[m - 1].logQ)) {      // no slab-wise download possible: plain copy
+    KZ_CUDA(cudaMemcpyAsync(io->h_out, d_data, bytes, cudaMemcpyDeviceToHost, cx.stream));
+    KZ_CUDA(cudaStreamSynchronize(cx.stream));
+  }
   return 0;
 }
 
 template <class P>
-int ntt_impl(int field, uint32_t* d_data, size_t n, size_t batch, const uint64_t* w, int inverse, const uint64_t* shift) {
+int ntt_impl(int field, uint32_t* d_data, size_t n, size_t batch, const uint64_t* w, int inverse, const uint64_t* shift,
+             const NttHostIo* io = nullptr) {
   if (n == 0 || (n & (n - 1))) return kz_fail(KZGPU_EINVAL, "NTT length %zu is not a power of two (fft_ff.py:74)", n);
   if (batch == 0) return 0;
   uint32_t logn = 0;
@@ -442,7 +488,7 @@ int ntt_impl(int field, uint32_t* d_data, size_t n, size_t batch, const uint64_t
     if (it->field == field && it->logn == logn && it->inverse == (inverse ? 1 : 0) && it->has_shift == (shift != nullptr) &&
         !memcmp(it->w, wc.v, 32) && (!shift || !memcmp(it->shift, sc.v, 32))) {
       g_plans.splice(g_plans.begin(), g_plans, it);
-      return run_plan<P>(g_plans.front(), d_data, batch);
+      return run_plan<P>(g_plans.front(), d_data, batch, io);
     }
   }
   NttPlan pl;
@@ -453,12 +499,13 @@ int ntt_impl(int field, uint32_t* d_data, size_t n, size_t batch, const uint64_t
   if (rc) { pl.free_tables(); return rc; }
   g_plans.push_front(pl);
   while (g_plans.size() > kMaxPlans) { g_plans.back().free_tables(); g_plans.pop_back(); }
-  return run_plan<P>(g_plans.front(), d_data, batch);
+  return run_plan<P>(g_plans.front(), d_data, batch, io);
 }
 
-int ntt_dispatch(int field, uint32_t* d_data, size_t n, size_t batch, const uint64_t* w, int inverse, const uint64_t* shift) {
-  if (field == KZGPU_BN254) return ntt_impl<FrBN254>(field, d_data, n, batch, w, inverse, shift);
-  if (field == KZGPU_BLS12_381) return ntt_impl<FrBLS381>(field, d_data, n, batch, w, inverse, shift);
+int ntt_dispatch(int field, uint32_t* d_data, size_t n, size_t batch, const uint64_t* w, int inverse, const uint64_t* shift,
+                 const NttHostIo* io = nullptr) {
+  if (field == KZGPU_BN254) return ntt_impl<FrBN254>(field, d_data, n, batch, w, inverse, shift, io);
+  if (field == KZGPU_BLS12_381) return ntt_impl<FrBLS381>(field, d_data, n, batch, w, inverse, shift, io);
   return kz_fail(KZGPU_EINVAL, "unknown field id %d", field);
 }
 
@@ -495,6 +542,11 @@ int kzgpu_ntt_batch(int field, uint64_t* data, size_t n, size_t batch, const uin
   if (bytes == 0) return 0;
   int rc = g_ntt_io.ensure(bytes);
   if (rc) return rc;
+  if (batch == 1 && n >= (1u << 20) && !getenv("KZGPU_NTT_NO_OVERLAP")) {
+    // one long vector: transfers pipelined with the first and last pass (>= 2 passes at this size, >= kSlabs tiles each)
+    NttHostIo io{data, data};
+    return ntt_dispatch(field, (uint32_t*)g_ntt_io.p, n, 1, w, inverse, coset_shift, &io);
+  }
   KZ_CUDA(cudaMemcpyAsync(g_ntt_io.p, data, bytes, cudaMemcpyHostToDevice, cx.stream));
   rc = ntt_dispatch(field, (uint32_t*)g_ntt_io.p, n, batch, w, inverse, coset_shift);
   if (rc) return rc;
