@@ -123,3 +123,35 @@ def test_test_verifier_accepts_the_reference_provers_proof():
     # the trapdoor form of the same equation (used for BLS12-381, which has no pairing stand-in) agrees
     assert plonk_verifier.verify_trapdoor(ivk, x, proof, "bn254")
     assert not plonk_verifier.verify_trapdoor(ivk, x, bad, "bn254")
+
+
+def test_product_transcript_agrees_with_reference_transcript():
+    """kzg_snark_b200.plonk.Transcript (restated from transcript.py:18-100) against the test verifier's
+    independent restatement on the reference proof's messages, and -- when the reference tree is
+    mounted -- against transcript.py itself."""
+    import plonk_verifier
+    from kzg_snark_b200.plonk import Transcript
+    from kzg_snark_b200.sageshim import GF
+    d, ivk, proof = _normalized_fixture()
+    F = GF(R)
+    msgs = [("public-inputs", [F(H(v)) for v in d["x"]]),
+            ("round1-commitments", [tuple(list(proof["commitments"][k]) + [1]) for k in "abc"]),
+            ("round2-commitment", tuple(list(proof["commitments"]["z"]) + [1])),
+            ("round4-evaluations", [F(v) for v in proof["evaluations"].values()]),
+            ("int-and-str", [7, "label", b"bytes"])]
+    ours, theirs = Transcript("plonk-proof", F), plonk_verifier._Transcript("plonk-proof")
+    ref = None
+    if os.path.isfile("/root/reference/transcript.py"):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_transcript", "/root/reference/transcript.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        ref = mod.Transcript("plonk-proof", F)
+    for label, data in msgs:
+        ours.append_message(label, data)
+        theirs.append(label, data)
+        c1, c2 = int(ours.get_challenge(label + "-c")), theirs.challenge(label + "-c")
+        assert c1 == c2
+        if ref is not None:
+            ref.append_message(label, data)
+            assert int(ref.get_challenge(label + "-c")) == c1
