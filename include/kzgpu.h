@@ -186,9 +186,11 @@ int kzgpu_plonk_permutation_dev(int field, size_t n, const uint64_t* d_a, const 
  * d_evals = 15 device vectors of n4 = 4n evaluations in the order a, b, c, z, qM, qL, qR, qO, qC,
  * S_sigma1, S_sigma2, S_sigma3, PI, L1, X (the coset points themselves); params = 9 elements
  * alpha, beta, gamma, k1, k2, 1/v_H(x_0..3) (v_H has period 4 on the coset).  d_t receives
- * t(x_i); one inverse coset NTT of it gives t's coefficients. */
+ * t(x_i), canonical; one inverse coset NTT of it gives t's coefficients.  mont_in != 0: the 15 vectors hold
+ * Montgomery-form values v * 2^256 mod r (scale the coefficient vectors by 2^256 mod r before their coset NTTs, e.g.
+ * with kzgpu_poly_lincomb_dev -- the transform is linear), which saves the 16 per-point conversions. */
 int kzgpu_plonk_quotient_dev(int field, size_t n4, const uint64_t* const* d_evals, const uint64_t* params,
-                             uint64_t* d_t);
+                             int mont_in, uint64_t* d_t);
 
 /* ---- diagnostics used by the parity tests and bench.py ---------------------------------- */
 /* elementwise Montgomery-core check: out[i] = a[i] op b[i] in the chosen field.

@@ -176,33 +176,36 @@ enum { Q_A, Q_B, Q_C, Q_Z, Q_QM, Q_QL, Q_QR, Q_QO, Q_QC, Q_S1, Q_S2, Q_S3, Q_PI,
 struct QuotPtrs { const uint32_t* p[Q_COUNT]; };
 template <class P> struct QuotParams { Fe<P> alpha, beta, gamma, k1, k2, zh_inv[4]; };   // Montgomery form
 
-template <class P>
+// MONT: the operand vectors already hold Montgomery-form values (their coefficient vectors were scaled by R before the
+// coset NTTs, which are linear), so the 16 per-point conversions disappear; the result is stored canonical either way.
+template <class P, bool MONT>
 __global__ void quotient_kernel(size_t n4, QuotPtrs q, QuotParams<P> pp, uint32_t* out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const size_t o = i * P::N;
-  Fe<P> a = ld_mont<P>(q.p[Q_A] + o), b = ld_mont<P>(q.p[Q_B] + o), c = ld_mont<P>(q.p[Q_C] + o);
-  Fe<P> z = ld_mont<P>(q.p[Q_Z] + o);
+  auto ld_mont = [](const uint32_t* p) { return MONT ? ld_fe<P>(p) : fe_to_mont<P>(ld_fe<P>(p)); };
+  Fe<P> a = ld_mont(q.p[Q_A] + o), b = ld_mont(q.p[Q_B] + o), c = ld_mont(q.p[Q_C] + o);
+  Fe<P> z = ld_mont(q.p[Q_Z] + o);
   // gate constraint  a b qM + a qL + b qR + c qO + PI + qC           plonk/prover.py:297
-  Fe<P> t = fe_mul<P>(fe_mul<P>(a, b), ld_mont<P>(q.p[Q_QM] + o));
-  t = fe_add<P>(t, fe_mul<P>(a, ld_mont<P>(q.p[Q_QL] + o)));
-  t = fe_add<P>(t, fe_mul<P>(b, ld_mont<P>(q.p[Q_QR] + o)));
-  t = fe_add<P>(t, fe_mul<P>(c, ld_mont<P>(q.p[Q_QO] + o)));
-  t = fe_add<P>(t, fe_add<P>(ld_mont<P>(q.p[Q_PI] + o), ld_mont<P>(q.p[Q_QC] + o)));
+  Fe<P> t = fe_mul<P>(fe_mul<P>(a, b), ld_mont(q.p[Q_QM] + o));
+  t = fe_add<P>(t, fe_mul<P>(a, ld_mont(q.p[Q_QL] + o)));
+  t = fe_add<P>(t, fe_mul<P>(b, ld_mont(q.p[Q_QR] + o)));
+  t = fe_add<P>(t, fe_mul<P>(c, ld_mont(q.p[Q_QO] + o)));
+  t = fe_add<P>(t, fe_add<P>(ld_mont(q.p[Q_PI] + o), ld_mont(q.p[Q_QC] + o)));
   // permutation numerator  alpha z (a + beta X + gamma)(b + beta k1 X + gamma)(c + beta k2 X + gamma)   :298-300
   Fe<P> ag = fe_add<P>(a, pp.gamma), bg = fe_add<P>(b, pp.gamma), cg = fe_add<P>(c, pp.gamma);
-  Fe<P> bx = fe_mul<P>(ld_mont<P>(q.p[Q_X] + o), pp.beta);
+  Fe<P> bx = fe_mul<P>(ld_mont(q.p[Q_X] + o), pp.beta);
   Fe<P> u = fe_mul<P>(fe_mul<P>(fe_add<P>(ag, bx), fe_add<P>(bg, fe_mul<P>(bx, pp.k1))), fe_add<P>(cg, fe_mul<P>(bx, pp.k2)));
   u = fe_mul<P>(u, z);
   // permutation denominator  alpha (a + beta S1 + gamma)(b + beta S2 + gamma)(c + beta S3 + gamma) z(wX)   :301-305
   size_t is = i + 4 < n4 ? i + 4 : i + 4 - n4;            // w = w_4n^4: z(w x_i) = z(x_{i+4})
-  Fe<P> zw = ld_mont<P>(q.p[Q_Z] + is * P::N);
-  Fe<P> v = fe_mul<P>(fe_mul<P>(fe_add<P>(ag, fe_mul<P>(ld_mont<P>(q.p[Q_S1] + o), pp.beta)),
-                                fe_add<P>(bg, fe_mul<P>(ld_mont<P>(q.p[Q_S2] + o), pp.beta))),
-                      fe_add<P>(cg, fe_mul<P>(ld_mont<P>(q.p[Q_S3] + o), pp.beta)));
+  Fe<P> zw = ld_mont(q.p[Q_Z] + is * P::N);
+  Fe<P> v = fe_mul<P>(fe_mul<P>(fe_add<P>(ag, fe_mul<P>(ld_mont(q.p[Q_S1] + o), pp.beta)),
+                                fe_add<P>(bg, fe_mul<P>(ld_mont(q.p[Q_S2] + o), pp.beta))),
+                      fe_add<P>(cg, fe_mul<P>(ld_mont(q.p[Q_S3] + o), pp.beta)));
   v = fe_mul<P>(v, zw);
   // alpha^2 (z - 1) L1                                                                           :306-307
-  Fe<P> w4 = fe_mul<P>(fe_sub<P>(z, fe_one<P>()), ld_mont<P>(q.p[Q_L1] + o));
+  Fe<P> w4 = fe_mul<P>(fe_sub<P>(z, fe_one<P>()), ld_mont(q.p[Q_L1] + o));
   Fe<P> perm = fe_add<P>(fe_sub<P>(u, v), fe_mul<P>(w4, pp.alpha));
   t = fe_add<P>(t, fe_mul<P>(perm, pp.alpha));
   t = fe_mul<P>(t, pp.zh_inv[i & 3]);
@@ -210,7 +213,7 @@ __global__ void quotient_kernel(size_t n4, QuotPtrs q, QuotParams<P> pp, uint32_
 }
 
 template <class P>
-int quotient_impl(size_t n4, const uint64_t* const* d_evals, const uint64_t* params, uint32_t* d_t) {
+int quotient_impl(size_t n4, const uint64_t* const* d_evals, const uint64_t* params, int mont_in, uint32_t* d_t) {
   KzgpuCtx& cx = kz_ctx();
   QuotPtrs q;
   for (int i = 0; i < Q_COUNT; i++) {
@@ -224,7 +227,8 @@ int quotient_impl(size_t n4, const uint64_t* const* d_evals, const uint64_t* par
     if (!kz_fe_reduced<P>(v)) return kz_fail(KZGPU_ERANGE, "quotient parameter %d is not a canonical field element", i);
     *dst[i] = fe_to_mont<P>(v);
   }
-  quotient_kernel<P><<<(unsigned)kz_div_up(n4, 128), 128, 0, cx.stream>>>(n4, q, pp, d_t);
+  if (mont_in) quotient_kernel<P, true><<<(unsigned)kz_div_up(n4, 128), 128, 0, cx.stream>>>(n4, q, pp, d_t);
+  else quotient_kernel<P, false><<<(unsigned)kz_div_up(n4, 128), 128, 0, cx.stream>>>(n4, q, pp, d_t);
   KZ_LAUNCHED();
   return 0;
 }
@@ -253,12 +257,13 @@ int kzgpu_plonk_permutation_dev(int field, size_t n, const uint64_t* d_a, const 
   return kz_fail(KZGPU_EINVAL, "unknown field id %d", field);
 }
 
-int kzgpu_plonk_quotient_dev(int field, size_t n4, const uint64_t* const* d_evals, const uint64_t* params, uint64_t* d_t) {
+int kzgpu_plonk_quotient_dev(int field, size_t n4, const uint64_t* const* d_evals, const uint64_t* params, int mont_in,
+                             uint64_t* d_t) {
   KZ_REQUIRE_INIT();
   if (!d_evals || !params || !d_t) return kz_fail(KZGPU_EINVAL, "null pointer");
   if (n4 < 8 || (n4 & (n4 - 1))) return kz_fail(KZGPU_EINVAL, "the coset size must be a power of two >= 8");
-  if (field == KZGPU_BN254) return quotient_impl<FrBN254>(n4, d_evals, params, (uint32_t*)d_t);
-  if (field == KZGPU_BLS12_381) return quotient_impl<FrBLS381>(n4, d_evals, params, (uint32_t*)d_t);
+  if (field == KZGPU_BN254) return quotient_impl<FrBN254>(n4, d_evals, params, mont_in, (uint32_t*)d_t);
+  if (field == KZGPU_BLS12_381) return quotient_impl<FrBLS381>(n4, d_evals, params, mont_in, (uint32_t*)d_t);
   return kz_fail(KZGPU_EINVAL, "unknown field id %d", field);
 }
 

@@ -274,17 +274,20 @@ class Indexer:
         n4 = 4 * n
         w4 = f.root(n4)
         shift = _GEN[cid]
+        # (kept in Montgomery form, value * 2^256 mod r: the NTT is linear, so scaling the n coefficients once saves the
+        # quotient kernel a conversion per operand and point)
+        rm = pow(2, 256, r)
         coset = {}
         for name in names:
             e = DVec(n4, zero=True)
-            e.copy_from(polys[name], n)
+            f.lincomb(e, n, [(polys[name].ptr, n, rm)])
             f.coset_ntt(e, n4, w4, shift)
             coset[name] = e
         l1 = DVec(n4, zero=True)                                        # L1 = (X^n - 1)/(n (X - 1)) = (1/n) sum X^i
-        f.powers(l1, n, 1, pow(n, -1, r))
+        f.powers(l1, n, 1, pow(n, -1, r) * rm % r)
         f.coset_ntt(l1, n4, w4, shift)
         xs = DVec(n4)
-        f.powers(xs, n4, w4, shift)
+        f.powers(xs, n4, w4, shift * rm % r)
         sn = pow(shift, n, r)
         iota = pow(w4, n, r)                                            # primitive 4th root of unity
         zh_inv = [pow((sn * pow(iota, k, r) - 1) % r, -1, r) for k in range(4)]
@@ -294,7 +297,7 @@ class Indexer:
             "ck": srs, "polynomials": polys, "commitments": commitments,
             "subgroups": {**sub, "H": H}, "sigma_star": sigma_star,
             "vanishing_poly": ("X^n - 1", n),
-            "coset": {"n4": n4, "w4": w4, "shift": shift, "evals": coset, "L1": l1, "X": xs, "zh_inv": zh_inv},
+            "coset": {"n4": n4, "w4": w4, "shift": shift, "evals": coset, "L1": l1, "X": xs, "zh_inv": zh_inv, "mont": rm},
         }
         ivk = {"rk": None, "commitments": commitments, "subgroups": sub, "tau": tau}
         return ipk, ivk
@@ -395,7 +398,7 @@ class Prover:
         for name, vec, length in (("a", a_poly, n + 2), ("b", b_poly, n + 2), ("c", c_poly, n + 2),
                                   ("z", z_poly, n + 3), ("PI", pi, n)):
             e = DVec(n4, zero=True)
-            e.copy_from(vec, length)
+            f.lincomb(e, length, [(vec.ptr, length, cs["mont"])])       # copy scaled by 2^256: Montgomery-form evaluations
             f.coset_ntt(e, n4, w4, shift)
             ev[name] = e
         ce = cs["evals"]
@@ -403,7 +406,7 @@ class Prover:
                  ce["S_sigma1"], ce["S_sigma2"], ce["S_sigma3"], ev["PI"], cs["L1"], cs["X"]]
         params = ints_to_limbs([int(alpha), int(beta), int(gamma), k1, k2] + cs["zh_inv"], r)
         t = DVec(n4)
-        check(lib.kzgpu_plonk_quotient_dev(cid, n4, _voidp_array([v.ptr for v in order]), ptr(params), t.ptr))
+        check(lib.kzgpu_plonk_quotient_dev(cid, n4, _voidp_array([v.ptr for v in order]), ptr(params), 1, t.ptr))
         f.coset_ntt(t, n4, w4, shift, inverse=True)
         for e in ev.values():
             e.free()
@@ -450,22 +453,24 @@ class Prover:
         r_poly = DVec(n + 6)
         f.lincomb(r_poly, n + 6, terms, constant=const)
 
-        def open_dev(polys, point):
+        def quotient_into(dst, polys, point):
+            """(sum_j v^(j+1) p_j - value) / (X - point) left on the device (kzg.py:147-154)."""
             k = len(polys)
-            out = np.zeros(2 * device.FP_LIMBS[cid], dtype=np.uint64)
-            inf = ctypes.c_int(0)
-            evo = np.zeros(4, dtype=np.uint64)
             lens = (ctypes.c_size_t * k)(*[ln for _, ln in polys])
-            rc = lib.kzgpu_open_dev(srs.handle, _voidp_array([p.ptr for p, _ in polys]), lens, k, ptr(f.L(point)), ptr(f.L(v)),
-                                    ptr(out), ctypes.byref(inf), ptr(evo))
-            if rc == _ffi.E_RANGE:
-                raise ValueError(_ffi.last_error())
-            check(rc)
-            return kzg._codec.from_device(out, bool(inf.value))
+            ql = ctypes.c_size_t(0)
+            check(lib.kzgpu_open_quotient_dev(cid, _voidp_array([p.ptr for p, _ in polys]), lens, k, ptr(f.L(point)), ptr(f.L(v)),
+                                              dst.ptr, ctypes.byref(ql), None))
+            return ql.value
 
         lap("round5_linearisation")
-        W_z = open_dev([(r_poly, n + 6), (a_poly, n + 2), (b_poly, n + 2), (c_poly, n + 2), (P["S_sigma1"], n), (P["S_sigma2"], n)], zi)
-        W_zw = open_dev([(z_poly, n + 3)], zi * g % r)
+        # the two opening proofs are the commitments of two quotients: formed on the device, committed in one MSM pass
+        q_buf = DVec(2 * (n + 5), zero=True)
+        quotient_into(_View(q_buf, 0), [(r_poly, n + 6), (a_poly, n + 2), (b_poly, n + 2), (c_poly, n + 2),
+                                        (P["S_sigma1"], n), (P["S_sigma2"], n)], zi)            # n + 5 coefficients
+        quotient_into(_View(q_buf, n + 5), [(z_poly, n + 3)], zi * g % r)                         # n + 2 coefficients
+        outs, infs = device.msm_batch_dev(srs, q_buf, n + 5, 2)
+        W_z, W_zw = (kzg._codec.from_device(o, i) for o, i in zip(outs, infs))
+        q_buf.free()
         lap("round5_openings")
         self.last_r_zeta = f.eval(r_poly, n + 6, zi)                    # plonk/prover.py:171 asserts this is 0
         self.last_t_top = t.read_ints(3 * n + 6, min(8, n4 - 3 * n - 6))   # deg t <= 3n+5: must be zeros
