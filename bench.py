@@ -159,26 +159,51 @@ def cpu_ntt_rate(logn, cores):
     return (1 << logn) * cores / wall, wall
 
 
-def cpu_plonk_hotpath():
-    """Seconds the restated oracle needs for the hot-path calls the reference's PLONK prover made on
-    the bundled instance (the kzg.commit / kzg.open / fft_ff_interpolation records of
-    tests/golden/ref_trace_plonk.json after the indexer's), 1 core."""
+def _replay_prover_calls(name, make_key, commit, open_, fns, F):
+    """Time the hot-path calls the reference's prover made on a bundled instance (the records of
+    tests/golden/ref_trace_<name>.json after the indexer's) through one implementation of the boundary."""
+    tr = json.load(open(os.path.join(ROOT, "tests", "golden", f"ref_trace_{name}.json")))
+    H = lambda v: int(v, 16)                                          # noqa: E731
+    keys = [make_key([(H(p[0]), H(p[1])) for p in k]) for k in tr["keys"]]
+    calls = tr["calls"][tr["notes"]["index_calls"]:]
+    t0 = time.perf_counter()
+    for rec in calls:
+        if rec["fn"] == "commit":
+            commit(keys[rec["ck_id"]], [[H(c) for c in p] for p in rec["polys"]])
+        elif rec["fn"] == "open":
+            open_(keys[rec["ck_id"]], [[H(c) for c in p] for p in rec["polys"]], H(rec["z"]), H(rec["xi"]))
+        else:
+            fns[rec["fn"]]([F(H(v)) for v in rec["in"]], F(H(rec["w"])), F)
+    return time.perf_counter() - t0, len(calls), tr["notes"]["prove_seconds"]
+
+
+def cpu_hotpath(name):
+    """The restated oracle on those calls, 1 core (the reference is single-threaded)."""
     from oracle import fft_ff as off
     from oracle.field import GFp
     from oracle.kzg import KZGOracle
-    tr = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_trace_plonk.json")))
-    H = lambda v: int(v, 16)                                          # noqa: E731
-    ko, F = KZGOracle("bn254"), GFp(R_BN254)
-    keys = [[(H(p[0]), H(p[1]), 1) for p in k] for k in tr["keys"]]
-    t0 = time.perf_counter()
-    for rec in tr["calls"][tr["notes"]["index_calls"]:]:
-        if rec["fn"] == "commit":
-            ko.commit(keys[rec["ck_id"]], [[H(c) for c in p] for p in rec["polys"]])
-        elif rec["fn"] == "open":
-            ko.open(keys[rec["ck_id"]], [[H(c) for c in p] for p in rec["polys"]], H(rec["z"]), H(rec["xi"]))
-        else:
-            off.fft_ff_interpolation([F(H(v)) for v in rec["in"]], F(H(rec["w"])), F)
-    return time.perf_counter() - t0
+    ko = KZGOracle("bn254")
+    return _replay_prover_calls(name, lambda pts: [(x, y, 1) for x, y in pts], ko.commit, ko.open,
+                                {"fft_ff": off.fft_ff, "ifft_ff": off.ifft_ff, "fft_ff_interpolation": off.fft_ff_interpolation},
+                                GFp(R_BN254))[0]
+
+
+def dropin_hotpath(name):
+    """The same calls through the GPU drop-in modules (`kzg.KZG`, `fft_ff`): Python objects in, Python objects out,
+    i.e. what the reference's unmodified prover pays when the two modules are shadowed."""
+    from kzg_snark_b200.kzg import KZG
+    from kzg_snark_b200 import fft_ff as gff
+    kzg = KZG("bn254")
+    fq = kzg._codec.fq
+    fns = {"fft_ff": gff.fft_ff, "ifft_ff": gff.ifft_ff, "fft_ff_interpolation": gff.fft_ff_interpolation}
+    mk = lambda pts: [(fq(x), fq(y), fq(1)) for x, y in pts]           # noqa: E731
+    _replay_prover_calls(name, mk, kzg.commit, kzg.open, fns, kzg.Fq)                   # warm-up: key upload, NTT plans
+    best = min(_replay_prover_calls(name, mk, kzg.commit, kzg.open, fns, kzg.Fq) for _ in range(3))
+    return {"dropin_hotpath_s": best[0], "calls": best[1], "reference_prove_s": best[2]}
+
+
+def cpu_plonk_hotpath():
+    return cpu_hotpath("plonk")
 
 
 def run_reference(args):
@@ -487,6 +512,10 @@ def run_gpu(args):
         launches = (_ffi.launch_count() - l0) // 5
         assert prover.last_r_zeta == 0 and not any(prover.last_t_top), "r(zeta) != 0: the proof would not verify"
         times = sorted(times[3:])
+        out["bundled"].update({k: v for k, v in dropin_hotpath("plonk").items() if k != "reference_prove_s"})
+        out["marlin_bundled"] = {**dropin_hotpath("marlin"),
+                                 "note": "configs[4] bundled R1CS instance: the 19 commit / open / fft_ff / fft_ff_interpolation calls "
+                                         "marlin/prover.py made (tests/golden/ref_trace_marlin.json), replayed through the drop-in"}
         out["synthetic"] = {"gates": n, "prove_s": times[len(times) // 2], "index_s": t_index, "circuit_generation_s": t_gen,
                             "h2d_bytes": int(wl.nbytes), "host_buffers": "pinned (cudaHostAlloc)", "gpu_launches_per_prove": int(launches),
                             "rounds_s": {k: round(v, 5) for k, v in prover.timings.items()},
@@ -669,6 +698,7 @@ def run_gpu(args):
         if plonk is not None:
             if cpu_plonk is not None:
                 plonk["bundled"]["cpu_port_hotpath_s"] = cpu_plonk
+                plonk["marlin_bundled"]["cpu_port_hotpath_s"] = cpu_hotpath("marlin")
             line["plonk"] = plonk
         if secondary is not None:
             line["ntt"] = {"metric": "ntt_elements_per_s", "value": secondary["value"], "unit": "elements/s",

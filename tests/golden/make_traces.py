@@ -168,6 +168,7 @@ def trace_marlin():
         t0 = time.time()
         ipk, ivk = rr.load("marlin.indexer").Indexer(curve_type="bn254").preprocess(A, B, C, max_degree=200)
         t1 = time.time()
+        index_calls = len(rr.trace)
         proof = rr.load("marlin.prover").Prover(curve_type="bn254").prove(ipk, x, w)
         t2 = time.time()
         ok = rr.load("marlin.verifier").Verifier(curve_type="bn254").verify(ivk, x, proof)
@@ -175,7 +176,8 @@ def trace_marlin():
         dump("ref_trace_marlin.json", {
             "source": "reference marlin/{indexer,prover,verifier}.py + kzg.py + fft_ff.py run by oracle/refrun.py",
             "seed": SEED + 3, "curve": "bn254",
-            "notes": {"verify": bool(ok), "index_seconds": round(t1 - t0, 3), "prove_seconds": round(t2 - t1, 3)},
+            "notes": {"verify": bool(ok), "index_calls": index_calls, "index_seconds": round(t1 - t0, 3),
+                      "prove_seconds": round(t2 - t1, 3)},
             "keys": rr.keys, "calls": rr.trace})
 
 
