@@ -192,6 +192,22 @@ int kzgpu_plonk_permutation_dev(int field, size_t n, const uint64_t* d_a, const 
 int kzgpu_plonk_quotient_dev(int field, size_t n4, const uint64_t* const* d_evals, const uint64_t* params,
                              int mont_in, uint64_t* d_t);
 
+/* Marlin prover evaluation loops.  d_row / d_col / d_val: the K-domain evaluations of the index
+ * polynomials row_M, col_M, val_M for M = A, B, C back to back (3 * m elements each; marlin/encoder.py:98-125).
+ * f2 evaluations (marlin/prover.py:404-466):  d_out[kappa] = scale * sum_M eta_M val_M(kappa) /
+ * ((beta1 - row_M(kappa)) (alpha - col_M(kappa))), terms with a zero denominator skipped as in the reference;
+ * scale = v_H(beta1) v_H(alpha); one inverse NTT over K gives f_2 (:469). */
+int kzgpu_marlin_f2_evals_dev(int field, size_t m, const uint64_t* d_row, const uint64_t* d_col, const uint64_t* d_val,
+                              const uint64_t* eta, const uint64_t* alpha, const uint64_t* beta1, const uint64_t* scale,
+                              uint64_t* d_out);
+/* t(X) on H (marlin/prover.py:248-301): d_out[i] = t(h_i) = scale * h_i^-1 * sum over the entries (M, kappa) whose row is
+ * h_i of eta_M val_M(kappa) / (alpha - col_M(kappa)), scale = n v_H(alpha) (v_H(X)/(X - h) vanishes on H except at h, where
+ * it is n/h).  d_row_index: 3 * m indices i of row_M(kappa) = h_i, ascending per matrix (the index is built in row-major
+ * order), 0xffffffff for padding entries; d_H[i] = h_i.  One inverse NTT over H gives t's coefficients. */
+int kzgpu_marlin_t_evals_dev(int field, size_t n, size_t m, const uint32_t* d_row_index, const uint64_t* d_col,
+                             const uint64_t* d_val, const uint64_t* d_H, const uint64_t* eta, const uint64_t* alpha,
+                             const uint64_t* scale, uint64_t* d_out);
+
 /* ---- diagnostics used by the parity tests and bench.py ---------------------------------- */
 /* elementwise Montgomery-core check: out[i] = a[i] op b[i] in the chosen field.
  * which: 0 = Fp(curve), 1 = Fr(curve); op: 0 mul, 1 add, 2 sub, 3 inverse(a). */

@@ -1,5 +1,11 @@
-// PLONK prover polynomial kernels: the two places where the reference's
-// prover spends its time once commit/open/fft_ff are on the GPU.
+// Prover polynomial kernels for the callers of commit / open / fft_ff: the places where
+// the reference's PLONK and Marlin provers spend their time once the hot path itself is on the GPU.
+//
+//   Marlin evaluation loops     marlin/prover.py:248-301 (_compute_t_polynomial), :404-470 (_compute_f2_polynomial)
+//        both sum, over the non-zero entries kappa of the three index matrices, eta_M val_M(kappa) divided by
+//        (x - row_M(kappa)) (alpha - col_M(kappa)); the reference loops over K with one rational-function division per
+//        entry.  Here: numerators / denominators per entry, ONE batched inversion over the 3m denominators, then a sum per
+//        kappa (f_2, x = beta_1) or per row of H (t: v_H(X)/(X - h) vanishes on H except at h, where it is n/h).
 //
 //   permutation grand product   plonk/prover.py:245-258   z(w^0) = 1,
 //        z(w^(i+1)) = z(w^i) * num_i / den_i,
@@ -233,6 +239,79 @@ int quotient_impl(size_t n4, const uint64_t* const* d_evals, const uint64_t* par
   return 0;
 }
 
+// ---------------------------------------------------------------------------- Marlin loops (N4)
+template <class P> struct MarlinParams { Fe<P> eta[3], alpha, beta1, scale; };   // Montgomery form
+
+// entry e = M * m + kappa: num = eta_M * val, den = (alpha - col) [* (beta1 - row) when WITH_ROW]; den == 0 -> term skipped
+template <class P, bool WITH_ROW>
+__global__ void marlin_terms_kernel(size_t m, const uint32_t* row, const uint32_t* col, const uint32_t* val, MarlinParams<P> pp,
+                                    uint32_t* num, uint32_t* den) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 3 * m) return;
+  const uint32_t M = (uint32_t)(e / m);
+  Fe<P> d = fe_sub<P>(pp.alpha, ld_mont<P>(col + e * P::N));
+  if (WITH_ROW) d = fe_mul<P>(d, fe_sub<P>(pp.beta1, ld_mont<P>(row + e * P::N)));
+  Fe<P> nu = fe_mul<P>(ld_mont<P>(val + e * P::N), pp.eta[M]);
+  if (fe_is_zero<P>(d)) { nu = fe_zero<P>(); d = fe_one<P>(); }     // `if denom != 0` of the reference
+  st_fe<P>(num + e * P::N, nu);
+  st_fe<P>(den + e * P::N, d);
+}
+
+// f2(kappa) = scale * sum_M ratio[M * m + kappa]
+template <class P>
+__global__ void marlin_f2_sum_kernel(size_t m, const uint32_t* ratio, Fe<P> scale, uint32_t* out) {
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  Fe<P> s = fe_add<P>(fe_add<P>(ld_fe<P>(ratio + k * P::N), ld_fe<P>(ratio + (m + k) * P::N)), ld_fe<P>(ratio + (2 * m + k) * P::N));
+  st_fe<P>(out + k * P::N, fe_from_mont<P>(fe_mul<P>(s, scale)));
+}
+
+// t(h_i) = scale * h_i^-1 * sum over the entries whose row is h_i (row_index sorted ascending per matrix, 0xffffffff = padding)
+template <class P>
+__global__ void marlin_t_rows_kernel(size_t n, size_t m, const uint32_t* row_index, const uint32_t* ratio, const uint32_t* H, Fe<P> scale,
+                                     uint32_t* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fe<P> s = fe_zero<P>();
+  for (uint32_t M = 0; M < 3; M++) {
+    const uint32_t* ri = row_index + (size_t)M * m;
+    size_t lo = 0, hi = m;                       // first kappa with ri[kappa] >= i
+    while (lo < hi) { size_t mid = (lo + hi) >> 1; if (ri[mid] < (uint32_t)i) lo = mid + 1; else hi = mid; }
+    for (size_t k = lo; k < m && ri[k] == (uint32_t)i; k++) s = fe_add<P>(s, ld_fe<P>(ratio + ((size_t)M * m + k) * P::N));
+  }
+  Fe<P> hinv = ld_fe<P>(H + ((n - i) & (n - 1)) * P::N);            // h_i^-1 = h_(n-i), canonical: the product comes out canonical
+  st_fe<P>(out + i * P::N, fe_mul<P>(fe_mul<P>(s, scale), hinv));
+}
+
+template <class P>
+int marlin_impl(bool is_t, size_t n, size_t m, const uint32_t* d_row_or_index, const uint32_t* d_col, const uint32_t* d_val,
+                const uint32_t* d_H, const uint64_t* eta, const uint64_t* alpha, const uint64_t* beta1, const uint64_t* scale,
+                uint32_t* d_out) {
+  KzgpuCtx& cx = kz_ctx();
+  MarlinParams<P> pp;
+  const uint64_t* src[6] = {eta, eta + 4, eta + 8, alpha, beta1 ? beta1 : alpha, scale};
+  Fe<P>* dst[6] = {&pp.eta[0], &pp.eta[1], &pp.eta[2], &pp.alpha, &pp.beta1, &pp.scale};
+  for (int i = 0; i < 6; i++) {
+    Fe<P> v = kz_fe_from_u64<P>(src[i]);
+    if (!kz_fe_reduced<P>(v)) return kz_fail(KZGPU_ERANGE, "eta / alpha / beta_1 / scale must be canonical field elements");
+    *dst[i] = fe_to_mont<P>(v);
+  }
+  int rc;
+  const size_t eb = P::N * 4, cnt = 3 * m;
+  if ((rc = g_ws.num.ensure(cnt * eb)) || (rc = g_ws.den.ensure(cnt * eb)) || (rc = g_ws.pre.ensure(cnt * eb)) || (rc = g_ws.flag.ensure(64))) return rc;
+  uint32_t *num = (uint32_t*)g_ws.num.p, *den = (uint32_t*)g_ws.den.p, *pre = (uint32_t*)g_ws.pre.p;
+  if (is_t) marlin_terms_kernel<P, false><<<(unsigned)kz_div_up(cnt, 128), 128, 0, cx.stream>>>(m, nullptr, d_col, d_val, pp, num, den);
+  else marlin_terms_kernel<P, true><<<(unsigned)kz_div_up(cnt, 128), 128, 0, cx.stream>>>(m, d_row_or_index, d_col, d_val, pp, num, den);
+  KZ_LAUNCHED();
+  size_t T = kz_div_up(cnt, INV_ROUNDS);
+  batch_ratio_kernel<P><<<(unsigned)kz_div_up(T, 128), 128, 0, cx.stream>>>(cnt, T, num, den, pre, (int*)g_ws.flag.p);
+  KZ_LAUNCHED();
+  if (is_t) marlin_t_rows_kernel<P><<<(unsigned)kz_div_up(n, 128), 128, 0, cx.stream>>>(n, m, d_row_or_index, num, d_H, pp.scale, d_out);
+  else marlin_f2_sum_kernel<P><<<(unsigned)kz_div_up(m, 128), 128, 0, cx.stream>>>(m, num, pp.scale, d_out);
+  KZ_LAUNCHED();
+  return 0;
+}
+
 }  // namespace
 
 void kz_plonk_release() {
@@ -264,6 +343,30 @@ int kzgpu_plonk_quotient_dev(int field, size_t n4, const uint64_t* const* d_eval
   if (n4 < 8 || (n4 & (n4 - 1))) return kz_fail(KZGPU_EINVAL, "the coset size must be a power of two >= 8");
   if (field == KZGPU_BN254) return quotient_impl<FrBN254>(n4, d_evals, params, mont_in, (uint32_t*)d_t);
   if (field == KZGPU_BLS12_381) return quotient_impl<FrBLS381>(n4, d_evals, params, mont_in, (uint32_t*)d_t);
+  return kz_fail(KZGPU_EINVAL, "unknown field id %d", field);
+}
+
+int kzgpu_marlin_f2_evals_dev(int field, size_t m, const uint64_t* d_row, const uint64_t* d_col, const uint64_t* d_val,
+                              const uint64_t* eta, const uint64_t* alpha, const uint64_t* beta1, const uint64_t* scale, uint64_t* d_out) {
+  KZ_REQUIRE_INIT();
+  if (!d_row || !d_col || !d_val || !eta || !alpha || !beta1 || !scale || !d_out) return kz_fail(KZGPU_EINVAL, "null pointer");
+  if (m == 0) return 0;
+  if (field == KZGPU_BN254)
+    return marlin_impl<FrBN254>(false, 0, m, (const uint32_t*)d_row, (const uint32_t*)d_col, (const uint32_t*)d_val, nullptr, eta, alpha, beta1, scale, (uint32_t*)d_out);
+  if (field == KZGPU_BLS12_381)
+    return marlin_impl<FrBLS381>(false, 0, m, (const uint32_t*)d_row, (const uint32_t*)d_col, (const uint32_t*)d_val, nullptr, eta, alpha, beta1, scale, (uint32_t*)d_out);
+  return kz_fail(KZGPU_EINVAL, "unknown field id %d", field);
+}
+
+int kzgpu_marlin_t_evals_dev(int field, size_t n, size_t m, const uint32_t* d_row_index, const uint64_t* d_col, const uint64_t* d_val,
+                             const uint64_t* d_H, const uint64_t* eta, const uint64_t* alpha, const uint64_t* scale, uint64_t* d_out) {
+  KZ_REQUIRE_INIT();
+  if (!d_row_index || !d_col || !d_val || !d_H || !eta || !alpha || !scale || !d_out) return kz_fail(KZGPU_EINVAL, "null pointer");
+  if (n == 0 || (n & (n - 1))) return kz_fail(KZGPU_EINVAL, "|H| must be a power of two");
+  if (field == KZGPU_BN254)
+    return marlin_impl<FrBN254>(true, n, m, d_row_index, (const uint32_t*)d_col, (const uint32_t*)d_val, (const uint32_t*)d_H, eta, alpha, nullptr, scale, (uint32_t*)d_out);
+  if (field == KZGPU_BLS12_381)
+    return marlin_impl<FrBLS381>(true, n, m, d_row_index, (const uint32_t*)d_col, (const uint32_t*)d_val, (const uint32_t*)d_H, eta, alpha, nullptr, scale, (uint32_t*)d_out);
   return kz_fail(KZGPU_EINVAL, "unknown field id %d", field);
 }
 

@@ -17,6 +17,8 @@ reference's outputs (points normalised to affine):
   ref_trace_fft.json     fft_ff / ifft_ff / fft_ff_interpolation from fft_ff.py on n = 1 .. 2^8 (fft_ff also 2^10)
   ref_trace_plonk.json   main.py:64-94: Indexer.preprocess, Prover.prove, Verifier.verify (accepts)
   ref_trace_marlin.json  main.py:39-61 likewise
+  ref_marlin_loops.json  the reference's `_compute_t_polynomial` / `_compute_f2_polynomial` (marlin/prover.py:248-301,
+                         404-470) on the bundled index with seeded challenges: inputs and outputs (for the N4 kernels)
   ref_plonk_normalized.json
                          the reference PLONK prover run once more with commitments NORMALISED to
                          (x, y, 1) before they reach the transcript -- what any drop-in returning
@@ -181,6 +183,39 @@ def trace_marlin():
             "keys": rr.keys, "calls": rr.trace})
 
 
+def marlin_loops():
+    """The two evaluation loops of marlin/prover.py that SURVEY.md 8f (N4) names -- `_compute_t_polynomial`
+    (:248-301) and `_compute_f2_polynomial` (:404-470) -- run by the reference itself on the bundled R1CS index
+    with seeded challenges: inputs (K-domain row / col / val evaluations of the star matrices) and outputs."""
+    import random
+    with refrun.ReferenceRun(seed=SEED + 5, record=False) as rr:
+        Fq = rr.kzg.KZG("bn254").Fq
+        inst = fixtures.load_r1cs_instance(os.path.join(REF_CS, "R1CS_INSTANCE.pkl"))
+        A, B, C = (sageshim.matrix(Fq, inst[k]) for k in "ABC")
+        ipk, _ = rr.load("marlin.indexer").Indexer(curve_type="bn254").preprocess(A, B, C, max_degree=200)
+        prover = rr.load("marlin.prover").Prover(curve_type="bn254")
+        sub, polys = ipk["subgroups"], ipk["polynomials"]
+        H, K, n, m, g_K = sub["H"], sub["K"], sub["n"], sub["m"], sub["g_K"]
+        v_H, v_K = ipk["vanishing_polys"]["v_H"], ipk["vanishing_polys"]["v_K"]
+        rng = random.Random(SEED + 5)
+        q = Fq.order()
+        eta = [Fq(rng.randrange(q)) for _ in range(3)]
+        alpha, beta1 = Fq(rng.randrange(q)), Fq(rng.randrange(q))
+        assert alpha not in H and beta1 not in H
+        R = rr.kzg.KZG("bn254").R
+        t = prover._compute_t_polynomial(polys, *eta, alpha, v_H, K, R)
+        f2 = prover._compute_f2_polynomial(polys, *eta, beta1, alpha, v_H, v_K, K, g_K, Fq, R)
+        hidx = {int(h): i for i, h in enumerate(H)}
+        ev = {k: [int(polys[k](kap)) for kap in K] for k in polys}
+        dump("ref_marlin_loops.json", {
+            "source": "reference marlin/prover.py _compute_t_polynomial / _compute_f2_polynomial on the bundled R1CS index",
+            "seed": SEED + 5, "n": n, "m": m, "g_H": rr.enc_scalar(sub["g_H"] if "g_H" in sub else H[1]), "g_K": rr.enc_scalar(g_K),
+            "eta": [rr.enc_scalar(e) for e in eta], "alpha": rr.enc_scalar(alpha), "beta1": rr.enc_scalar(beta1),
+            "evals": {k: [hex(v) for v in vals] for k, vals in ev.items()},
+            "row_index": {M: [hidx.get(v, -1) for v in ev[f"row_{M}"]] for M in "ABC"},
+            "t": rr.enc_poly(t), "f2": rr.enc_poly(f2)})
+
+
 def trace_plonk_normalized():
     """Reference prover + indexer with KZG.commit / KZG.open outputs normalised to (x, y, 1): the
     transcript then hashes what a canonical-affine drop-in returns, so kzg_snark_b200.plonk can be
@@ -240,4 +275,5 @@ if __name__ == "__main__":
     trace_fft()
     trace_plonk()
     trace_marlin()
+    marlin_loops()
     trace_plonk_normalized()

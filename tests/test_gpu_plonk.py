@@ -221,3 +221,43 @@ def test_permutation_grand_product(n):
     _ffi.check(f.lib.kzgpu_plonk_permutation_dev(_ffi.BN254, n, va2.ptr, vb.ptr, vc.ptr, vs.ptr, vh.ptr,
                                                  L(k1), L(k2), L(beta), L(gamma), z.ptr, ctypes.byref(flag)))
     assert flag.value == 1
+
+
+def test_marlin_loops_match_the_reference_functions():
+    """`_compute_t_polynomial` and `_compute_f2_polynomial` of marlin/prover.py, run by the reference
+    itself on the bundled R1CS index (tests/golden/ref_marlin_loops.json), against the batched device versions."""
+    from kzg_snark_b200 import marlin
+    from kzg_snark_b200.limbs import ints_to_limbs, limbs_to_ints
+    d = load("ref_marlin_loops.json")
+    n, m = d["n"], d["m"]
+    cat = lambda kind: ints_to_limbs([H(v) for M in "ABC" for v in d["evals"][f"{kind}_{M}"]], R)    # noqa: E731
+    eta = [H(v) for v in d["eta"]]
+    alpha, beta1 = H(d["alpha"]), H(d["beta1"])
+    g_H, g_K = pow(5, (R - 1) // n, R), H(d["g_K"])
+    ridx = [i for M in "ABC" for i in d["row_index"][M]]
+
+    def strip(c):
+        c = list(c)
+        while c and c[-1] == 0:
+            c.pop()
+        return c
+
+    f2 = limbs_to_ints(marlin.compute_f2_polynomial("bn254", cat("row"), cat("col"), cat("val"), eta, alpha, beta1, n, g_K))
+    assert strip(f2) == [H(v) for v in d["f2"]]
+    t = limbs_to_ints(marlin.compute_t_polynomial("bn254", ridx, cat("col"), cat("val"), eta, alpha, n, g_H))
+    assert strip(t) == [H(v) for v in d["t"]]
+    # a zero denominator (alpha equal to a column value) drops that term, as `if denom != 0` does in the reference
+    col0 = H(d["evals"]["col_A"][0])
+    f2b = limbs_to_ints(marlin.compute_f2_polynomial("bn254", cat("row"), cat("col"), cat("val"), eta, col0, beta1, n, g_K))
+    ev = {k: [H(v) for v in vals] for k, vals in d["evals"].items()}
+    scale = (pow(beta1, n, R) - 1) * (pow(col0, n, R) - 1) % R
+    exp = []
+    for k in range(m):
+        acc = 0
+        for e, M in zip(eta, "ABC"):
+            den = (beta1 - ev[f"row_{M}"][k]) * (col0 - ev[f"col_{M}"][k]) % R
+            if den:
+                acc += e * scale % R * ev[f"val_{M}"][k] % R * pow(den, -1, R)
+        exp.append(acc % R)
+    from oracle.fft_ff import ifft_ff_int
+    assert f2b == ifft_ff_int(exp, g_K, R)
