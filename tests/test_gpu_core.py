@@ -435,3 +435,22 @@ def test_point_sharded_open_equals_single_open(dev):
     wit = ko.witness(polys, z, xi)
     assert point_of(cv, out, finf, 4) == cv.normalize(cv.multiply(cv.G1, poly_eval(wit, tau, cv.r)))
     srs.destroy()
+
+
+def test_msm_batch_falls_back_per_polynomial_when_the_pass_does_not_fit(dev):
+    """More polynomials than one pass takes (> 64 bucket sets): the batch entry point runs them one by one;
+    same results.  Also the argument checks of the verifier-side combination."""
+    from kzg_snark_b200 import _ffi
+    cv = get_curve("bn254")
+    rng = random.Random(3)
+    tau = rng.randrange(1, cv.r)
+    srs = dev.Srs.generate("bn254", tau, 40)
+    k, m = 70, 33
+    polys = [[rng.randrange(cv.r) for _ in range(m)] for _ in range(k)]
+    d = _ffi.DeviceBuffer(k * m * 32).upload(np.concatenate([L(p, cv.r) for p in polys]))
+    out, infs = dev.msm_batch_dev(srs, d, m, k)
+    for j in (0, 1, 37, 69):
+        assert point_of(cv, out[j], infs[j], 4) == cv.normalize(cv.multiply(cv.G1, poly_eval(polys[j], tau, cv.r)))
+    with pytest.raises(_ffi.KzgpuError):
+        dev.g1_lincomb("bn254", np.zeros((70000, 8), np.uint64), np.zeros((70000, 4), np.uint64))
+    d.free(); srs.destroy()

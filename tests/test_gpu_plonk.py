@@ -63,6 +63,14 @@ def test_prover_matches_the_reference_prover_bit_for_bit():
         assert int(proof["evaluations"][k]) == H(v), k
     for k, v in exp["kzg_proofs"].items():
         assert aff(proof["kzg_proofs"][k]) == (H(v[0]), H(v[1])), k
+    # the same with the commitment key handed in as a list of points, the way the reference's ipk carries it
+    # (plonk/indexer.py:92-93), and witness values as field elements
+    fq = idx.kzg._codec.fq
+    ck = [(fq(H(p[0])), fq(H(p[1])), fq(1)) for p in d["keys"][0]]
+    ipk2, _ = idx.preprocess(*sel, perm, max_degree=n + 5, ck=ck, k1=H(d["k1"]), k2=H(d["k2"]))
+    proof2 = prover.prove(ipk2, x, [Fq(v) for v in w], blinders=[H(b) for b in d["prover_draws"][-11:]])
+    assert {k: aff(v) for k, v in proof2["commitments"].items()} == {k: aff(v) for k, v in proof["commitments"].items()}
+    assert {k: aff(v) for k, v in proof2["kzg_proofs"].items()} == {k: aff(v) for k, v in proof["kzg_proofs"].items()}
 
 
 @pytest.mark.parametrize("logn,n_pub", [(3, 2), (6, 5), (10, 7), (14, 16), (20, 16)])
