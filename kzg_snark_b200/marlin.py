@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _ffi, device
 from ._ffi import check, ptr
-from .limbs import ints_to_limbs, int_to_limbs
+from .limbs import ints_to_limbs
 from .plonk import DVec, _Field
 
 
