@@ -774,8 +774,10 @@ uint32_t choose_c(size_t n, int bits) {
 }
 
 // window size of the precomputed tables for a key of n points: minimise
-//   10 * n * W(c)  (mixed additions, 10 modmul each)  +  56 * 2^(c-1)  (bucket reduction: 2 full adds per bucket
-//   plus the per-chunk fix-up and the tree sums; calibrated with scripts/c_sweep.py, profiles/r1_c_sweep.txt)
+//   10 * n * W(c)  (mixed additions, 10 modmul each)  +  28 * 2^(c-1)  (bucket reduction, 2 full adds per bucket)
+// (checked against forced-window sweeps, scripts/c_sweep.py / profiles/r1_c_sweep.txt: the model's choice is the
+// measured optimum at 2^16, 2^18, 2^20, 2^22 and 2^24; a larger bucket term would pick windows whose few, heavy
+// buckets leave too few accumulate tasks to fill the SMs)
 // subject to the memory cap and to 31-bit point indices.  Returns 0 when tables are disabled.
 uint32_t choose_table_c(size_t n, int bits, size_t point_bytes) {
   const char* env = getenv("KZGPU_SRS_TABLES");
@@ -796,7 +798,7 @@ uint32_t choose_table_c(size_t n, int bits, size_t point_bytes) {
     uint32_t W = (bits + 1 + c - 1) / c;
     double mem = (double)W * (double)n * (double)point_bytes;
     if (mem > cap || (double)W * (double)n >= 2147483648.0) continue;
-    double cost = 10.0 * (double)(n ? n : 1) * W + 56.0 * (double)(1ull << (c - 1));
+    double cost = 10.0 * (double)(n ? n : 1) * W + 28.0 * (double)(1ull << (c - 1));
     if (cost < best) { best = cost; best_c = c; }
   }
   return best_c;
