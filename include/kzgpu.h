@@ -216,7 +216,10 @@ int kzgpu_field_op(int curve, int which, int op, const uint64_t* a, const uint64
 /* throughput microbenchmarks (DESIGN.md "integer roofline"): runs `iters` dependent
  * operations per thread on blocks*threads threads and returns the elapsed device ms.
  * kind: 0 = IMAD.WIDE.U32 carry chain (raw pipe), 1 = Fp(BN254) Montgomery mul,
- *       2 = Fp(BLS12-381) Montgomery mul, 3 = XYZZ mixed add BN254, 4 = XYZZ mixed add BLS */
+ *       2 = Fp(BLS12-381) Montgomery mul, 3 = XYZZ mixed add BN254, 4 = XYZZ mixed add BLS,
+ *       5..11 = issue-slot probes (ALU / FP64 beside IMAD.WIDE), 12 / 13 = batched-affine pair additions with one
+ *       inversion per thread over `iters` pairs, operands consecutive (12) or gathered from an 8 GiB table (13);
+ *       *ops = additions */
 int kzgpu_microbench(int kind, int blocks, int threads, int iters, float* ms, double* ops);
 /* per-kernel device timing (CUDA events on the launching stream) for bench.py's roofline:
  * which: 0 = MSM bucket-accumulate kernel, 1 = NTT pass kernel, 2 = MSM sort (histogram+scatter),

@@ -413,8 +413,117 @@ int kzgpu_field_op(int curve, int which, int op, const uint64_t* a, const uint64
   return kz_fail(KZGPU_EINVAL, "unknown curve id %d", curve);
 }
 
+}  // extern "C"
+
+// ---- batched-affine feasibility probe ---------------------------------------------------------
+// npairs independent affine additions P[2k] + P[2k+1] with ONE inversion per thread: thread t owns pairs t, t+T, ...
+// (coalesced); forward pass stores the running product of the denominators x2 - x1 (32 B per pair), one Fermat inversion,
+// backward pass peels the inverses off and finishes the additions (6 modmul per addition + 381 / K for the inversion).
+// GATHER: operands are fetched through a random index into a table far larger than L2 (the first pairing round of a bucket
+// sum reads the key's window tables this way); otherwise they are consecutive (the later rounds).  Operands are arbitrary
+// field elements, which is all the arithmetic cares about.
+namespace {
+template <class P> __device__ __forceinline__ Fe<P> mb_ld(const uint32_t* p) {
+  Fe<P> r;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < P::N / 4; i++) { uint4 t = __ldg(q + i); r.v[4 * i] = t.x; r.v[4 * i + 1] = t.y; r.v[4 * i + 2] = t.z; r.v[4 * i + 3] = t.w; }
+  return r;
+}
+template <class P> __device__ __forceinline__ void mb_st(uint32_t* p, const Fe<P>& a) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < P::N / 4; i++) q[i] = make_uint4(a.v[4 * i], a.v[4 * i + 1], a.v[4 * i + 2], a.v[4 * i + 3]);
+}
+__global__ void mb_fill_kernel(uint32_t* buf, size_t words, uint32_t seed) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= words) return;
+  uint32_t x = (uint32_t)i * 2654435761u ^ seed ^ (uint32_t)(i >> 32);
+  x ^= x << 13; x ^= x >> 17; x ^= x << 5;
+  buf[i] = (i & 7) == 7 ? (x & 0x0fffffffu) : x;          // every 8-word element stays below the 254-bit moduli
+}
+__global__ void mb_index_kernel(uint32_t* idx, size_t n, uint32_t mask, uint32_t seed) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t x = (uint32_t)i * 747796405u + seed;
+  x ^= x >> 16; x *= 2246822519u; x ^= x >> 13; x *= 3266489917u; x ^= x >> 16;
+  idx[i] = x & mask;
+}
+template <class P, bool GATHER>
+__global__ void __launch_bounds__(128) mb_affine_pairs_kernel(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ idx,
+                                                             uint32_t npairs, uint32_t* __restrict__ pre, uint32_t* __restrict__ out) {
+  const uint32_t T = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npairs) return;
+  auto at = [&](uint32_t slot) { return pts + (size_t)(GATHER ? __ldg(idx + slot) : slot) * 2 * P::N; };
+  Fe<P> acc = fe_one<P>();
+  Fe<P> nx1 = mb_ld<P>(at(2 * t)), nx2 = mb_ld<P>(at(2 * t + 1));
+  uint32_t last = t;
+  for (uint32_t k = t; k < npairs; k += T) {
+    Fe<P> x1 = nx1, x2 = nx2;
+    if (k + T < npairs) { nx1 = mb_ld<P>(at(2 * (k + T))); nx2 = mb_ld<P>(at(2 * (k + T) + 1)); }
+    mb_st<P>(pre + (size_t)k * P::N, acc);
+    acc = fe_mul<P>(acc, fe_sub<P>(x2, x1));
+    last = k;
+  }
+  Fe<P> inv = fe_inv<P>(acc);
+  const uint32_t* p1 = at(2 * last); const uint32_t* p2 = at(2 * last + 1);
+  Fe<P> a1 = mb_ld<P>(p1), b1 = mb_ld<P>(p1 + P::N), a2 = mb_ld<P>(p2), b2 = mb_ld<P>(p2 + P::N), pr = mb_ld<P>(pre + (size_t)last * P::N);
+  for (uint32_t k = last;; k -= T) {
+    Fe<P> x1 = a1, y1 = b1, x2 = a2, y2 = b2, pk = pr;
+    if (k >= T) {
+      p1 = at(2 * (k - T)); p2 = at(2 * (k - T) + 1);
+      a1 = mb_ld<P>(p1); b1 = mb_ld<P>(p1 + P::N); a2 = mb_ld<P>(p2); b2 = mb_ld<P>(p2 + P::N); pr = mb_ld<P>(pre + (size_t)(k - T) * P::N);
+    }
+    Fe<P> d = fe_sub<P>(x2, x1);
+    Fe<P> di = fe_mul<P>(inv, pk);
+    inv = fe_mul<P>(inv, d);
+    Fe<P> lam = fe_mul<P>(fe_sub<P>(y2, y1), di);
+    Fe<P> x3 = fe_sub<P>(fe_sub<P>(fe_sqr<P>(lam), x1), x2);
+    Fe<P> y3 = fe_sub<P>(fe_mul<P>(lam, fe_sub<P>(x1, x3)), y1);
+    mb_st<P>(out + (size_t)k * 2 * P::N, x3);
+    mb_st<P>(out + (size_t)k * 2 * P::N + P::N, y3);
+    if (k < T) break;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+// kind 12 / 13: `iters` pairs per thread; *ops = additions performed
+static int microbench_affine(bool gather, int blocks, int threads, int iters, float* ms, double* ops) {
+  KzgpuCtx& cx = kz_ctx();
+  const size_t npairs = (size_t)blocks * threads * iters;
+  if (npairs >= (1ull << 31)) return kz_fail(KZGPU_EINVAL, "too many pairs");
+  const size_t table_pts = gather ? (1ull << 27) : 2 * npairs;         // 8 GiB table for the gather probe
+  uint32_t *pts = nullptr, *idx = nullptr, *pre = nullptr, *out = nullptr;
+  KZ_CUDA(cudaMalloc(&pts, table_pts * 64));
+  KZ_CUDA(cudaMalloc(&pre, npairs * 32));
+  KZ_CUDA(cudaMalloc(&out, npairs * 64));
+  mb_fill_kernel<<<(unsigned)kz_div_up(table_pts * 16, 256), 256, 0, cx.stream>>>(pts, table_pts * 16, 99u);
+  if (gather) {
+    KZ_CUDA(cudaMalloc(&idx, 2 * npairs * 4));
+    mb_index_kernel<<<(unsigned)kz_div_up(2 * npairs, 256), 256, 0, cx.stream>>>(idx, 2 * npairs, (uint32_t)(table_pts - 1), 7u);
+  }
+  for (int rep = 0; rep < 2; rep++) {
+    KZ_CUDA(cudaEventRecord(cx.ev0, cx.stream));
+    if (gather) mb_affine_pairs_kernel<FpBN254, true><<<blocks, threads, 0, cx.stream>>>(pts, idx, (uint32_t)npairs, pre, out);
+    else mb_affine_pairs_kernel<FpBN254, false><<<blocks, threads, 0, cx.stream>>>(pts, idx, (uint32_t)npairs, pre, out);
+    KZ_LAUNCHED();
+    KZ_CUDA(cudaEventRecord(cx.ev1, cx.stream));
+    KZ_CUDA(cudaEventSynchronize(cx.ev1));
+    KZ_CUDA(cudaEventElapsedTime(ms, cx.ev0, cx.ev1));
+  }
+  if (ops) *ops = (double)npairs;
+  cudaFree(pts); cudaFree(idx); cudaFree(pre); cudaFree(out);
+  return 0;
+}
+
 int kzgpu_microbench(int kind, int blocks, int threads, int iters, float* ms, double* ops) {
   KZ_REQUIRE_INIT();
+  if (kind == 12 || kind == 13) {
+    if (blocks <= 0 || threads <= 0 || threads > 128 || iters <= 0 || !ms) return kz_fail(KZGPU_EINVAL, "bad argument");
+    return microbench_affine(kind == 13, blocks, threads, iters, ms, ops);
+  }
   if (blocks <= 0 || threads <= 0 || threads > 1024 || iters <= 0 || !ms) return kz_fail(KZGPU_EINVAL, "bad argument");
   KzgpuCtx& cx = kz_ctx();
   uint32_t* sink = nullptr;
