@@ -299,7 +299,9 @@ class Indexer:
             "vanishing_poly": ("X^n - 1", n),
             "coset": {"n4": n4, "w4": w4, "shift": shift, "evals": coset, "L1": l1, "X": xs, "zh_inv": zh_inv, "mont": rm},
         }
-        ivk = {"rk": None, "commitments": commitments, "subgroups": sub, "tau": tau}
+        # rk = tau * G2 needs G2 arithmetic, which stays with py_ecc as in the reference (kzg.py:75); None without it
+        rk = kzg.multiply(kzg.G2, tau) if (kzg.have_py_ecc and tau is not None) else None
+        ivk = {"rk": rk, "commitments": commitments, "subgroups": sub, "tau": tau}
         return ipk, ivk
 
 
@@ -484,3 +486,53 @@ class Prover:
                             "s_sigma1": evaluations[3], "s_sigma2": evaluations[4], "z_omega": evaluations[5]},
             "kzg_proofs": {"W_z": W_z, "W_zw": W_zw},
         }
+
+
+class Verifier:
+    """plonk/verifier.py:8-205 with the reference's interface (`verify(ivk, x, proof)`).  The transcript replay and
+    the scalar arithmetic run on the host; the linearisation commitment and the two sides of the batched opening
+    check are G1 combinations on the device (`KZG.batch_check` -> `kzgpu_g1_lincomb`); the final two pairings are
+    py_ecc's, exactly as in the reference (kzg.py:283-286), so `verify` raises ImportError at that point when py_ecc
+    is not installed."""
+
+    def __init__(self, curve_type="bn254"):
+        self.kzg = KZG(curve_type=curve_type)
+
+    def verify(self, ivk, x, proof):
+        kzg = self.kzg
+        r, Fq = kzg.curve_order, kzg.Fq
+        C = ivk["commitments"]
+        sub = ivk["subgroups"]
+        n, g, k1, k2 = sub["n"], int(sub["g"]), int(sub["k1"]), int(sub["k2"])
+        pc, ev = proof["commitments"], proof["evaluations"]
+        a, b, c = (int(ev[k]) % r for k in ("a", "b", "c"))
+        s1, s2, zw = (int(ev[k]) % r for k in ("s_sigma1", "s_sigma2", "z_omega"))
+        t = Transcript("plonk-proof", Fq)                                           # plonk/verifier.py:91-110
+        t.append_message("public-inputs", x)
+        t.append_message("round1-commitments", [pc["a"], pc["b"], pc["c"]])
+        beta, gamma = int(t.get_challenge("beta")), int(t.get_challenge("gamma"))
+        t.append_message("round2-commitment", pc["z"])
+        alpha = int(t.get_challenge("alpha"))
+        t.append_message("round3-commitments", [pc["t_lo"], pc["t_mid"], pc["t_hi"]])
+        zeta = int(t.get_challenge("zeta"))
+        t.append_message("round4-evaluations", [ev["a"], ev["b"], ev["c"], ev["s_sigma1"], ev["s_sigma2"], ev["z_omega"]])
+        v = t.get_challenge("v")
+        u = t.get_challenge("u")
+        zn = pow(zeta, n, r)
+        zh = (zn - 1) % r
+        l1 = zh * pow(n * (zeta - 1) % r, -1, r) % r
+        pi = 0                                                                      # PI(zeta), plonk/encoder.py:196-223
+        for i, xi in enumerate(x):
+            gi = pow(g, i, r)
+            pi = (pi - int(xi) * gi % r * zh % r * pow(n * (zeta - gi) % r, -1, r)) % r
+        # r(X) commitment (plonk/verifier.py:117-157): every term is scalar * point -> one device combination
+        f1 = alpha * (a + beta * zeta + gamma) % r * (b + beta * k1 * zeta + gamma) % r * (c + beta * k2 * zeta + gamma) % r
+        f2 = alpha * (a + beta * s1 + gamma) % r * (b + beta * s2 + gamma) % r * zw % r
+        al2l1 = alpha * alpha % r * l1 % r
+        r_comm = kzg.g1_lincomb(
+            [C["qM"], C["qL"], C["qR"], C["qO"], C["qC"], kzg.G1, pc["z"], C["S_sigma3"], pc["t_lo"], pc["t_mid"], pc["t_hi"]],
+            [a * b, a, b, c, 1, pi - f2 * (c + gamma) - al2l1, f1 + al2l1, -f2 * beta, -zh, -zh * zn, -zh * zn % r * zn])
+        return kzg.batch_check(ivk["rk"],
+                               [[r_comm, pc["a"], pc["b"], pc["c"], C["S_sigma1"], C["S_sigma2"]], [pc["z"]]],
+                               [zeta, zeta * g % r], [[0, a, b, c, s1, s2], [zw]],
+                               [proof["kzg_proofs"]["W_z"], proof["kzg_proofs"]["W_zw"]], [v, v], u)

@@ -269,3 +269,30 @@ def test_marlin_loops_match_the_reference_functions():
         exp.append(acc % R)
     from oracle.fft_ff import ifft_ff_int
     assert f2b == ifft_ff_int(exp, g_K, R)
+
+
+def test_product_verifier_with_the_oracle_pairing_in_py_eccs_role():
+    """kzg_snark_b200.plonk.Verifier (plonk/verifier.py's interface; G1 combinations on the device) accepts the
+    device prover's proof and rejects tampered ones; the two pairings -- py_ecc's in the reference, absent here --
+    come from the oracle's stand-in, the role py_ecc plays for the drop-in."""
+    from kzg_snark_b200.plonk import Indexer, Prover, Verifier
+    from kzg_snark_b200.plonk_synth import synthetic_circuit
+    from oracle import pyecc_standin as E
+    n, n_pub = 1 << 9, 4
+    qM, qL, qR, qO, qC, perm, w = synthetic_circuit(n, n_pub, R, seed=9)
+    idx = Indexer("bn254")
+    ipk, ivk = idx.preprocess(qM, qL, qR, qO, qC, perm, max_degree=n + 5, rng=random.Random(31))
+    x = [idx.kzg.Fq(v) for v in w[:n_pub]]
+    proof = Prover("bn254").prove(ipk, x, w[n_pub:])
+    ver = Verifier("bn254")
+    if ver.kzg.have_py_ecc:
+        pytest.skip("py_ecc present: the verifier already uses it")
+    ver.kzg.G2 = E.G2
+    ver.kzg.pairing = lambda Q, P: E.pairing(Q, tuple(E.FQ(int(c)) for c in P))
+    ivk = {**ivk, "rk": E.multiply(E.G2, ivk["tau"])}
+    assert ver.verify(ivk, x, proof)
+    bad = {**proof, "evaluations": {**proof["evaluations"], "b": proof["evaluations"]["b"] + 1}}
+    assert not ver.verify(ivk, x, bad)
+    assert not ver.verify(ivk, [x[0] + 1] + x[1:], proof)
+    swapped = {**proof, "kzg_proofs": {"W_z": proof["kzg_proofs"]["W_zw"], "W_zw": proof["kzg_proofs"]["W_z"]}}
+    assert not ver.verify(ivk, x, swapped)
