@@ -12,10 +12,13 @@ yields at marlin/prover.py:439-449) as (3m, 4) limb arrays, matrices A, B, C bac
 No CPU path: everything goes through libkzgpu.so.
 """
 
+import random
+
 import numpy as np
 
 from . import _ffi, device
 from ._ffi import check, ptr
+from .kzg import KZG
 from .limbs import ints_to_limbs
 from .plonk import DVec, _Field
 
@@ -62,3 +65,82 @@ def compute_t_polynomial(curve, row_index, col, val, eta, alpha, n, g_H):
     for v in (d_col, d_val, H, out):
         v.free()
     return res
+
+
+def _entries(M):
+    """(nrows, ncols, [(i, j, value)]) of a matrix given as a dense list of rows, as {"shape": (r, c), "entries":
+    [(i, j, v), ...]}, or as an object with Sage's nrows() / ncols() / nonzero_positions() / [i, j]."""
+    if isinstance(M, dict):
+        return M["shape"][0], M["shape"][1], [(int(i), int(j), int(v)) for i, j, v in M["entries"] if int(v)]
+    if hasattr(M, "nonzero_positions"):
+        return M.nrows(), M.ncols(), [(i, j, int(M[i, j])) for i, j in M.nonzero_positions()]
+    rows = [list(r) for r in M]
+    return len(rows), (len(rows[0]) if rows else 0), [(i, j, int(v)) for i, r in enumerate(rows) for j, v in enumerate(r) if int(v)]
+
+
+class Indexer:
+    """marlin/indexer.py:8-112 with the polynomial work on the device: the R1CS matrices are encoded as the row / col /
+    val polynomials over K of their "star" forms (marlin/indexer.py:47-54, marlin/encoder.py:98-125), all nine are
+    committed in ONE batched MSM pass (marlin/indexer.py:69), and the K-domain evaluations plus row indices stay resident
+    for the prover's evaluation loops (`compute_t_polynomial`, `compute_f2_polynomial`)."""
+
+    def __init__(self, curve_type="bn254"):
+        self.kzg = KZG(curve_type=curve_type)
+
+    def preprocess(self, A, B, C, max_degree, *, tau=None, ck=None, rng=None):
+        kzg = self.kzg
+        cid, r = kzg._cid, kzg.curve_order
+        f = _Field(cid)
+        mats = {"A": _entries(A), "B": _entries(B), "C": _entries(C)}
+        pow2 = lambda v: 1 << max(v - 1, 0).bit_length()                       # noqa: E731  (encoder.find_subgroup_size)
+        n = pow2(max(mats["A"][0], mats["A"][1]))                               # marlin/encoder.py:37
+        m = pow2(max(len(e[2]) for e in mats.values()))                         # :38-44
+        assert max_degree + 1 >= m, "the SRS must cover the index polynomials (degree m - 1)"
+        g_H, g_K = f.root(n), f.root(m)
+        if ck is None:
+            tau = (rng or random.SystemRandom()).randrange(1, r) if tau is None else int(tau) % r
+            srs = device.Srs.generate(cid, tau, max_degree + 1)
+        elif isinstance(ck, device.Srs):
+            srs = ck
+        else:
+            srs = device.Srs.from_affine(cid, kzg._codec.points_to_limbs(ck))
+        Hs = [1] * n
+        for i in range(1, n):
+            Hs[i] = Hs[i - 1] * g_H % r
+        ninv = pow(n, -1, r)
+        # star matrix M* = M^T with column c scaled by u_H(h_c, h_c) = n / h_c; entry (r_, c_) of M* encodes
+        # row = h_r, col = h_c, val = M*[r_, c_] / (u_H(h_r, h_r) u_H(h_c, h_c)) = M[c_, r_] * h_r / n, in row-major order
+        evals, row_index = {}, {}
+        for name, (_, _, ent) in mats.items():
+            star = sorted((j, i, v) for i, j, v in ent)                         # (row of M*, column of M*, M[c_, r_])
+            row = [Hs[rr] for rr, _, _ in star] + [0] * (m - len(star))
+            col = [Hs[cc] for _, cc, _ in star] + [0] * (m - len(star))
+            val = [v % r * Hs[rr] % r * ninv % r for rr, _, v in star] + [0] * (m - len(star))
+            evals[name] = (row, col, val)
+            row_index[name] = [rr for rr, _, _ in star] + [-1] * (m - len(star))
+        names = [f"{kind}_{M}" for M in "ABC" for kind in ("row", "col", "val")]  # commit order of marlin/indexer.py:63-69
+        coeff = DVec(9 * m)
+        flat = [v for M in "ABC" for k in range(3) for v in evals[M][k]]
+        coeff.write(0, flat, r)
+        check(f.lib.kzgpu_ntt_batch_dev(cid, coeff.ptr, m, 9, ptr(f.L(g_K)), 1, None))      # 9 interpolations over K
+        outs, infs = device.msm_batch_dev(srs, coeff, m, 9)
+        commitments = {nm: kzg._codec.from_device(o, i) for nm, o, i in zip(names, outs, infs)}
+        # resident K-domain evaluations, kind-major (row_A row_B row_C | col ... | val ...) as the loop kernels take them
+        kd = {kind: DVec.from_limbs(ints_to_limbs([v for M in "ABC" for v in evals[M][k]], r))
+              for k, kind in enumerate(("row", "col", "val"))}
+        ridx = np.ascontiguousarray(np.array([i for M in "ABC" for i in row_index[M]], dtype=np.int64).astype(np.uint32))
+        sub = {"n": n, "m": m, "g_H": kzg.Fq(g_H), "g_K": kzg.Fq(g_K)}
+        ipk = {"ck": srs, "A": A, "B": B, "C": C, "commitments": commitments, "subgroups": sub,
+               "polynomials": {"buffer": coeff, "names": names, "length": m},
+               "evals": kd, "row_index": _ffi.DeviceBuffer(ridx.nbytes).upload(ridx),
+               "vanishing_polys": {"v_H": ("X^n - 1", n), "v_K": ("X^m - 1", m)}}
+        rk = kzg.multiply(kzg.G2, tau) if (kzg.have_py_ecc and tau is not None) else None
+        ivk = {"rk": rk, "commitments": commitments, "subgroups": {"n": n, "m": m, "g_H": kzg.Fq(g_H)},
+               "vanishing_polys": ipk["vanishing_polys"], "tau": tau}
+        return ipk, ivk
+
+    @staticmethod
+    def polynomial(ipk, name):
+        """Coefficients (ints, low -> high, length m) of one index polynomial."""
+        p = ipk["polynomials"]
+        return p["buffer"].read_ints(p["names"].index(name) * p["length"], p["length"])

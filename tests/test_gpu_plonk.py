@@ -296,3 +296,34 @@ def test_product_verifier_with_the_oracle_pairing_in_py_eccs_role():
     assert not ver.verify(ivk, [x[0] + 1] + x[1:], proof)
     swapped = {**proof, "kzg_proofs": {"W_z": proof["kzg_proofs"]["W_zw"], "W_zw": proof["kzg_proofs"]["W_z"]}}
     assert not ver.verify(ivk, x, swapped)
+
+
+def test_marlin_indexer_matches_the_reference_indexer():
+    """marlin/indexer.py:Indexer.preprocess on the bundled R1CS instance: the nine index polynomials and their
+    commitments (ONE batched MSM pass here) against what the reference's indexer computed (the indexer's commit
+    record in tests/golden/ref_trace_marlin.json); then the two prover loops on the indexer's resident data."""
+    from kzg_snark_b200 import marlin
+    tr = load("ref_trace_marlin.json")
+    inst = json.load(open(os.path.join(GOLD, "r1cs_instance.json")))
+    A, B, C = ([[H(v) for v in row] for row in inst[k]] for k in "ABC")
+    rec = tr["calls"][tr["notes"]["index_calls"] - 1]
+    assert rec["fn"] == "commit" and len(rec["polys"]) == 9
+    idx = marlin.Indexer("bn254")
+    fq = idx.kzg._codec.fq
+    ck = [(fq(H(p[0])), fq(H(p[1])), fq(1)) for p in tr["keys"][rec["ck_id"]]]
+    ipk, ivk = idx.preprocess(A, B, C, max_degree=200, ck=ck)
+    names = ipk["polynomials"]["names"]
+    for nm, exp_poly, exp_pt in zip(names, rec["polys"], rec["out"]):
+        got = marlin.Indexer.polynomial(ipk, nm)
+        while got and got[-1] == 0:
+            got.pop()
+        assert got == [H(c) for c in exp_poly], nm
+        assert aff(ipk["commitments"][nm]) == (H(exp_pt[0]), H(exp_pt[1])), nm
+    # a sparse description of the same matrices gives the same index
+    sp = lambda M: {"shape": (len(M), len(M[0])), "entries": [(i, j, v) for i, r_ in enumerate(M) for j, v in enumerate(r_) if v]}   # noqa: E731
+    ipk2, _ = idx.preprocess(sp(A), sp(B), sp(C), max_degree=200, ck=ck)
+    assert {k: aff(v) for k, v in ipk2["commitments"].items()} == {k: aff(v) for k, v in ipk["commitments"].items()}
+    # the loop fixtures were produced on the same index: its resident evaluations reproduce them
+    d = load("ref_marlin_loops.json")
+    for kind in ("row", "col", "val"):
+        assert ipk["evals"][kind].read_ints() == [H(v) for M in "ABC" for v in d["evals"][f"{kind}_{M}"]]
