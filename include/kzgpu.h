@@ -192,6 +192,15 @@ int kzgpu_plonk_permutation_dev(int field, size_t n, const uint64_t* d_a, const 
 int kzgpu_plonk_quotient_dev(int field, size_t n4, const uint64_t* const* d_evals, const uint64_t* params,
                              int mont_in, uint64_t* d_t);
 
+/* d_out[i] = d_a[i] * d_b[i]: the point-wise step of NTT-based polynomial products (the Sage `*` of marlin/prover.py:96,
+ * 131) */
+int kzgpu_poly_mul_pointwise_dev(int field, uint64_t* d_out, const uint64_t* d_a, const uint64_t* d_b, size_t n);
+/* Marlin third round on the coset {s w_8m^i} (marlin/prover.py:166-171, 303-353): d_row / d_col / d_val hold the
+ * coset evaluations of row_M, col_M, val_M for M = A, B, C back to back (3 * m8 each), d_f2 those of f_2;
+ * params = eta_A, eta_B, eta_C, alpha, beta_1, v_H(beta_1) v_H(alpha), 1 / v_K(x_0..7) (14 elements).
+ * d_out[i] = (a - b f_2)(x_i) / v_K(x_i) with a, b as in _compute_a_b_polynomials; its inverse coset NTT is h_2. */
+int kzgpu_marlin_h2_evals_dev(int field, size_t m8, const uint64_t* d_row, const uint64_t* d_col, const uint64_t* d_val,
+                              const uint64_t* d_f2, const uint64_t* params, uint64_t* d_out);
 /* Marlin prover evaluation loops.  d_row / d_col / d_val: the K-domain evaluations of the index
  * polynomials row_M, col_M, val_M for M = A, B, C back to back (3 * m elements each; marlin/encoder.py:98-125).
  * f2 evaluations (marlin/prover.py:404-466):  d_out[kappa] = scale * sum_M eta_M val_M(kappa) /

@@ -283,6 +283,53 @@ __global__ void marlin_t_rows_kernel(size_t n, size_t m, const uint32_t* row_ind
   st_fe<P>(out + i * P::N, fe_mul<P>(fe_mul<P>(s, scale), hinv));
 }
 
+// out[i] = a[i] * b[i] (canonical in, canonical out): the point-wise step of an NTT-based polynomial product
+template <class P>
+__global__ void pointwise_mul_kernel(size_t n, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  st_fe<P>(out + i * P::N, fe_mul<P>(ld_fe<P>(a + i * P::N), ld_mont<P>(b + i * P::N)));
+}
+
+// Marlin third round (marlin/prover.py:166-171, 303-353): on the coset {s w_8m^i} form
+//   b = prod_M (beta1 - row_M)(alpha - col_M),  a = sum_M eta_M vv val_M prod_{O != M} (beta1 - row_O)(alpha - col_O),
+//   out = (a - b f_2) / v_K   (v_K takes 8 values on the coset),  whose inverse coset NTT is h_2.
+template <class P> struct H2Params { Fe<P> eta[3], alpha, beta1, vv, vk_inv[8]; };
+template <class P>
+__global__ void marlin_h2_kernel(size_t m8, const uint32_t* row, const uint32_t* col, const uint32_t* val, const uint32_t* f2,
+                                 H2Params<P> pp, uint32_t* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m8) return;
+  Fe<P> fac[3], v[3];
+#pragma unroll
+  for (int M = 0; M < 3; M++) {
+    fac[M] = fe_mul<P>(fe_sub<P>(pp.beta1, ld_mont<P>(row + ((size_t)M * m8 + i) * P::N)),
+                       fe_sub<P>(pp.alpha, ld_mont<P>(col + ((size_t)M * m8 + i) * P::N)));
+    v[M] = fe_mul<P>(fe_mul<P>(ld_mont<P>(val + ((size_t)M * m8 + i) * P::N), pp.eta[M]), pp.vv);
+  }
+  Fe<P> a = fe_add<P>(fe_add<P>(fe_mul<P>(v[0], fe_mul<P>(fac[1], fac[2])), fe_mul<P>(v[1], fe_mul<P>(fac[0], fac[2]))),
+                      fe_mul<P>(v[2], fe_mul<P>(fac[0], fac[1])));
+  Fe<P> b = fe_mul<P>(fe_mul<P>(fac[0], fac[1]), fac[2]);
+  Fe<P> t = fe_mul<P>(fe_sub<P>(a, fe_mul<P>(b, ld_mont<P>(f2 + i * P::N))), pp.vk_inv[i & 7]);
+  st_fe<P>(out + i * P::N, fe_from_mont<P>(t));
+}
+
+template <class P>
+int h2_impl(size_t m8, const uint32_t* row, const uint32_t* col, const uint32_t* val, const uint32_t* f2, const uint64_t* params, uint32_t* out) {
+  KzgpuCtx& cx = kz_ctx();
+  H2Params<P> pp;
+  Fe<P>* dst[14] = {&pp.eta[0], &pp.eta[1], &pp.eta[2], &pp.alpha, &pp.beta1, &pp.vv, &pp.vk_inv[0], &pp.vk_inv[1], &pp.vk_inv[2],
+                    &pp.vk_inv[3], &pp.vk_inv[4], &pp.vk_inv[5], &pp.vk_inv[6], &pp.vk_inv[7]};
+  for (int i = 0; i < 14; i++) {
+    Fe<P> v = kz_fe_from_u64<P>(params + 4 * i);
+    if (!kz_fe_reduced<P>(v)) return kz_fail(KZGPU_ERANGE, "h_2 parameter %d is not a canonical field element", i);
+    *dst[i] = fe_to_mont<P>(v);
+  }
+  marlin_h2_kernel<P><<<(unsigned)kz_div_up(m8, 128), 128, 0, cx.stream>>>(m8, row, col, val, f2, pp, out);
+  KZ_LAUNCHED();
+  return 0;
+}
+
 template <class P>
 int marlin_impl(bool is_t, size_t n, size_t m, const uint32_t* d_row_or_index, const uint32_t* d_col, const uint32_t* d_val,
                 const uint32_t* d_H, const uint64_t* eta, const uint64_t* alpha, const uint64_t* beta1, const uint64_t* scale,
@@ -343,6 +390,32 @@ int kzgpu_plonk_quotient_dev(int field, size_t n4, const uint64_t* const* d_eval
   if (n4 < 8 || (n4 & (n4 - 1))) return kz_fail(KZGPU_EINVAL, "the coset size must be a power of two >= 8");
   if (field == KZGPU_BN254) return quotient_impl<FrBN254>(n4, d_evals, params, mont_in, (uint32_t*)d_t);
   if (field == KZGPU_BLS12_381) return quotient_impl<FrBLS381>(n4, d_evals, params, mont_in, (uint32_t*)d_t);
+  return kz_fail(KZGPU_EINVAL, "unknown field id %d", field);
+}
+
+int kzgpu_poly_mul_pointwise_dev(int field, uint64_t* d_out, const uint64_t* d_a, const uint64_t* d_b, size_t n) {
+  KZ_REQUIRE_INIT();
+  if (n && (!d_out || !d_a || !d_b)) return kz_fail(KZGPU_EINVAL, "null pointer");
+  if (!n) return 0;
+  KzgpuCtx& cx = kz_ctx();
+  if (field == KZGPU_BN254)
+    pointwise_mul_kernel<FrBN254><<<(unsigned)kz_div_up(n, 128), 128, 0, cx.stream>>>(n, (const uint32_t*)d_a, (const uint32_t*)d_b, (uint32_t*)d_out);
+  else if (field == KZGPU_BLS12_381)
+    pointwise_mul_kernel<FrBLS381><<<(unsigned)kz_div_up(n, 128), 128, 0, cx.stream>>>(n, (const uint32_t*)d_a, (const uint32_t*)d_b, (uint32_t*)d_out);
+  else return kz_fail(KZGPU_EINVAL, "unknown field id %d", field);
+  KZ_LAUNCHED();
+  return 0;
+}
+
+int kzgpu_marlin_h2_evals_dev(int field, size_t m8, const uint64_t* d_row, const uint64_t* d_col, const uint64_t* d_val,
+                              const uint64_t* d_f2, const uint64_t* params, uint64_t* d_out) {
+  KZ_REQUIRE_INIT();
+  if (!d_row || !d_col || !d_val || !d_f2 || !params || !d_out) return kz_fail(KZGPU_EINVAL, "null pointer");
+  if (m8 < 8 || (m8 & (m8 - 1))) return kz_fail(KZGPU_EINVAL, "the coset size must be a power of two >= 8");
+  if (field == KZGPU_BN254)
+    return h2_impl<FrBN254>(m8, (const uint32_t*)d_row, (const uint32_t*)d_col, (const uint32_t*)d_val, (const uint32_t*)d_f2, params, (uint32_t*)d_out);
+  if (field == KZGPU_BLS12_381)
+    return h2_impl<FrBLS381>(m8, (const uint32_t*)d_row, (const uint32_t*)d_col, (const uint32_t*)d_val, (const uint32_t*)d_f2, params, (uint32_t*)d_out);
   return kz_fail(KZGPU_EINVAL, "unknown field id %d", field);
 }
 

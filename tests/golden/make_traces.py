@@ -216,6 +216,58 @@ def marlin_loops():
             "t": rr.enc_poly(t), "f2": rr.enc_poly(f2)})
 
 
+def trace_marlin_normalized():
+    """Reference Marlin indexer + prover + verifier with commitments normalised to (x, y, 1) before the transcript (what a
+    canonical-affine drop-in returns): random draws, the polynomials of every commit / open call and the proof -- the
+    fixture for a device Marlin prover."""
+    from oracle import pyecc_standin as E
+    with refrun.ReferenceRun(seed=SEED + 6) as rr:
+        KZG = rr.kzg.KZG
+
+        def norm(pt):
+            if E.is_inf(pt):
+                return E.Z1
+            x, y = E.normalize(pt)
+            return (E.FQ(x.n), E.FQ(y.n), E.FQ(1))
+
+        traced_commit, traced_open = KZG.commit, KZG.open
+        KZG.commit = lambda s, ck, polys: [norm(c) for c in traced_commit(s, ck, polys)]
+        KZG.open = lambda s, ck, polys, z, xi: norm(traced_open(s, ck, polys, z, xi))
+        draws = []
+        orig_rand = sageshim.GFShim.random_element
+
+        def rand(self):
+            v = orig_rand(self)
+            draws.append(hex(int(v)))
+            return v
+
+        sageshim.GFShim.random_element = rand
+        try:
+            Fq = KZG("bn254").Fq
+            inst = fixtures.load_r1cs_instance(os.path.join(REF_CS, "R1CS_INSTANCE.pkl"))
+            A, B, C = (sageshim.matrix(Fq, inst[k]) for k in "ABC")
+            z = [Fq(v) for v in inst["z"]]
+            x, w = z[:5], z[5:]
+            ipk, ivk = rr.load("marlin.indexer").Indexer(curve_type="bn254").preprocess(A, B, C, max_degree=200)
+            n_index_draws, n_index_calls = len(draws), len(rr.trace)
+            proof = rr.load("marlin.prover").Prover(curve_type="bn254").prove(ipk, x, w)
+            n_prove_draws = len(draws)
+            ok = rr.load("marlin.verifier").Verifier(curve_type="bn254").verify(ivk, x, proof)
+        finally:
+            sageshim.GFShim.random_element = orig_rand
+        assert ok
+        pr = {"commitments": {k: [rr.enc_point(c) for c in v] for k, v in proof["commitments"].items()},
+              "evaluations": {k: [rr.enc_scalar(e) for e in v] for k, v in proof["evaluations"].items()},
+              "kzg_proofs": {k: rr.enc_point(v) for k, v in proof["kzg_proofs"].items()}}
+        dump("ref_marlin_normalized.json", {
+            "source": "reference marlin indexer + prover with commitments normalised to (x,y,1) before the transcript",
+            "seed": SEED + 6, "curve": "bn254", "index_draws": draws[:n_index_draws],
+            "prover_draws": draws[n_index_draws:n_prove_draws], "keys": rr.keys,
+            "x": [rr.enc_scalar(v) for v in x], "w": [rr.enc_scalar(v) for v in w],
+            "prover_calls": [{k: v for k, v in c.items() if k != "out" or c["fn"] != "x"} for c in rr.trace[n_index_calls:]],
+            "proof": pr, "notes": {"verify": bool(ok)}})
+
+
 def trace_plonk_normalized():
     """Reference prover + indexer with KZG.commit / KZG.open outputs normalised to (x, y, 1): the
     transcript then hashes what a canonical-affine drop-in returns, so kzg_snark_b200.plonk can be
@@ -276,4 +328,5 @@ if __name__ == "__main__":
     trace_plonk()
     trace_marlin()
     marlin_loops()
+    trace_marlin_normalized()
     trace_plonk_normalized()

@@ -327,3 +327,38 @@ def test_marlin_indexer_matches_the_reference_indexer():
     d = load("ref_marlin_loops.json")
     for kind in ("row", "col", "val"):
         assert ipk["evals"][kind].read_ints() == [H(v) for M in "ABC" for v in d["evals"][f"{kind}_{M}"]]
+
+
+def test_marlin_prover_matches_the_reference_prover_bit_for_bit():
+    """marlin/prover.py on the bundled R1CS instance (configs[4]), run by the reference itself with commitments normalised
+    to (x, y, 1) before the transcript (tests/golden/ref_marlin_normalized.json): the device prover, fed the same SRS and
+    the same 41 random draws, must produce the same polynomials in every round and the same proof."""
+    from kzg_snark_b200 import marlin
+    d = load("ref_marlin_normalized.json")
+    inst = json.load(open(os.path.join(GOLD, "r1cs_instance.json")))
+    A, B, C = ([[H(v) for v in row] for row in inst[k]] for k in "ABC")
+    idx = marlin.Indexer("bn254")
+    ipk, _ = idx.preprocess(A, B, C, max_degree=200, tau=H(d["index_draws"][0]))
+    Fq = idx.kzg.Fq
+    prover = marlin.Prover("bn254")
+    prover.capture = True
+    proof = prover.prove(ipk, [Fq(H(v)) for v in d["x"]], [H(v) for v in d["w"]], draws=[H(v) for v in d["prover_draws"]])
+    calls = [c for c in d["prover_calls"] if c["fn"] in ("commit", "open")]
+    expected = dict(zip(["w_masked", "zA", "zB", "zC", "h_0", "s"], calls[0]["polys"]))
+    expected.update(zip(["t", "g_1", "h_1"], calls[1]["polys"]))
+    expected.update(zip(["g_2", "h_2"], calls[2]["polys"]))
+    expected.update(zip(["f_1", "f_2"], calls[3]["polys"][:2]))
+    expected["f_3"] = calls[4]["polys"][0]
+    for nm, exp in expected.items():
+        got = list(prover.captured[nm])
+        while got and got[-1] == 0:
+            got.pop()
+        assert got == [H(c) for c in exp], nm
+    assert set(prover.checks.values()) == {0}
+    exp = d["proof"]
+    for rnd, pts in exp["commitments"].items():
+        assert [aff(p) for p in proof["commitments"][rnd]] == [(H(p[0]), H(p[1])) for p in pts], rnd
+    for k, vals in exp["evaluations"].items():
+        assert [int(v) for v in proof["evaluations"][k]] == [H(v) for v in vals], k
+    for k, p in exp["kzg_proofs"].items():
+        assert aff(proof["kzg_proofs"][k]) == (H(p[0]), H(p[1])), k
