@@ -195,6 +195,10 @@ int kzgpu_plonk_quotient_dev(int field, size_t n4, const uint64_t* const* d_eval
 /* d_out[i] = d_a[i] * d_b[i]: the point-wise step of NTT-based polynomial products (the Sage `*` of marlin/prover.py:96,
  * 131) */
 int kzgpu_poly_mul_pointwise_dev(int field, uint64_t* d_out, const uint64_t* d_a, const uint64_t* d_b, size_t n);
+/* d_out = M d_z for a CSR matrix over the scalar field (row_ptr: n_rows + 1 offsets, col: column indices, d_val: values),
+ * the z_A = A z, z_B = B z, z_C = C z of marlin/encoder.py:205-207 */
+int kzgpu_spmv_dev(int field, size_t n_rows, const uint32_t* d_row_ptr, const uint32_t* d_col, const uint64_t* d_val,
+                   const uint64_t* d_z, uint64_t* d_out);
 /* Marlin third round on the coset {s w_8m^i} (marlin/prover.py:166-171, 303-353): d_row / d_col / d_val hold the
  * coset evaluations of row_M, col_M, val_M for M = A, B, C back to back (3 * m8 each), d_f2 those of f_2;
  * params = eta_A, eta_B, eta_C, alpha, beta_1, v_H(beta_1) v_H(alpha), 1 / v_K(x_0..7) (14 elements).

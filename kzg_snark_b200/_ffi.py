@@ -81,6 +81,7 @@ SIGNATURES = {
     "kzgpu_plonk_permutation_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t] + [ctypes.c_void_p] * 10 + [_intp]),
     "kzgpu_plonk_quotient_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "kzgpu_poly_mul_pointwise_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "kzgpu_spmv_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t] + [ctypes.c_void_p] * 5),
     "kzgpu_marlin_h2_evals_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t] + [ctypes.c_void_p] * 6),
     "kzgpu_marlin_f2_evals_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t] + [ctypes.c_void_p] * 8),
     "kzgpu_marlin_t_evals_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t] + [ctypes.c_void_p] * 8),

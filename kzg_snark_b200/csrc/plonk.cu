@@ -291,6 +291,18 @@ __global__ void pointwise_mul_kernel(size_t n, const uint32_t* a, const uint32_t
   st_fe<P>(out + i * P::N, fe_mul<P>(ld_fe<P>(a + i * P::N), ld_mont<P>(b + i * P::N)));
 }
 
+// out[i] = sum_k val[k] * z[col[k]] over row i of a CSR matrix (z_M = M z, marlin/encoder.py:205-207): one thread per row
+template <class P>
+__global__ void spmv_kernel(size_t n_rows, const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col,
+                            const uint32_t* __restrict__ val, const uint32_t* __restrict__ z, uint32_t* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  Fe<P> acc = fe_zero<P>();
+  for (uint32_t k = row_ptr[i]; k < row_ptr[i + 1]; k++)
+    acc = fe_add<P>(acc, fe_mul<P>(ld_fe<P>(val + (size_t)k * P::N), ld_mont<P>(z + (size_t)col[k] * P::N)));
+  st_fe<P>(out + i * P::N, acc);
+}
+
 // Marlin third round (marlin/prover.py:166-171, 303-353): on the coset {s w_8m^i} form
 //   b = prod_M (beta1 - row_M)(alpha - col_M),  a = sum_M eta_M vv val_M prod_{O != M} (beta1 - row_O)(alpha - col_O),
 //   out = (a - b f_2) / v_K   (v_K takes 8 values on the coset),  whose inverse coset NTT is h_2.
@@ -402,6 +414,21 @@ int kzgpu_poly_mul_pointwise_dev(int field, uint64_t* d_out, const uint64_t* d_a
     pointwise_mul_kernel<FrBN254><<<(unsigned)kz_div_up(n, 128), 128, 0, cx.stream>>>(n, (const uint32_t*)d_a, (const uint32_t*)d_b, (uint32_t*)d_out);
   else if (field == KZGPU_BLS12_381)
     pointwise_mul_kernel<FrBLS381><<<(unsigned)kz_div_up(n, 128), 128, 0, cx.stream>>>(n, (const uint32_t*)d_a, (const uint32_t*)d_b, (uint32_t*)d_out);
+  else return kz_fail(KZGPU_EINVAL, "unknown field id %d", field);
+  KZ_LAUNCHED();
+  return 0;
+}
+
+int kzgpu_spmv_dev(int field, size_t n_rows, const uint32_t* d_row_ptr, const uint32_t* d_col, const uint64_t* d_val,
+                   const uint64_t* d_z, uint64_t* d_out) {
+  KZ_REQUIRE_INIT();
+  if (n_rows && (!d_row_ptr || !d_col || !d_val || !d_z || !d_out)) return kz_fail(KZGPU_EINVAL, "null pointer");
+  if (!n_rows) return 0;
+  KzgpuCtx& cx = kz_ctx();
+  if (field == KZGPU_BN254)
+    spmv_kernel<FrBN254><<<(unsigned)kz_div_up(n_rows, 128), 128, 0, cx.stream>>>(n_rows, d_row_ptr, d_col, (const uint32_t*)d_val, (const uint32_t*)d_z, (uint32_t*)d_out);
+  else if (field == KZGPU_BLS12_381)
+    spmv_kernel<FrBLS381><<<(unsigned)kz_div_up(n_rows, 128), 128, 0, cx.stream>>>(n_rows, d_row_ptr, d_col, (const uint32_t*)d_val, (const uint32_t*)d_z, (uint32_t*)d_out);
   else return kz_fail(KZGPU_EINVAL, "unknown field id %d", field);
   KZ_LAUNCHED();
   return 0;

@@ -14,13 +14,14 @@ No CPU path: everything goes through libkzgpu.so.
 
 import ctypes
 import random
+import time
 
 import numpy as np
 
 from . import _ffi, device
 from ._ffi import check, ptr
 from .kzg import KZG
-from .limbs import ints_to_limbs
+from .limbs import ints_to_limbs, limbs_to_ints
 from .plonk import DVec, Transcript, _Field, _View, _voidp_array
 
 
@@ -141,10 +142,21 @@ class Indexer:
         z8 = pow(w8, m, r)                                                      # primitive 8th root of unity
         vk_inv = [pow((sm * pow(z8, i, r) - 1) % r, -1, r) for i in range(8)]
         ridx = np.ascontiguousarray(np.array([i for M in "ABC" for i in row_index[M]], dtype=np.int64).astype(np.uint32))
+        # CSR copies of A, B, C for the prover's z_M = M z
+        csr = {}
+        for name, (nr, _, ent) in mats.items():
+            ent = sorted(ent)
+            rp = np.zeros(n + 1, dtype=np.uint32)
+            if ent:
+                np.add.at(rp, np.array([e[0] for e in ent], dtype=np.int64) + 1, 1)
+            rp = np.ascontiguousarray(np.cumsum(rp, dtype=np.uint64).astype(np.uint32))
+            ci = np.ascontiguousarray(np.array([e[1] for e in ent], dtype=np.uint32))
+            csr[name] = (_ffi.DeviceBuffer(rp.nbytes).upload(rp), _ffi.DeviceBuffer(max(ci.nbytes, 4)).upload(ci),
+                         DVec.from_limbs(ints_to_limbs([e[2] for e in ent], r)) if ent else DVec(1))
         sub = {"n": n, "m": m, "g_H": kzg.Fq(g_H), "g_K": kzg.Fq(g_K)}
         ipk = {"ck": srs, "A": A, "B": B, "C": C, "commitments": commitments, "subgroups": sub,
                "polynomials": {"buffer": coeff, "names": names, "length": m},
-               "evals": kd, "row_index": _ffi.DeviceBuffer(ridx.nbytes).upload(ridx), "matrices": mats,
+               "evals": kd, "row_index": _ffi.DeviceBuffer(ridx.nbytes).upload(ridx), "matrices": mats, "csr": csr,
                "coset8": {"m8": m8, "w8": w8, "shift": shift, "evals": cos, "vk_inv": vk_inv},
                "vanishing_polys": {"v_H": ("X^n - 1", n), "v_K": ("X^m - 1", m)}}
         rk = kzg.multiply(kzg.G2, tau) if (kzg.have_py_ecc and tau is not None) else None
@@ -184,11 +196,13 @@ class Prover:
         if draws is None:
             sr = random.SystemRandom()
             draws = [sr.randrange(r) for _ in range(4 * b + 2 * n + b - 1)]
-        draws = [int(d) % r for d in draws]
-        zi = [int(v) % r for v in list(x) + list(w)]
-        Hs = [1] * n
-        for i in range(1, n):
-            Hs[i] = Hs[i - 1] * g_H % r
+        # `w` and `draws` may be (k, 4) limb arrays (large instances: no per-element Python conversion)
+        d_limbs = np.ascontiguousarray(draws, dtype=np.uint64).reshape(-1, 4) if isinstance(draws, np.ndarray) else ints_to_limbs(draws, r)
+        head = limbs_to_ints(d_limbs[:4 * b])                                            # the 4b masking scalars
+        w_limbs = np.ascontiguousarray(w, dtype=np.uint64).reshape(-1, 4) if isinstance(w, np.ndarray) else ints_to_limbs(w, r)
+        xs = [int(v) % r for v in x]
+        nz = ell + w_limbs.shape[0]
+        Hs = [pow(g_H, i, r) for i in range(ell)]                                        # only the public part of H is needed here
 
         def new(length, zero=True):
             return DVec(length, zero=zero)
@@ -229,6 +243,14 @@ class Prover:
             return [kzg._codec.from_device(o, i) for o, i in zip(outs, infs)]
 
         self.captured = cap = {}
+        self.timings = tm = {}
+        clock = [time.perf_counter()]
+
+        def lap(name):
+            check(lib.kzgpu_sync())
+            now = time.perf_counter()
+            tm[name] = tm.get(name, 0.0) + now - clock[0]
+            clock[0] = now
 
         def keep(name, vec, length):                                                     # tests compare every round's polynomials
             if self.capture:
@@ -237,9 +259,9 @@ class Prover:
         transcript = Transcript("marlin-proof", Fq)
         transcript.append_message("public-inputs", x)                                    # marlin/prover.py:56
 
+        lap("setup")
         # ---- witness and linear-combination encodings (marlin/encoder.py:133-229)
         # x_poly through (h_i, x_i), i < ell, and v_H_x = prod (X - h_i): ell is the public-input size (small), host
-        xs = zi[:ell]
         vhx = [1]
         for i in range(ell):
             vhx = [(-Hs[i] * vhx[0]) % r] + [(vhx[k - 1] - Hs[i] * vhx[k]) % r for k in range(1, len(vhx))] + [vhx[-1]]
@@ -263,12 +285,14 @@ class Prover:
         xe.copy_from(x_poly, n)
         check(lib.kzgpu_ntt_dev(cid, xe.ptr, n, ptr(f.L(g_H)), 0, None))                 # x_poly on H
         zv = new(n)
-        zv.write(0, zi, r)
+        if ell:
+            zv.write(0, xs, r)
+        check(lib.kzgpu_h2d(zv.at(ell), ptr(w_limbs), w_limbs.nbytes))
         vals = new(n)
         lin(vals, n, [(zv, n, 1), (xe, n, -1)])                                          # w_i - x_poly(h_i) ...
         check(lib.kzgpu_memset(vals.ptr, 0, ell * 32))                                   # ... zero on the public part
-        if len(zi) < n:
-            check(lib.kzgpu_memset(vals.at(len(zi)), 0, (n - len(zi)) * 32))             # and on the padding (:150-154)
+        if nz < n:
+            check(lib.kzgpu_memset(vals.at(nz), 0, (n - nz) * 32))                       # and on the padding (:150-154)
         f.intt(vals, n, g_H)
         w_poly, tmp, wl = vals, new(n), n
         for i in range(ell):                                                             # w_poly = f // v_H_x (:156)
@@ -282,23 +306,23 @@ class Prover:
         for i in range(ell):
             vl = div_linear(oth, cur, vl, Hs[i])
             cur, oth = oth, cur
-        w_rand, zr = draws[0:b], [draws[b * (j + 1): b * (j + 2)] for j in range(3)]
+        w_rand, zr = head[0:b], [head[b * (j + 1): b * (j + 2)] for j in range(3)]
         w_masked, wml = new(n + b), vl + b - 1                                           # w_poly + w_random * v_H_w (:89)
         lin(w_masked, wml, [(w_poly, wl, 1)] + [(_View(cur.base, cur.off - i), vl + i, w_rand[i]) for i in range(b)])
-        # z_M = M z (host, sparse) -> interpolation -> masking with z_M_random * (X^n - 1) (:90-92)
+        lap("witness_encoding")
+        # z_M = M z (CSR product on the device) -> interpolation -> masking with z_M_random * (X^n - 1) (:90-92)
         zm = []
         for j, M in enumerate("ABC"):
-            rows = [0] * n
-            for i_, j_, v_ in ipk["matrices"][M][2]:
-                rows[i_] = (rows[i_] + v_ * zi[j_]) % r if j_ < len(zi) else rows[i_]
+            rp, ci, vv_ = ipk["csr"][M]
             p = new(n + b)
-            p.write(0, rows, r)
+            check(lib.kzgpu_spmv_dev(cid, n, rp.ptr, ci.ptr, vv_.ptr, zv.ptr, p.ptr))
             f.intt(p, n, g_H)
             lo = p.read_ints(0, b)
             p.write(0, [(lo[k] - zr[j][k]) % r for k in range(b)], r)
             p.write(n, zr[j], r)
             zm.append(p)
         zA, zB, zC = zm
+        lap("matvec_encoding")
         # z_masked = w_masked * v_H_x + x_poly (:93): v_H_x has ell + 1 coefficients -> shifted views of w_masked
         wpad = new(ell + wml)
         wpad.copy_from(w_masked, wml, ell)
@@ -310,15 +334,19 @@ class Prover:
         h_0, h0l = new(pl - n), pl - n
         lin(h_0, h0l, [(prod.at(n), pl - n, 1), (prod.at(2 * n), max(pl - 2 * n, 0), 1)])
         prod.free()
+        lap("h_0")
         # s: the draws as coefficients, constant term adjusted so that the sum over H vanishes (:100-102)
         sl = 2 * n + b - 1
-        sc_ = list(draws[4 * b: 4 * b + sl])
-        sc_[0] = (sc_[0] - sum(sc_[k] for k in range(0, sl, n))) % r
-        s_poly = new(sl)
-        s_poly.write(0, sc_, r)
+        assert d_limbs.shape[0] >= 4 * b + sl, "not enough random draws"
+        s_poly = new(sl, zero=False)
+        check(lib.kzgpu_h2d(s_poly.ptr, ptr(np.ascontiguousarray(d_limbs[4 * b: 4 * b + sl])), sl * 32))
+        fold = limbs_to_ints(d_limbs[[4 * b + k for k in range(0, sl, n)]])              # c_0, c_n, c_2n
+        s_poly.write(0, [(fold[0] - sum(fold)) % r], r)
         for nm, v_, ln in (("w_masked", w_masked, wml), ("zA", zA, n + b), ("zB", zB, n + b), ("zC", zC, n + b), ("h_0", h_0, h0l), ("s", s_poly, sl)):
             keep(nm, v_, ln)
+        lap("s_upload")
         first = commit([(w_masked, wml), (zA, n + b), (zB, n + b), (zC, n + b), (h_0, h0l), (s_poly, sl)])
+        lap("round1_msm")
         transcript.append_message("round1-commitments", first)
         eta = [int(transcript.get_challenge(k)) for k in ("eta_A", "eta_B", "eta_C")]
         alpha = int(transcript.get_challenge("alpha"))
@@ -348,7 +376,9 @@ class Prover:
         g_1 = _View(rem, 1)
         for nm, v_, ln in (("t", t_poly, n), ("g_1", g_1, n - 1), ("h_1", h_1, h1l)):
             keep(nm, v_, ln)
+        lap("sumcheck1")
         second = commit([(t_poly, n), (g_1, n - 1), (h_1, h1l)])
+        lap("round2_msm")
         transcript.append_message("round2-commitments", second)
         beta1 = int(transcript.get_challenge("beta_1"))
         while pow(beta1, n, r) == 1:
@@ -375,7 +405,9 @@ class Prover:
         h_2, h2l = f2c, 6 * m - 6                                                         # deg h_2 = 6(m-1) + (m-1) - m
         keep("g_2", g_2, m - 1)
         keep("h_2", h_2, h2l)
+        lap("sumcheck2_h2")
         third = commit([(g_2, m - 1), (h_2, h2l)])
+        lap("round3_msm")
         transcript.append_message("round3-commitments", third)
         beta2 = int(transcript.get_challenge("beta_2"))
 
@@ -426,8 +458,10 @@ class Prover:
             check(rc_)
             return kzg._codec.from_device(out, bool(inf.value))
 
+        lap("linearisations")
         proof_b1 = open_dev([(f_1, max(h0l, n + b)), (f_2p, f2l), (zA, n + b), (t_poly, n)], beta1, xi1)
         proof_b2 = open_dev([(f_3, h2l)] + [(ipoly[f"{kind}_{M}"], m) for M in "ABC" for kind in ("row", "col")], beta2, xi2)
+        lap("openings")
         self.checks = {"f_1(beta_1)": f.eval(f_1, max(h0l, n + b), beta1), "f_2(beta_1)": f.eval(f_2p, f2l, beta1),
                        "f_3(beta_2)": f.eval(f_3, h2l, beta2)}                            # the reference asserts all three are 0
         return {"commitments": {"first_round": first, "second_round": second, "third_round": third},
@@ -444,3 +478,24 @@ class Prover:
             f.powers(H, n, g_H)
             cls._h_cache[key] = H
         return cls._h_cache[key]
+
+
+def synthetic_r1cs(n_rows, n_pub, r, nnz_per_row=2, seed=0):
+    """A satisfied R1CS instance of arbitrary size in the reference's format (constraint-system/R1CS_INSTANCE.pkl: square
+    matrices A, B, C and an assignment z with (A z) o (B z) = C z, z[0] = 1, the first n_pub entries public): sparse
+    descriptions {"shape", "entries"} plus z.  Row i of A and B holds `nnz_per_row` random entries; row i of C holds the one
+    entry that makes the constraint true."""
+    rng = random.Random(seed)
+    z = [1] + [rng.randrange(1, r) for _ in range(n_rows - 1)]
+    ents = {"A": [], "B": [], "C": []}
+    for i in range(n_rows):
+        acc = {}
+        for M in "AB":
+            cols = rng.sample(range(n_rows), nnz_per_row)
+            vals = [rng.randrange(1, 1 << 16) for _ in cols]
+            ents[M] += [(i, c, v) for c, v in zip(cols, vals)]
+            acc[M] = sum(v * z[c] for c, v in zip(cols, vals)) % r
+        j = rng.randrange(n_rows)
+        ents["C"].append((i, j, acc["A"] * acc["B"] % r * pow(z[j], -1, r) % r))
+    mats = [{"shape": (n_rows, n_rows), "entries": ents[M]} for M in "ABC"]
+    return mats[0], mats[1], mats[2], z[:n_pub], z[n_pub:]

@@ -362,3 +362,28 @@ def test_marlin_prover_matches_the_reference_prover_bit_for_bit():
         assert [int(v) for v in proof["evaluations"][k]] == [H(v) for v in vals], k
     for k, p in exp["kzg_proofs"].items():
         assert aff(proof["kzg_proofs"][k]) == (H(p[0]), H(p[1])), k
+
+
+@pytest.mark.parametrize("curve,logn", [("bn254", 6), ("bn254", 11), ("bls12_381", 8)])
+def test_marlin_prover_synthetic_r1cs_identities(curve, logn):
+    """Sizes and the second curve the bundled instance does not cover: on a random satisfied R1CS the prover's three
+    linearisation polynomials must vanish at their challenge points -- f_1(beta_1) = f_2(beta_1) = f_3(beta_2) = 0 are the
+    polynomial identities the Marlin verifier checks (marlin/prover.py:198-200 asserts the same) -- the first sumcheck's
+    remainder has no constant term, and an unsatisfied instance must break them."""
+    from kzg_snark_b200 import marlin
+    rq = CURVES[curve]["r"]
+    n = 1 << logn
+    A, B, C, x, w = marlin.synthetic_r1cs(n, 5, rq, seed=logn)
+    idx = marlin.Indexer(curve)
+    m_need = 1 << (2 * n - 1).bit_length()                     # nnz(A) = 2n -> |K| = 2n
+    ipk, _ = idx.preprocess(A, B, C, max_degree=6 * m_need, rng=random.Random(logn))
+    assert ipk["subgroups"]["m"] == m_need
+    prover = marlin.Prover(curve)
+    proof = prover.prove(ipk, [idx.kzg.Fq(v) for v in x], w)
+    assert set(prover.checks.values()) == {0}
+    assert len(proof["commitments"]["first_round"]) == 6 and all(int(p[2]) == 1 for p in proof["commitments"]["first_round"])
+    bad = list(w)
+    bad[7] = (bad[7] + 1) % rq
+    with pytest.raises(AssertionError):                        # "Sum over H is not 0" (marlin/prover.py:134) or a failed identity
+        prover.prove(ipk, [idx.kzg.Fq(v) for v in x], bad)
+        assert set(prover.checks.values()) == {0}
