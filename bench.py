@@ -516,6 +516,50 @@ def run_gpu(args):
         out["marlin_bundled"] = {**dropin_hotpath("marlin"),
                                  "note": "configs[4] bundled R1CS instance: the 19 commit / open / fft_ff / fft_ff_interpolation calls "
                                          "marlin/prover.py made (tests/golden/ref_trace_marlin.json), replayed through the drop-in"}
+        # configs[4]: the device Marlin prover on the bundled R1CS instance (proof compared with the reference prover's) and on a
+        # synthetic R1CS of 2^marlin_rows_logn rows
+        from kzg_snark_b200 import marlin
+        dm = json.load(open(os.path.join(gold, "ref_marlin_normalized.json")))
+        r1 = json.load(open(os.path.join(gold, "r1cs_instance.json")))
+        mats = [[[H(v) for v in row] for row in r1[k]] for k in "ABC"]
+        midx = marlin.Indexer("bn254")
+        mipk, _ = midx.preprocess(*mats, max_degree=200, tau=H(dm["index_draws"][0]))
+        mx, mw, mdr = [midx.kzg.Fq(H(v)) for v in dm["x"]], [H(v) for v in dm["w"]], [H(v) for v in dm["prover_draws"]]
+        mpr = marlin.Prover("bn254")
+        mt = []
+        for i in range(Wm + K):
+            t0 = time.perf_counter()
+            mproof = mpr.prove(mipk, mx, mw, draws=mdr)
+            mt.append(time.perf_counter() - t0)
+        mt = sorted(mt[Wm:])
+        pt2 = lambda P: (int(P[0]), int(P[1]))                           # noqa: E731
+        msame = (all([pt2(p) for p in mproof["commitments"][k]] == [(H(q[0]), H(q[1])) for q in v] for k, v in dm["proof"]["commitments"].items())
+                 and all([int(e) for e in mproof["evaluations"][k]] == [H(q) for q in v] for k, v in dm["proof"]["evaluations"].items())
+                 and all(pt2(mproof["kzg_proofs"][k]) == (H(v[0]), H(v[1])) for k, v in dm["proof"]["kzg_proofs"].items()))
+        out["marlin_bundled"].update({"prove_s": mt[len(mt) // 2], "proof_equals_reference_prover": bool(msame)})
+        rows = 1 << args.marlin_rows_logn
+        t0 = time.perf_counter()
+        sA, sB, sC, sx, sw = marlin.synthetic_r1cs(rows, 8, R_BN254, seed=args.marlin_rows_logn)
+        swl = ints_to_limbs(sw, R_BN254)
+        sdraws = random_scalars(8 + 2 * rows + 1, R_BN254, seed=4)
+        t_gen = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        mK = 1 << (2 * rows - 1).bit_length()
+        sipk, _ = midx.preprocess(sA, sB, sC, max_degree=6 * mK, tau=TAU)
+        _ffi.check(_ffi._lib.kzgpu_sync())
+        t_mindex = time.perf_counter() - t0
+        sxs = [midx.kzg.Fq(v) for v in sx]
+        mt = []
+        for i in range(3 + 5):
+            t0 = time.perf_counter()
+            mpr.prove(sipk, sxs, swl, draws=sdraws)
+            mt.append(time.perf_counter() - t0)
+        assert set(mpr.checks.values()) == {0}, "a Marlin linearisation identity failed"
+        mt = sorted(mt[3:])
+        out["marlin_synthetic"] = {"rows": rows, "H": sipk["subgroups"]["n"], "K": sipk["subgroups"]["m"], "prove_s": mt[len(mt) // 2],
+                                   "index_s": t_mindex, "instance_generation_s": t_gen,
+                                   "rounds_s": {k: round(v, 5) for k, v in mpr.timings.items()},
+                                   "checks": "f_1(beta_1) = f_2(beta_1) = f_3(beta_2) = 0 asserted (the verifier's polynomial identities)"}
         out["synthetic"] = {"gates": n, "prove_s": times[len(times) // 2], "index_s": t_index, "circuit_generation_s": t_gen,
                             "h2d_bytes": int(wl.nbytes), "host_buffers": "pinned (cudaHostAlloc)", "gpu_launches_per_prove": int(launches),
                             "rounds_s": {k: round(v, 5) for k, v in prover.timings.items()},
@@ -721,6 +765,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="msm", choices=["msm", "ntt", "plonk", "marlin"])
     ap.add_argument("--marlin-logn", type=int, default=20, help="constraints of the Marlin kernel workload (log2)")
+    ap.add_argument("--marlin-rows-logn", type=int, default=16, help="rows of the synthetic R1CS for the device Marlin prover (log2)")
     ap.add_argument("--plonk-logn", type=int, default=20, help="gates of the synthetic PLONK circuit (log2)")
     ap.add_argument("--logn", type=int, default=24)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
