@@ -234,6 +234,135 @@ __global__ void __launch_bounds__(kThreads, 4) ntt_pass_kernel(NttPassArgs a, Nt
   }
 }
 
+// ---- compile-time shapes: R = 2^B with a full 1024-element tile (B = 6..9, C = 2^(10-B) columns).  Same algorithm and
+// shared-memory layout as ntt_pass_kernel; with B fixed every plane stride, digit width and swizzle shift is an immediate and
+// the digit loops fold away (the generic kernel spends ~15 % of its instructions on that address arithmetic).
+template <int B> struct NttShape {
+  static constexpr int LOGC = kLogTile - B;
+  static constexpr int ND = (B + 2) / 3;
+  static constexpr int width(int s) { return B - 3 * s >= 3 ? 3 : B - 3 * s; }
+  static constexpr int done(int li) { return 3 * li; }                 // all layers before the last are radix 8
+  static constexpr int off(int li) { return B - done(li) - width(li); }
+};
+
+template <class P, int B, int LI>
+__device__ __forceinline__ void ntt_layer_c(uint32_t* sm, const uint32_t* smw, const NttConsts<P>& c) {
+  using S = NttShape<B>;
+  constexpr int D = S::width(LI), OFF = S::off(LI), DONE = S::done(LI), LOGC = S::LOGC;
+  constexpr uint32_t tile = 1u << kLogTile, ngroups = tile >> D, Cmask = (1u << LOGC) - 1;
+#pragma unroll
+  for (uint32_t gsub = 0; gsub < (8u >> D); gsub++) {
+    const uint32_t G = threadIdx.x + kThreads * gsub;
+    if (ngroups < kThreads * (8u >> D) && G >= ngroups) break;
+    const uint32_t cc = G & Cmask, rest = G >> LOGC;
+    const uint32_t low = rest & ((1u << OFF) - 1), high = rest >> OFF;
+    uint32_t V = 0;
+    {
+      uint32_t hb = high;
+      int sh = DONE;
+#pragma unroll
+      for (int s = LI - 1; s >= 0; s--) {
+        constexpr int dd = 3;
+        sh -= dd;
+        V |= (hb & ((1u << dd) - 1)) << sh;
+        hb >>= dd;
+      }
+    }
+    Fe<P> x[1 << D];
+    const uint32_t base_l = (high << (OFF + D)) | low;
+#pragma unroll
+    for (int u = 0; u < (1 << D); u++) {
+      uint32_t l = base_l | ((uint32_t)u << OFF);
+      x[u] = sm_ld<P>(sm, tile, swz((l << LOGC) | cc, LOGC));
+    }
+    if constexpr (LI > 0) {
+#pragma unroll
+      for (int u = 1; u < (1 << D); u++) {
+        uint32_t e = ((uint32_t)u << OFF) * V;
+        x[u] = fe_mul<P>(x[u], sm_ld<P>(smw, 1u << B, e));
+      }
+    }
+    dft_small<P, D>(x, c);
+#pragma unroll
+    for (int u = 0; u < (1 << D); u++) {
+      uint32_t l = base_l | ((uint32_t)u << OFF);
+      sm_st<P>(sm, tile, swz((l << LOGC) | cc, LOGC), x[u]);
+    }
+  }
+}
+
+template <class P, int B>
+__global__ void __launch_bounds__(kThreads, 4) ntt_pass_kernel_c(NttPassArgs a, NttConsts<P> c) {
+  using S = NttShape<B>;
+  constexpr int LOGC = S::LOGC;
+  constexpr uint32_t tile = 1u << kLogTile, R = 1u << B, Cmask = (1u << LOGC) - 1, Rmask = R - 1;
+  extern __shared__ uint32_t sm[];
+  uint32_t* smw = sm + (size_t)P::N * tile;
+  for (uint32_t e = threadIdx.x; e < R; e += kThreads) sm_st<P>(smw, R, e, ldg_fe<P>(a.wR + (size_t)e * P::N));
+  const uint32_t Kmask = (1u << a.logK) - 1;
+  const size_t boff = (size_t)blockIdx.y * a.n;
+  const size_t q0 = ((size_t)blockIdx.x + a.blk0) << LOGC;
+
+#pragma unroll 1
+  for (uint32_t o0 = threadIdx.x; o0 < tile; o0 += 4 * kThreads) {
+    Fe<P> v[4], tw[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint32_t o = o0 + k * kThreads;
+      uint32_t l = o >> LOGC, cc = o & Cmask;
+      size_t qq = q0 + cc;
+      v[k] = ld_fe<P>(a.in + (boff + ((size_t)l << a.logQ) + qq) * P::N);
+      if (a.bnd) tw[k] = ldg_fe<P>(a.bnd + (((size_t)l << a.logK) + (qq & Kmask)) * P::N);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint32_t o = o0 + k * kThreads;
+      if (a.bnd) v[k] = fe_mul<P>(v[k], tw[k]);
+      sm_st<P>(sm, tile, swz(o, LOGC), v[k]);
+    }
+  }
+  __syncthreads();
+
+  ntt_layer_c<P, B, 0>(sm, smw, c);
+  __syncthreads();
+  if constexpr (S::ND > 1) { ntt_layer_c<P, B, 1>(sm, smw, c); __syncthreads(); }
+  if constexpr (S::ND > 2) { ntt_layer_c<P, B, 2>(sm, smw, c); __syncthreads(); }
+
+  const uint32_t logCm = (uint32_t)LOGC < a.logK ? (uint32_t)LOGC : a.logK;
+#pragma unroll 1
+  for (uint32_t o = threadIdx.x; o < tile; o += kThreads) {
+    uint32_t cc_lo = o & ((1u << logCm) - 1);
+    uint32_t kt = (o >> logCm) & Rmask;
+    uint32_t cc_hi = o >> (logCm + B);
+    uint32_t cc = (cc_hi << logCm) | cc_lo;
+    size_t qq = q0 + cc;
+    size_t jlo = qq >> a.logK, kk = qq & Kmask;
+    uint32_t l = 0, kr = kt;
+    int ob = B;
+#pragma unroll
+    for (int s = 0; s < S::ND; s++) {
+      constexpr int dummy = 0; (void)dummy;
+      const int dd = S::width(s);
+      ob -= dd;
+      l |= (kr & ((1u << dd) - 1)) << ob;
+      kr >>= dd;
+    }
+    Fe<P> v = sm_ld<P>(sm, tile, swz((l << LOGC) | cc, LOGC));
+    if (a.post) v = fe_mul<P>(v, ldg_fe<P>(a.post + (size_t)kt * P::N));
+    st_fe<P>(a.out + (boff + (((jlo << B) + kt) << a.logK) + kk) * P::N, v);
+  }
+}
+
+template <class P>
+void launch_pass(const NttPassArgs& a, const NttConsts<P>& c, dim3 grid, uint32_t threads, size_t smem, cudaStream_t st) {
+  const bool full = a.b + a.logC == (uint32_t)kLogTile && threads == (uint32_t)kThreads && a.nd > 1;
+  if (full && a.b == 9) ntt_pass_kernel_c<P, 9><<<grid, threads, smem, st>>>(a, c);
+  else if (full && a.b == 8) ntt_pass_kernel_c<P, 8><<<grid, threads, smem, st>>>(a, c);
+  else if (full && a.b == 7) ntt_pass_kernel_c<P, 7><<<grid, threads, smem, st>>>(a, c);
+  else if (full && a.b == 6) ntt_pass_kernel_c<P, 6><<<grid, threads, smem, st>>>(a, c);
+  else ntt_pass_kernel<P><<<grid, threads, smem, st>>>(a, c);
+}
+
 template <class P> __device__ Fe<P> fe_pow_u64(Fe<P> base, uint64_t e) {
   Fe<P> r = fe_one<P>();
   while (e) {
@@ -400,6 +529,15 @@ int run_plan(const NttPlan& pl, uint32_t* d_data, size_t batch, const NttHostIo*
   if (!attr_set) {
     KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<FrBN254>, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 * 4 << kLogTile) + (32 << kMaxB)));
     KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<FrBLS381>, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 * 4 << kLogTile) + (32 << kMaxB)));
+    const int smax = (8 * 4 << kLogTile) + (32 << kMaxB);
+    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel_c<FrBN254, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel_c<FrBN254, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel_c<FrBN254, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel_c<FrBN254, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel_c<FrBLS381, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel_c<FrBLS381, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel_c<FrBLS381, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel_c<FrBLS381, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
     attr_set = true;
   }
   const uint32_t* src = d_data;
@@ -435,7 +573,7 @@ int run_plan(const NttPlan& pl, uint32_t* d_data, size_t batch, const NttHostIo*
         if (slab_in) KZ_CUDA(cudaStreamWaitEvent(cx.stream, cx.copy_ev[k], 0));
         a.blk0 = k * (tiles / kSlabs);
         KzProf prof(1);
-        ntt_pass_kernel<P><<<dim3(tiles / kSlabs, 1), threads, smem, cx.stream>>>(a, c);
+        launch_pass<P>(a, c, dim3(tiles / kSlabs, 1), threads, smem, cx.stream);
         KZ_LAUNCHED();
         prof.stop(k == 0 ? 1 : 0, k == 0 ? (double)n : 0.0);
         if (slab_out) {
@@ -451,7 +589,7 @@ int run_plan(const NttPlan& pl, uint32_t* d_data, size_t batch, const NttHostIo*
     }
     dim3 grid((unsigned)tiles, (unsigned)batch);
     KzProf prof(1);
-    ntt_pass_kernel<P><<<grid, threads, smem, cx.stream>>>(a, c);
+    launch_pass<P>(a, c, grid, threads, smem, cx.stream);
     KZ_LAUNCHED();
     prof.stop(1, (double)n * (double)batch);
     src = dst;
