@@ -18,6 +18,8 @@ struct KzgpuCtx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t copy_stream = nullptr;     // chunked host->device uploads overlapped with compute
   cudaEvent_t copy_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t sort_stream = nullptr;     // MSM: sort of chunk k+1 (HBM/LSU-bound) overlapped with the accumulate of chunk k (multiplier-bound)
+  cudaEvent_t sort_ev[2] = {nullptr, nullptr}, acc_ev[2] = {nullptr, nullptr}, start_ev = nullptr;
   uint64_t launches = 0;
   char err[512] = {0};
   // per-kernel profiling (bench.py roofline): enabled -> events around selected launches

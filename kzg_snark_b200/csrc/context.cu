@@ -223,6 +223,16 @@ int kzgpu_init(int device) {
   cx.stream = cx.own_stream;
   KZ_CUDA(cudaStreamCreateWithFlags(&cx.copy_stream, cudaStreamNonBlocking));
   for (int k = 0; k < 4; k++) KZ_CUDA(cudaEventCreateWithFlags(&cx.copy_ev[k], cudaEventDisableTiming));
+  {
+    int lo_prio = 0, hi_prio = 0;
+    KZ_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    KZ_CUDA(cudaStreamCreateWithPriority(&cx.sort_stream, cudaStreamNonBlocking, hi_prio));
+    for (int k = 0; k < 2; k++) {
+      KZ_CUDA(cudaEventCreateWithFlags(&cx.sort_ev[k], cudaEventDisableTiming));
+      KZ_CUDA(cudaEventCreateWithFlags(&cx.acc_ev[k], cudaEventDisableTiming));
+    }
+    KZ_CUDA(cudaEventCreateWithFlags(&cx.start_ev, cudaEventDisableTiming));
+  }
   KZ_CUDA(cudaEventCreate(&cx.ev0));
   KZ_CUDA(cudaEventCreate(&cx.ev1));
   cx.device = device;
@@ -244,6 +254,10 @@ int kzgpu_shutdown(void) {
   cudaStreamDestroy(cx.own_stream);
   cudaStreamDestroy(cx.copy_stream);
   for (int k = 0; k < 4; k++) cudaEventDestroy(cx.copy_ev[k]);
+  cudaStreamDestroy(cx.sort_stream);
+  for (int k = 0; k < 2; k++) { cudaEventDestroy(cx.sort_ev[k]); cudaEventDestroy(cx.acc_ev[k]); }
+  cudaEventDestroy(cx.start_ev);
+  cx.sort_stream = nullptr;
   cx.stream = cx.own_stream = nullptr;
   cx.inited = false;
   cx.device = -1;

@@ -38,11 +38,17 @@ struct Srs {
 std::map<uint64_t, Srs> g_srs;
 uint64_t g_next_handle = 1;
 
-struct MsmWs {
-  KzScratch counts, offsets, cursor, entries, buckets, partials, winsums, blocksums, result, flag, scal;
-  KzScratch ntasks, task_off, size_hist, t_start, t_len, t_dest, tparts, multi, sort_tmp, coarse;
+struct MsmWs {                         // shared by all chunks of a call
+  KzScratch buckets, partials, winsums, result, flag, scal;
 };
 MsmWs g_ws;
+// what the sort + task phase of one chunk produces and its accumulate / merge consumes: two sets, so that the
+// sort of chunk k+1 (sort stream) runs while chunk k is accumulated (main stream)
+struct MsmSortWs {
+  KzScratch counts, offsets, cursor, entries, blocksums;
+  KzScratch ntasks, task_off, size_hist, t_start, t_len, t_dest, tparts, multi, sort_tmp, coarse;
+};
+MsmSortWs g_sw[2];
 
 // ---------------------------------------------------------------- device helpers
 template <class P> __device__ __forceinline__ void ld_words(uint32_t* dst, const uint32_t* src) {
@@ -814,18 +820,32 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   using R = typename Cfg::Fr;
   KzgpuCtx& cx = kz_ctx();
   cudaStream_t st = cx.stream;
-  // Host scalars (the e2e entry point): the upload is split into chunks on the copy stream and the
-  // MSM runs chunk by chunk into the same buckets, so that all but the first chunk's PCIe time
-  // hides behind the sort + accumulate of the previous chunk.
-  // Chunk sizes grow (1/16, 3/16, 1/4, 1/2 of the scalars): only the first chunk's transfer is exposed, so it is
-  // the smallest; each later transfer has the previous chunk's (shorter or equal) compute to hide behind.
-  const uint32_t nchunks = (h_scalars && n >= (1u << 20)) ? 4u : 1u;
+  // Chunks.  Host scalars (the e2e entry point): the upload is split into chunks on the copy stream and the MSM runs
+  // chunk by chunk into the same buckets, so that all but the first chunk's PCIe time hides behind the work on the
+  // previous chunk.  Chunk sizes grow (1/16, 3/16, 1/4, 1/2 of the scalars): only the first chunk's transfer is exposed.
+  // The sort + task construction of chunk k+1 (HBM / shared-memory-atomic bound) runs on a high-priority second stream
+  // while chunk k is accumulated (multiplier bound), each chunk owning one of two sort workspaces.  Measured at 2^24
+  // (scripts/pipe_ab.py): 38.0 -> 37.3 ms for host scalars.  The same split applied to device-resident scalars
+  // (KZGPU_MSM_DEV_SPLIT=d: chunks n/d and the rest) does NOT pay -- 35.7 -> 35.9 ms: a resident sort block takes the
+  // registers of one of the four accumulate blocks of its SM, and the accumulate kernel at 3 warps per scheduler
+  // loses about what the overlap wins, plus the second chunk's bucket fix-up -- so it stays off by default.
+  static const bool pipe_ok = !getenv("KZGPU_MSM_NO_PIPE");
+  uint32_t nchunks = 1;
+  if (batch == 1 && h_scalars && n >= (1u << 20)) nchunks = 4;
+  else if (batch == 1 && !h_scalars && n >= (1u << 22) && pipe_ok && getenv("KZGPU_MSM_DEV_SPLIT")) nchunks = 2;
   size_t chunk_lo[5] = {0, n, n, n, n};
   if (nchunks == 4) {
     const char* env = getenv("KZGPU_MSM_CHUNKS");      // "uniform": four equal chunks (A/B measurements)
     if (env && env[0] == 'u') { chunk_lo[1] = n / 4; chunk_lo[2] = n / 2; chunk_lo[3] = 3 * (n / 4); }
     else { chunk_lo[1] = n / 16; chunk_lo[2] = n / 4; chunk_lo[3] = n / 2; }
+  } else if (nchunks == 2) {
+    static const char* env = getenv("KZGPU_MSM_DEV_SPLIT");     // first chunk = n / split (A/B measurements)
+    const size_t split = env && atoi(env) >= 2 ? (size_t)atoi(env) : 8;
+    chunk_lo[1] = n / split;
   }
+  // profiling (per-kernel CUDA events on the main stream) keeps everything on one stream
+  const bool piped = nchunks > 1 && pipe_ok && !cx.profile;
+  cudaStream_t sst = piped ? cx.sort_stream : st;
   size_t chunk_n = 0;                                   // largest chunk: sizes the sort scratch
   for (uint32_t k = 0; k < nchunks; k++) if (chunk_lo[k + 1] - chunk_lo[k] > chunk_n) chunk_n = chunk_lo[k + 1] - chunk_lo[k];
   if (h_scalars && n) {
@@ -851,18 +871,41 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   if (ncoarse > kMaxCoarse) return kz_fail(KZGPU_EINVAL, "MSM window c=%u gives too many buckets (%zu)", c, nb);
   const size_t max_entries = (size_t)chunk_n * W;
   if (max_entries >= 0xffffffffull) return kz_fail(KZGPU_EINVAL, "MSM of %zu points x %u digits exceeds 2^32 entries", n, W);
-  const size_t max_sort_blocks = max_entries / kSortChunk + ncoarse + 1;
+  const size_t nblk = kz_div_up(nb, 1024);
+  // tasks: heavy buckets are split into <= T-point tasks, T from the chunk's mean bucket load
+  auto task_T = [&](size_t cn) {
+    uint32_t mean = (uint32_t)((((size_t)cn / batch) * (tabled ? W : 1u)) / B) + 1, t = 32;
+    while (t < 2 * mean && t < 1024) t <<= 1;
+    return t;
+  };
+  size_t max_tasks = 0, max_multi = 0;
+  for (uint32_t k = 0; k < nchunks; k++) {
+    const size_t cn = chunk_lo[k + 1] - chunk_lo[k];
+    const size_t split = (cn * W) / task_T(cn) + 1;               // a split bucket holds more than T points
+    if (nb + split > max_tasks) max_tasks = nb + split;
+    if (split > max_multi) max_multi = split;
+  }
   int rc;
-  if ((rc = g_ws.counts.ensure(nb * 4))) return rc;
-  if ((rc = g_ws.offsets.ensure((nb + 1) * 4))) return rc;
-  if ((rc = g_ws.cursor.ensure(nb * 4))) return rc;
-  if ((rc = g_ws.entries.ensure(max_entries * 4 + 4))) return rc;
-  if ((rc = g_ws.sort_tmp.ensure(max_entries * 8 + 8))) return rc;
-  if ((rc = g_ws.coarse.ensure((size_t)(4 * kMaxCoarse + 4) * 4))) return rc;
+  for (uint32_t s = 0; s < (nchunks > 1 ? 2u : 1u); s++) {
+    MsmSortWs& w = g_sw[s];
+    if ((rc = w.counts.ensure(nb * 4))) return rc;
+    if ((rc = w.offsets.ensure((nb + 1) * 4))) return rc;
+    if ((rc = w.cursor.ensure(nb * 4))) return rc;
+    if ((rc = w.entries.ensure(max_entries * 4 + 4))) return rc;
+    if ((rc = w.sort_tmp.ensure(max_entries * 8 + 8))) return rc;
+    if ((rc = w.coarse.ensure((size_t)(4 * kMaxCoarse + 4) * 4))) return rc;
+    if ((rc = w.blocksums.ensure(nblk * 4))) return rc;
+    if ((rc = w.ntasks.ensure(nb * 4))) return rc;
+    if ((rc = w.task_off.ensure((nb + 1) * 4))) return rc;
+    if ((rc = w.size_hist.ensure(2 * (1024 + 1) * 4))) return rc;
+    if ((rc = w.t_start.ensure(max_tasks * 4))) return rc;
+    if ((rc = w.t_len.ensure(max_tasks * 4))) return rc;
+    if ((rc = w.t_dest.ensure(max_tasks * 4))) return rc;
+    if ((rc = w.tparts.ensure(max_tasks * 4 * P::N * 4))) return rc;
+    if ((rc = w.multi.ensure((max_multi + 1) * 4))) return rc;
+  }
   if ((rc = g_ws.buckets.ensure(nb * 4 * P::N * 4))) return rc;
   if ((rc = g_ws.flag.ensure(4))) return rc;
-  const size_t nblk = kz_div_up(nb, 1024);
-  if ((rc = g_ws.blocksums.ensure(nblk * 4))) return rc;
   // buckets per reduce thread: each thread walks a chain of 2*CH dependent XYZZ additions (~7 us each when a
   // warp runs alone), so small bucket sets get short chunks -- enough threads to fill the SMs matters more than
   // the ~20-addition fix-up (lo * running) every chunk pays
@@ -874,18 +917,12 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   const size_t lvl1 = kz_div_up(cpw, 1024);
   if ((rc = g_ws.winsums.ensure(2 * (size_t)Wb * (lvl1 + 1) * 4 * P::N * 4))) return rc;
 
-  uint32_t* counts = (uint32_t*)g_ws.counts.p;
-  uint32_t* offsets = (uint32_t*)g_ws.offsets.p;
-  uint32_t* cursor = (uint32_t*)g_ws.cursor.p;
-  uint32_t* entries = (uint32_t*)g_ws.entries.p;
-  uint64_t* sort_tmp = (uint64_t*)g_ws.sort_tmp.p;
-  uint32_t* coarse_counts = (uint32_t*)g_ws.coarse.p;
-  uint32_t* coarse_off = coarse_counts + kMaxCoarse;        // ncoarse + 1 entries
-  uint32_t* coarse_cur = coarse_off + kMaxCoarse + 1;
-  uint32_t* blk_off = coarse_cur + kMaxCoarse;              // ncoarse + 1 entries
   uint32_t* flag = (uint32_t*)g_ws.flag.p;
-
   KZ_CUDA(cudaMemsetAsync(flag, 0, 4, st));
+  if (piped) {                                           // the sort stream starts after everything queued so far
+    KZ_CUDA(cudaEventRecord(cx.start_ev, st));
+    KZ_CUDA(cudaStreamWaitEvent(sst, cx.start_ev, 0));
+  }
   SortGeom geo;
   geo.c = c; geo.W = W; geo.B = B; geo.f = f; geo.ncoarse = ncoarse; geo.tabled = tabled ? 1u : 0u;
   geo.first = (uint32_t)first; geo.n_srs = (uint32_t)srs.n;
@@ -899,6 +936,7 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   }
   const uint32_t* d_scalars_all = d_scalars;
   const size_t n_all = n, first_all = first;
+  (void)n_all;
   for (uint32_t chunk = 0; chunk < nchunks; chunk++) {
   const size_t c_lo = chunk_lo[chunk];
   n = chunk_lo[chunk + 1] - c_lo;
@@ -907,88 +945,97 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
   first = first_all + c_lo;
   geo.first = (uint32_t)first;
   const uint32_t add_existing = chunk ? 1u : 0u;
-  if (h_scalars) KZ_CUDA(cudaStreamWaitEvent(st, cx.copy_ev[chunk], 0));
-  KZ_CUDA(cudaMemsetAsync(counts, 0, nb * 4, st));
-  KZ_CUDA(cudaMemsetAsync(coarse_counts, 0, kMaxCoarse * 4, st));
+  MsmSortWs& w = g_sw[chunk & 1];
+  uint32_t* counts = (uint32_t*)w.counts.p;
+  uint32_t* offsets = (uint32_t*)w.offsets.p;
+  uint32_t* cursor = (uint32_t*)w.cursor.p;
+  uint32_t* entries = (uint32_t*)w.entries.p;
+  uint64_t* sort_tmp = (uint64_t*)w.sort_tmp.p;
+  uint32_t* coarse_counts = (uint32_t*)w.coarse.p;
+  uint32_t* coarse_off = coarse_counts + kMaxCoarse;        // ncoarse + 1 entries
+  uint32_t* coarse_cur = coarse_off + kMaxCoarse + 1;
+  uint32_t* blk_off = coarse_cur + kMaxCoarse;              // ncoarse + 1 entries
+  uint32_t* blocksums = (uint32_t*)w.blocksums.p;
+  // ---- sort + tasks of this chunk (stream sst)
+  if (h_scalars) KZ_CUDA(cudaStreamWaitEvent(sst, cx.copy_ev[chunk], 0));
+  if (piped && chunk >= 2) KZ_CUDA(cudaStreamWaitEvent(sst, cx.acc_ev[chunk & 1], 0));   // workspace still read by chunk - 2
+  KZ_CUDA(cudaMemsetAsync(counts, 0, nb * 4, sst));
+  KZ_CUDA(cudaMemsetAsync(coarse_counts, 0, kMaxCoarse * 4, sst));
   KzProf prof_sort(2);
   if (n) {
     const unsigned tiles = (unsigned)kz_div_up(n, kSortTile);
-    msm_coarse_hist_kernel<<<tiles, 256, ncoarse * 4, st>>>(d_scalars, n, geo, doff, coarse_counts, flag);
+    msm_coarse_hist_kernel<<<tiles, 256, ncoarse * 4, sst>>>(d_scalars, n, geo, doff, coarse_counts, flag);
     KZ_LAUNCHED();
-    msm_coarse_scan_kernel<<<1, 1024, 0, st>>>(coarse_counts, ncoarse, coarse_off, coarse_cur, blk_off);
+    msm_coarse_scan_kernel<<<1, 1024, 0, sst>>>(coarse_counts, ncoarse, coarse_off, coarse_cur, blk_off);
     KZ_LAUNCHED();
     const uint32_t ptile = kSortStage / W;                       // scalars per partition block
     const size_t psmem = (size_t)ptile * W * 8 + (2 * (size_t)ncoarse + 512) * 4;
-    msm_partition_kernel<<<(unsigned)kz_div_up(n, ptile), 512, psmem, st>>>(d_scalars, n, ptile, geo, doff, coarse_cur, sort_tmp);
+    msm_partition_kernel<<<(unsigned)kz_div_up(n, ptile), 512, psmem, sst>>>(d_scalars, n, ptile, geo, doff, coarse_cur, sort_tmp);
     KZ_LAUNCHED();
-    msm_fine_hist_kernel<<<(unsigned)max_sort_blocks, 256, (4u << f), st>>>(sort_tmp, coarse_off, blk_off, ncoarse, f, (uint32_t)nb, counts);
+    const size_t sort_blocks = (n * W) / kSortChunk + ncoarse + 1;
+    msm_fine_hist_kernel<<<(unsigned)sort_blocks, 256, (4u << f), sst>>>(sort_tmp, coarse_off, blk_off, ncoarse, f, (uint32_t)nb, counts);
     KZ_LAUNCHED();
   }
-  scan_block_kernel<<<(unsigned)nblk, 256, 0, st>>>(counts, offsets, (uint32_t*)g_ws.blocksums.p, nb);
+  scan_block_kernel<<<(unsigned)nblk, 256, 0, sst>>>(counts, offsets, blocksums, nb);
   KZ_LAUNCHED();
-  scan_sums_kernel<<<1, 256, 0, st>>>((uint32_t*)g_ws.blocksums.p, nblk, offsets + nb);
+  scan_sums_kernel<<<1, 256, 0, sst>>>(blocksums, nblk, offsets + nb);
   KZ_LAUNCHED();
-  scan_add_kernel<<<(unsigned)kz_div_up(nb, 256), 256, 0, st>>>(offsets, (uint32_t*)g_ws.blocksums.p, nb, cursor);
+  scan_add_kernel<<<(unsigned)kz_div_up(nb, 256), 256, 0, sst>>>(offsets, blocksums, nb, cursor);
   KZ_LAUNCHED();
   if (n) {
-    msm_fine_scatter_kernel<<<(unsigned)max_sort_blocks, 512, ((8u << f) + (512 + kSortChunk) * 4), st>>>(sort_tmp, coarse_off, blk_off, ncoarse, f, (uint32_t)nb, cursor,
+    const size_t sort_blocks = (n * W) / kSortChunk + ncoarse + 1;
+    msm_fine_scatter_kernel<<<(unsigned)sort_blocks, 512, ((8u << f) + (512 + kSortChunk) * 4), sst>>>(sort_tmp, coarse_off, blk_off, ncoarse, f, (uint32_t)nb, cursor,
                                                                              entries);
     KZ_LAUNCHED();
   }
   const uint32_t ostride = 1u;                          // offsets[] entries per bucket
-  // tasks: split heavy buckets, sort by length
-  uint32_t mean = (uint32_t)((((size_t)n / batch) * (tabled ? W : 1u)) / B) + 1;
-  uint32_t T = 32;
-  while (T < 2 * mean && T < 1024) T <<= 1;
-  const size_t max_tasks = nb + ((size_t)n * W) / T + 1;
-  if ((rc = g_ws.ntasks.ensure(nb * 4))) return rc;
-  if ((rc = g_ws.task_off.ensure((nb + 1) * 4))) return rc;
-  if ((rc = g_ws.size_hist.ensure(2 * (1024 + 1) * 4))) return rc;
-  if ((rc = g_ws.t_start.ensure(max_tasks * 4))) return rc;
-  if ((rc = g_ws.t_len.ensure(max_tasks * 4))) return rc;
-  if ((rc = g_ws.t_dest.ensure(max_tasks * 4))) return rc;
-  if ((rc = g_ws.tparts.ensure(max_tasks * 4 * P::N * 4))) return rc;
-  const size_t max_multi = ((size_t)n * W) / T + 1;          // a split bucket holds more than T points
-  if ((rc = g_ws.multi.ensure((max_multi + 1) * 4))) return rc;
-  uint32_t* multi_count = (uint32_t*)g_ws.multi.p;
+  const uint32_t T = task_T(n);
+  uint32_t* multi_count = (uint32_t*)w.multi.p;
   uint32_t* multi_list = multi_count + 1;
-  KZ_CUDA(cudaMemsetAsync(multi_count, 0, 4, st));
-  uint32_t* ntasks = (uint32_t*)g_ws.ntasks.p;
-  uint32_t* task_off = (uint32_t*)g_ws.task_off.p;
-  uint32_t* size_hist = (uint32_t*)g_ws.size_hist.p;
+  KZ_CUDA(cudaMemsetAsync(multi_count, 0, 4, sst));
+  uint32_t* ntasks = (uint32_t*)w.ntasks.p;
+  uint32_t* task_off = (uint32_t*)w.task_off.p;
+  uint32_t* size_hist = (uint32_t*)w.size_hist.p;
   uint32_t* size_cursor = size_hist + (1024 + 1);
-  KZ_CUDA(cudaMemsetAsync(size_hist, 0, (1024 + 1) * 4, st));
-  task_count_kernel<<<(unsigned)kz_div_up(nb, 256), 256, (T + 1) * 4, st>>>(offsets, ostride, (uint32_t)nb, T, ntasks, size_hist, multi_count, multi_list);
+  KZ_CUDA(cudaMemsetAsync(size_hist, 0, (1024 + 1) * 4, sst));
+  task_count_kernel<<<(unsigned)kz_div_up(nb, 256), 256, (T + 1) * 4, sst>>>(offsets, ostride, (uint32_t)nb, T, ntasks, size_hist, multi_count, multi_list);
   KZ_LAUNCHED();
-  scan_block_kernel<<<(unsigned)nblk, 256, 0, st>>>(ntasks, task_off, (uint32_t*)g_ws.blocksums.p, nb);
+  scan_block_kernel<<<(unsigned)nblk, 256, 0, sst>>>(ntasks, task_off, blocksums, nb);
   KZ_LAUNCHED();
-  scan_sums_kernel<<<1, 256, 0, st>>>((uint32_t*)g_ws.blocksums.p, nblk, task_off + nb);
+  scan_sums_kernel<<<1, 256, 0, sst>>>(blocksums, nblk, task_off + nb);
   KZ_LAUNCHED();
-  scan_add_kernel<<<(unsigned)kz_div_up(nb, 256), 256, 0, st>>>(task_off, (uint32_t*)g_ws.blocksums.p, nb, nullptr);
+  scan_add_kernel<<<(unsigned)kz_div_up(nb, 256), 256, 0, sst>>>(task_off, blocksums, nb, nullptr);
   KZ_LAUNCHED();
-  task_size_scan_kernel<<<1, 32, 0, st>>>(size_hist, T, size_cursor);
+  task_size_scan_kernel<<<1, 32, 0, sst>>>(size_hist, T, size_cursor);
   KZ_LAUNCHED();
   // size_cursor[0] holds the task total and is not used as a cursor (no task has length 0)
-  task_emit_kernel<<<(unsigned)kz_div_up(nb, 256), 256, 0, st>>>(offsets, ostride, ntasks, task_off, (uint32_t)nb, T, size_cursor,
-                                                                (uint32_t*)g_ws.t_start.p, (uint32_t*)g_ws.t_len.p,
-                                                                (uint32_t*)g_ws.t_dest.p);
+  task_emit_kernel<<<(unsigned)kz_div_up(nb, 256), 256, 0, sst>>>(offsets, ostride, ntasks, task_off, (uint32_t)nb, T, size_cursor,
+                                                                (uint32_t*)w.t_start.p, (uint32_t*)w.t_len.p,
+                                                                (uint32_t*)w.t_dest.p);
   KZ_LAUNCHED();
   prof_sort.stop(chunk == 0 ? 1 : 0, (double)n);
+  if (piped) {
+    KZ_CUDA(cudaEventRecord(cx.sort_ev[chunk & 1], sst));
+    KZ_CUDA(cudaStreamWaitEvent(st, cx.sort_ev[chunk & 1], 0));
+  }
+  // ---- accumulate + merge into the shared buckets (main stream)
+  const size_t chunk_tasks = nb + ((size_t)n * W) / T + 1;
   KzProf prof_acc(0);
-  msm_accumulate_kernel<Cfg><<<(unsigned)kz_div_up(max_tasks, 128), 128, 0, st>>>(
-      srs.d_points, entries, (uint32_t*)g_ws.t_start.p, (uint32_t*)g_ws.t_len.p, (uint32_t*)g_ws.t_dest.p, size_cursor,
-      add_existing, (uint32_t*)g_ws.buckets.p, (uint32_t*)g_ws.tparts.p);
+  msm_accumulate_kernel<Cfg><<<(unsigned)kz_div_up(chunk_tasks, 128), 128, 0, st>>>(
+      srs.d_points, entries, (uint32_t*)w.t_start.p, (uint32_t*)w.t_len.p, (uint32_t*)w.t_dest.p, size_cursor,
+      add_existing, (uint32_t*)g_ws.buckets.p, (uint32_t*)w.tparts.p);
   KZ_LAUNCHED();
   prof_acc.stop(chunk == 0 ? 1 : 0, (double)n * W);
   KzProf prof_merge(3);
   msm_merge_kernel<Cfg><<<cx.sm_count * 4, 128, 0, st>>>(ntasks, task_off, multi_count, multi_list, add_existing,
-                                                        (uint32_t*)g_ws.tparts.p, (uint32_t*)g_ws.buckets.p);
+                                                        (uint32_t*)w.tparts.p, (uint32_t*)g_ws.buckets.p);
   KZ_LAUNCHED();
   if (!add_existing) {
     msm_clear_empty_kernel<Cfg><<<(unsigned)kz_div_up(nb, 256), 256, 0, st>>>(ntasks, (uint32_t)nb, (uint32_t*)g_ws.buckets.p);
     KZ_LAUNCHED();
   }
   prof_merge.stop(0, 0.0);
+  if (piped) KZ_CUDA(cudaEventRecord(cx.acc_ev[chunk & 1], st));
   }  // chunks
   KzProf prof_red(3);
   msm_reduce_kernel<Cfg><<<(unsigned)kz_div_up((size_t)cpw * Wb, 128), 128, 0, st>>>((uint32_t*)g_ws.buckets.p, B, CH, cpw, Wb,
@@ -1203,11 +1250,13 @@ int upload_scalars(const uint64_t* scalars, size_t n, uint32_t** d) {
 void kz_msm_release() {
   for (auto& kv : g_srs) cudaFree(kv.second.d_points);
   g_srs.clear();
-  KzScratch* all[] = {&g_ws.counts, &g_ws.offsets, &g_ws.cursor, &g_ws.entries, &g_ws.buckets, &g_ws.partials,
-                      &g_ws.winsums, &g_ws.blocksums, &g_ws.result, &g_ws.flag, &g_ws.scal,
-                      &g_ws.ntasks, &g_ws.task_off, &g_ws.size_hist, &g_ws.t_start, &g_ws.t_len, &g_ws.t_dest, &g_ws.tparts, &g_ws.multi,
-                      &g_ws.sort_tmp, &g_ws.coarse};
+  KzScratch* all[] = {&g_ws.buckets, &g_ws.partials, &g_ws.winsums, &g_ws.result, &g_ws.flag, &g_ws.scal};
   for (auto* s : all) s->release();
+  for (auto& w : g_sw) {
+    KzScratch* per[] = {&w.counts, &w.offsets, &w.cursor, &w.entries, &w.blocksums, &w.ntasks, &w.task_off, &w.size_hist,
+                        &w.t_start, &w.t_len, &w.t_dest, &w.tparts, &w.multi, &w.sort_tmp, &w.coarse};
+    for (auto* s : per) s->release();
+  }
 }
 
 // used by poly.cu (open): MSM of device-resident scalars against a handle
