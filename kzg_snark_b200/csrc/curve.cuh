@@ -91,6 +91,38 @@ template <class P> HD void xyzz_madd(XYZZ<P>& acc, const Affine<P>& b) {
   acc.x = X3; acc.y = Y3;
 }
 
+// acc += b (canonical affine) with the accumulator's coordinates kept semi-reduced in [0, 2p) (field.cuh, FeLz<P>::ok):
+// same formulas and special cases as xyzz_madd, every product without its final conditional subtraction.  acc.zz is a
+// product of non-zero factors unless it was set to exactly 0 (infinity), so the exact-zero test still identifies infinity;
+// the difference Pd can be 0 or p when the x-coordinates agree.  The caller folds the result with xyzz_reduce_lz.
+template <class P> HD void xyzz_madd_lz(XYZZ<P>& acc, const Affine<P>& b) {
+  if (aff_is_inf<P>(b)) return;
+  if (xyzz_is_inf<P>(acc)) { acc = xyzz_from_affine<P>(b); return; }
+  Fe<P> U2 = fe_mul_lz<P>(b.x, acc.zz);
+  Fe<P> S2 = fe_mul_lz<P>(b.y, acc.zzz);
+  Fe<P> Pd = fe_sub_lz<P>(U2, acc.x);
+  Fe<P> Rd = fe_sub_lz<P>(S2, acc.y);
+  if (fe_is_zero_lz<P>(Pd)) {
+    if (fe_is_zero_lz<P>(Rd)) acc = xyzz_dbl_affine<P>(b);
+    else acc = xyzz_inf<P>();
+    return;
+  }
+  Fe<P> PP = fe_mul_lz<P>(Pd, Pd);
+  Fe<P> PPP = fe_mul_lz<P>(Pd, PP);
+  Fe<P> Q = fe_mul_lz<P>(acc.x, PP);
+  Fe<P> X3 = fe_sub_lz<P>(fe_sub_lz<P>(fe_sub_lz<P>(fe_mul_lz<P>(Rd, Rd), PPP), Q), Q);
+  Fe<P> Y3 = fe_sub_lz<P>(fe_mul_lz<P>(Rd, fe_sub_lz<P>(Q, X3)), fe_mul_lz<P>(acc.y, PPP));
+  acc.zz = fe_mul_lz<P>(acc.zz, PP);
+  acc.zzz = fe_mul_lz<P>(acc.zzz, PPP);
+  acc.x = X3; acc.y = Y3;
+}
+
+template <class P> HD XYZZ<P> xyzz_reduce_lz(const XYZZ<P>& a) {
+  XYZZ<P> r;
+  r.x = fe_reduce_lz<P>(a.x); r.y = fe_reduce_lz<P>(a.y); r.zz = fe_reduce_lz<P>(a.zz); r.zzz = fe_reduce_lz<P>(a.zzz);
+  return r;
+}
+
 // a + b, both XYZZ.  add-2008-s (12M + 2S) with special cases.
 template <class P> HD XYZZ<P> xyzz_add(const XYZZ<P>& a, const XYZZ<P>& b) {
   if (xyzz_is_inf<P>(a)) return b;

@@ -116,7 +116,8 @@ template <class P> HD void fe_redc_row(uint32_t* E, uint32_t* O, const uint32_t*
   Mp<N>::mad_even(E, mod, m, O[N - 1]);
 }
 
-template <class P> HD Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
+// Montgomery product without the final conditional subtraction: t = (a*b + m*p) / 2^(32N) < a*b / 2^(32N) + p
+template <class P> HD void fe_mul_nofinal(uint32_t* t, const Fe<P>& a, const Fe<P>& b) {
   constexpr int N = P::N;
   uint32_t mod[N], E[N], O[N];
   fe_load_mod<P>(mod);
@@ -137,10 +138,91 @@ template <class P> HD Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
     }
   }
   // N is even: after the last (odd) row the even-aligned accumulator is O, with O[0] == 0
-  uint32_t t[N];
   Mp<N>::merge(t, E, O);
+}
+
+template <class P> HD Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
+  uint32_t t[P::N];
+  fe_mul_nofinal<P>(t, a, b);
   Fe<P> r;
   fe_final_sub<P>(r.v, t);
+  return r;
+}
+
+// ---- lazy ("semi-reduced") arithmetic: values in [0, 2p).  Usable when 4p <= 2^(32N) (BN254 p and r, BLS12-381 p; not
+// BLS12-381 r): for a, b < 2p the Montgomery product is < 4p^2 / 2^(32N) + p <= 2p, so the final conditional subtraction
+// (17 ALU instructions of ~200) can be dropped; for a < 4p and a canonical b < p it is < 2p as well.  The running value of
+// the row loop stays < (a + p) * 2^32 < 2^(32(N+1)), so no carry is lost.  Additions and subtractions fold back into
+// [0, 2p) at the cost of the canonical ones; the *_nr forms skip that when the result only feeds a multiplication.
+template <class P> struct FeLz { static constexpr bool ok = (P::mod(P::N - 1) >> 30) == 0; };
+
+template <class P> HD void fe_load_mod2(uint32_t* m) {
+#pragma unroll
+  for (int i = 0; i < P::N; i++) m[i] = (P::mod(i) << 1) | (i ? (P::mod(i > 0 ? i - 1 : 0) >> 31) : 0u);
+}
+
+template <class P> HD Fe<P> fe_mul_lz(const Fe<P>& a, const Fe<P>& b) {
+  Fe<P> r;
+  fe_mul_nofinal<P>(r.v, a, b);
+  return r;
+}
+
+// a, b < 2p -> a + b folded into [0, 2p)
+template <class P> HD Fe<P> fe_add_lz(const Fe<P>& a, const Fe<P>& b) {
+  constexpr int N = P::N;
+  uint32_t s[N], m[N], t[N];
+  Mp<N>::add_cc(s, a.v, b.v);          // < 4p <= 2^(32N): no carry out
+  fe_load_mod2<P>(m);
+  uint32_t borrow = Mp<N>::sub_cc(t, s, m);
+  Fe<P> r;
+#pragma unroll
+  for (int i = 0; i < N; i++) r.v[i] = borrow ? s[i] : t[i];
+  return r;
+}
+
+// a, b < 2p -> a - b folded into [0, 2p)
+template <class P> HD Fe<P> fe_sub_lz(const Fe<P>& a, const Fe<P>& b) {
+  constexpr int N = P::N;
+  uint32_t d[N], m[N];
+  uint32_t borrow = Mp<N>::sub_cc(d, a.v, b.v);
+  fe_load_mod2<P>(m);
+#pragma unroll
+  for (int i = 0; i < N; i++) m[i] &= borrow;
+  Fe<P> r;
+  Mp<N>::add_cc(r.v, d, m);
+  return r;
+}
+
+// a, b < 2p -> a + b < 4p, not folded (multiplication operand only)
+template <class P> HD Fe<P> fe_add_nr(const Fe<P>& a, const Fe<P>& b) {
+  Fe<P> r;
+  Mp<P::N>::add_cc(r.v, a.v, b.v);
+  return r;
+}
+
+// a, b < 2p -> a - b + 2p in (0, 4p), not folded (multiplication operand only)
+template <class P> HD Fe<P> fe_sub_nr(const Fe<P>& a, const Fe<P>& b) {
+  constexpr int N = P::N;
+  uint32_t m[N], t[N];
+  fe_load_mod2<P>(m);
+  Mp<N>::add_cc(t, a.v, m);            // < 4p: no carry out
+  Fe<P> r;
+  Mp<N>::sub_cc(r.v, t, b.v);
+  return r;
+}
+
+// x < 2p is a multiple of p
+template <class P> HD bool fe_is_zero_lz(const Fe<P>& a) {
+  uint32_t o0 = 0, o1 = 0;
+#pragma unroll
+  for (int i = 0; i < P::N; i++) { o0 |= a.v[i]; o1 |= a.v[i] ^ P::mod(i); }
+  return o0 == 0 || o1 == 0;
+}
+
+// x < 2p -> canonical
+template <class P> HD Fe<P> fe_reduce_lz(const Fe<P>& a) {
+  Fe<P> r;
+  fe_final_sub<P>(r.v, a.v);
   return r;
 }
 

@@ -488,7 +488,7 @@ __global__ void task_emit_kernel(const uint32_t* __restrict__ offsets, uint32_t 
 // one thread per task: XYZZ accumulator in registers, points gathered through the sorted index;
 // the next point is fetched while the current mixed addition runs
 template <class Cfg>
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __restrict__ points,
+__global__ void __launch_bounds__(128, (Cfg::Fp::N == 8 ? 4 : 1)) msm_accumulate_kernel(const uint32_t* __restrict__ points,
                                                             const uint32_t* __restrict__ entries,
                                                             const uint32_t* __restrict__ t_start, const uint32_t* __restrict__ t_len,
                                                             const uint32_t* __restrict__ t_dest, const uint32_t* __restrict__ n_tasks,
@@ -512,8 +512,10 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __r
       nneg = ent >> 31;
     }
     if (neg) pt.y = fe_neg<P>(pt.y);
-    xyzz_madd<P>(acc, pt);
+    // 254/381-bit base fields: accumulator coordinates semi-reduced in [0, 2p) inside the loop (curve.cuh), folded once below
+    if constexpr (FeLz<P>::ok) xyzz_madd_lz<P>(acc, pt); else xyzz_madd<P>(acc, pt);
   }
+  if constexpr (FeLz<P>::ok) acc = xyzz_reduce_lz<P>(acc);
   if (dest >> 31) st_xyzz<P>(buckets, dest & 0x7fffffffu, acc);
   else st_xyzz<P>(partials, dest, acc);
 }

@@ -41,6 +41,7 @@ struct NttPassArgs {
   uint32_t nd;
   uint32_t dpack;         // layer widths, 2 bits each (kept out of an array: no local-memory indexing)
   uint32_t blk0;          // first column tile of this launch (column-slab launches of the host-buffer entry point)
+  uint32_t lazy, last;    // compile-time-shape kernels: values semi-reduced in [0, 2r) between passes; last pass folds them
 };
 
 __device__ __forceinline__ uint32_t layer_width(uint32_t dpack, uint32_t s) { return (dpack >> (2 * s)) & 3u; }
@@ -234,6 +235,62 @@ __global__ void __launch_bounds__(kThreads, 4) ntt_pass_kernel(NttPassArgs a, Nt
   }
 }
 
+// ---- arithmetic policy of the compile-time-shape kernels.  LZ (fields with 4r <= 2^256, i.e. BN254 r): data stays
+// semi-reduced in [0, 2r) in shared memory and between passes, products skip their final conditional subtraction and
+// sums / differences that only feed a constant multiplication are not folded (field.cuh); the last pass folds once.
+template <class P, bool LZ> struct Ar {
+  static __device__ __forceinline__ Fe<P> mul(const Fe<P>& a, const Fe<P>& b) {
+    if constexpr (LZ) return fe_mul_lz<P>(a, b); else return fe_mul<P>(a, b);
+  }
+  static __device__ __forceinline__ Fe<P> add(const Fe<P>& a, const Fe<P>& b) {
+    if constexpr (LZ) return fe_add_lz<P>(a, b); else return fe_add<P>(a, b);
+  }
+  static __device__ __forceinline__ Fe<P> sub(const Fe<P>& a, const Fe<P>& b) {
+    if constexpr (LZ) return fe_sub_lz<P>(a, b); else return fe_sub<P>(a, b);
+  }
+  static __device__ __forceinline__ Fe<P> add_m(const Fe<P>& a, const Fe<P>& b) {      // result is multiplied next
+    if constexpr (LZ) return fe_add_nr<P>(a, b); else return fe_add<P>(a, b);
+  }
+  static __device__ __forceinline__ Fe<P> sub_m(const Fe<P>& a, const Fe<P>& b) {
+    if constexpr (LZ) return fe_sub_nr<P>(a, b); else return fe_sub<P>(a, b);
+  }
+};
+
+// 4-point DFT; M: outputs 1..3 are multiplied by constants next (left unfolded under LZ)
+template <class P, bool LZ, bool M> __device__ __forceinline__ void dft4_t(Fe<P>* x, const NttConsts<P>& c) {
+  using A = Ar<P, LZ>;
+  Fe<P> s0 = A::add(x[0], x[2]), d0 = A::sub(x[0], x[2]);
+  Fe<P> s1 = A::add(x[1], x[3]);
+  Fe<P> t = A::mul(A::sub_m(x[1], x[3]), c.w4);
+  x[0] = A::add(s0, s1);
+  if constexpr (M) { x[1] = A::add_m(d0, t); x[2] = A::sub_m(s0, s1); x[3] = A::sub_m(d0, t); }
+  else { x[1] = A::add(d0, t); x[2] = A::sub(s0, s1); x[3] = A::sub(d0, t); }
+}
+
+template <class P, int D, bool LZ> __device__ __forceinline__ void dft_small_t(Fe<P>* x, const NttConsts<P>& c) {
+  using A = Ar<P, LZ>;
+  if constexpr (D == 1) {
+    Fe<P> s = A::add(x[0], x[1]);
+    x[1] = A::sub(x[0], x[1]);
+    x[0] = s;
+  } else if constexpr (D == 2) {
+    dft4_t<P, LZ, false>(x, c);
+  } else {
+    Fe<P> e[4] = {x[0], x[2], x[4], x[6]};
+    Fe<P> o[4] = {x[1], x[3], x[5], x[7]};
+    dft4_t<P, LZ, false>(e, c);
+    dft4_t<P, LZ, true>(o, c);
+    o[1] = A::mul(o[1], c.w8);
+    o[2] = A::mul(o[2], c.w4);
+    o[3] = A::mul(o[3], c.w8_3);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      x[i] = A::add(e[i], o[i]);
+      x[i + 4] = A::sub(e[i], o[i]);
+    }
+  }
+}
+
 // ---- compile-time shapes: R = 2^B with a full 1024-element tile (B = 6..9, C = 2^(10-B) columns).  Same algorithm and
 // shared-memory layout as ntt_pass_kernel; with B fixed every plane stride, digit width and swizzle shift is an immediate and
 // the digit loops fold away (the generic kernel spends ~15 % of its instructions on that address arithmetic).
@@ -245,7 +302,7 @@ template <int B> struct NttShape {
   static constexpr int off(int li) { return B - done(li) - width(li); }
 };
 
-template <class P, int B, int LI>
+template <class P, int B, int LI, bool LZ>
 __device__ __forceinline__ void ntt_layer_c(uint32_t* sm, const uint32_t* smw, const NttConsts<P>& c) {
   using S = NttShape<B>;
   constexpr int D = S::width(LI), OFF = S::off(LI), DONE = S::done(LI), LOGC = S::LOGC;
@@ -279,10 +336,10 @@ __device__ __forceinline__ void ntt_layer_c(uint32_t* sm, const uint32_t* smw, c
 #pragma unroll
       for (int u = 1; u < (1 << D); u++) {
         uint32_t e = ((uint32_t)u << OFF) * V;
-        x[u] = fe_mul<P>(x[u], sm_ld<P>(smw, 1u << B, e));
+        x[u] = Ar<P, LZ>::mul(x[u], sm_ld<P>(smw, 1u << B, e));
       }
     }
-    dft_small<P, D>(x, c);
+    dft_small_t<P, D, LZ>(x, c);
 #pragma unroll
     for (int u = 0; u < (1 << D); u++) {
       uint32_t l = base_l | ((uint32_t)u << OFF);
@@ -291,7 +348,7 @@ __device__ __forceinline__ void ntt_layer_c(uint32_t* sm, const uint32_t* smw, c
   }
 }
 
-template <class P, int B>
+template <class P, int B, bool LZ>
 __global__ void __launch_bounds__(kThreads, 4) ntt_pass_kernel_c(NttPassArgs a, NttConsts<P> c) {
   using S = NttShape<B>;
   constexpr int LOGC = S::LOGC;
@@ -317,16 +374,16 @@ __global__ void __launch_bounds__(kThreads, 4) ntt_pass_kernel_c(NttPassArgs a, 
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       uint32_t o = o0 + k * kThreads;
-      if (a.bnd) v[k] = fe_mul<P>(v[k], tw[k]);
+      if (a.bnd) v[k] = Ar<P, LZ>::mul(v[k], tw[k]);
       sm_st<P>(sm, tile, swz(o, LOGC), v[k]);
     }
   }
   __syncthreads();
 
-  ntt_layer_c<P, B, 0>(sm, smw, c);
+  ntt_layer_c<P, B, 0, LZ>(sm, smw, c);
   __syncthreads();
-  if constexpr (S::ND > 1) { ntt_layer_c<P, B, 1>(sm, smw, c); __syncthreads(); }
-  if constexpr (S::ND > 2) { ntt_layer_c<P, B, 2>(sm, smw, c); __syncthreads(); }
+  if constexpr (S::ND > 1) { ntt_layer_c<P, B, 1, LZ>(sm, smw, c); __syncthreads(); }
+  if constexpr (S::ND > 2) { ntt_layer_c<P, B, 2, LZ>(sm, smw, c); __syncthreads(); }
 
   const uint32_t logCm = (uint32_t)LOGC < a.logK ? (uint32_t)LOGC : a.logK;
 #pragma unroll 1
@@ -348,19 +405,49 @@ __global__ void __launch_bounds__(kThreads, 4) ntt_pass_kernel_c(NttPassArgs a, 
       kr >>= dd;
     }
     Fe<P> v = sm_ld<P>(sm, tile, swz((l << LOGC) | cc, LOGC));
-    if (a.post) v = fe_mul<P>(v, ldg_fe<P>(a.post + (size_t)kt * P::N));
+    if (a.post) v = fe_mul<P>(v, ldg_fe<P>(a.post + (size_t)kt * P::N));      // only on the last pass: canonical result
+    else if (LZ && a.last) v = fe_reduce_lz<P>(v);
     st_fe<P>(a.out + (boff + (((jlo << B) + kt) << a.logK) + kk) * P::N, v);
   }
 }
 
+// a pass runs on the compile-time-shape kernel when its tile is full (1024 elements) and R = 2^6..2^9
+inline bool pass_is_full(uint32_t b, uint32_t logC) { return b + logC == (uint32_t)kLogTile && b >= 6 && b <= 9; }
+
+template <class P, bool LZ>
+void launch_pass_c(const NttPassArgs& a, const NttConsts<P>& c, dim3 grid, size_t smem, cudaStream_t st) {
+  if (a.b == 9) ntt_pass_kernel_c<P, 9, LZ><<<grid, kThreads, smem, st>>>(a, c);
+  else if (a.b == 8) ntt_pass_kernel_c<P, 8, LZ><<<grid, kThreads, smem, st>>>(a, c);
+  else if (a.b == 7) ntt_pass_kernel_c<P, 7, LZ><<<grid, kThreads, smem, st>>>(a, c);
+  else ntt_pass_kernel_c<P, 6, LZ><<<grid, kThreads, smem, st>>>(a, c);
+}
+
 template <class P>
 void launch_pass(const NttPassArgs& a, const NttConsts<P>& c, dim3 grid, uint32_t threads, size_t smem, cudaStream_t st) {
-  const bool full = a.b + a.logC == (uint32_t)kLogTile && threads == (uint32_t)kThreads && a.nd > 1;
-  if (full && a.b == 9) ntt_pass_kernel_c<P, 9><<<grid, threads, smem, st>>>(a, c);
-  else if (full && a.b == 8) ntt_pass_kernel_c<P, 8><<<grid, threads, smem, st>>>(a, c);
-  else if (full && a.b == 7) ntt_pass_kernel_c<P, 7><<<grid, threads, smem, st>>>(a, c);
-  else if (full && a.b == 6) ntt_pass_kernel_c<P, 6><<<grid, threads, smem, st>>>(a, c);
-  else ntt_pass_kernel<P><<<grid, threads, smem, st>>>(a, c);
+  if (pass_is_full(a.b, a.logC)) {
+    if constexpr (FeLz<P>::ok) {
+      if (a.lazy) { launch_pass_c<P, true>(a, c, grid, smem, st); return; }
+    }
+    launch_pass_c<P, false>(a, c, grid, smem, st);
+    return;
+  }
+  (void)threads;
+  ntt_pass_kernel<P><<<grid, threads, smem, st>>>(a, c);
+}
+
+template <class P, int B, bool LZ> int set_pass_smem() {
+  KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel_c<P, B, LZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 * 4 << kLogTile) + (32 << kMaxB)));
+  return 0;
+}
+template <class P> int set_all_pass_smem() {
+  int rc;
+  if ((rc = set_pass_smem<P, 6, false>()) || (rc = set_pass_smem<P, 7, false>()) || (rc = set_pass_smem<P, 8, false>()) ||
+      (rc = set_pass_smem<P, 9, false>())) return rc;
+  if constexpr (FeLz<P>::ok) {
+    if ((rc = set_pass_smem<P, 6, true>()) || (rc = set_pass_smem<P, 7, true>()) || (rc = set_pass_smem<P, 8, true>()) ||
+        (rc = set_pass_smem<P, 9, true>())) return rc;
+  }
+  return 0;
 }
 
 template <class P> __device__ Fe<P> fe_pow_u64(Fe<P> base, uint64_t e) {
@@ -529,17 +616,11 @@ int run_plan(const NttPlan& pl, uint32_t* d_data, size_t batch, const NttHostIo*
   if (!attr_set) {
     KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<FrBN254>, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 * 4 << kLogTile) + (32 << kMaxB)));
     KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<FrBLS381>, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 * 4 << kLogTile) + (32 << kMaxB)));
-    const int smax = (8 * 4 << kLogTile) + (32 << kMaxB);
-    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel_c<FrBN254, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel_c<FrBN254, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel_c<FrBN254, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel_c<FrBN254, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel_c<FrBLS381, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel_c<FrBLS381, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel_c<FrBLS381, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-    KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel_c<FrBLS381, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+    { int rc2; if ((rc2 = set_all_pass_smem<FrBN254>()) || (rc2 = set_all_pass_smem<FrBLS381>())) return rc2; }
     attr_set = true;
   }
+  bool lazy = FeLz<P>::ok && !getenv("KZGPU_NTT_STRICT");
+  for (size_t i = 0; i < m; i++) lazy = lazy && pass_is_full(pl.passes[i].b, pl.passes[i].logC);   // every pass must speak [0, 2r)
   const uint32_t* src = d_data;
   for (size_t i = 0; i < m; i++) {
     const PassPlan& pp = pl.passes[i];
@@ -553,6 +634,7 @@ int run_plan(const NttPlan& pl, uint32_t* d_data, size_t batch, const NttHostIo*
     a.dpack = 0;
     for (uint32_t k = 0; k < pp.nd; k++) a.dpack |= pp.d[k] << (2 * k);
     a.blk0 = 0;
+    a.lazy = lazy ? 1u : 0u; a.last = (i == m - 1) ? 1u : 0u;
     uint32_t tile = 1u << (pp.b + pp.logC);
     uint32_t threads = tile / 8 < 32 ? 32 : (tile / 8 > (uint32_t)kThreads ? kThreads : tile / 8);
     const uint32_t tiles = (uint32_t)(1ull << (pp.logQ - pp.logC));

@@ -40,6 +40,17 @@ template <class P> void field_op(const std::string& op, std::istringstream& in) 
   else if (op == "add") r = fe_add<P>(x, y);
   else if (op == "sub") r = fe_sub<P>(x, y);
   else if (op == "rawmul") { std::cout << hex<P>(fe_mul<P>(parse<P>(a), parse<P>(b))) << "\n"; return; }
+  else if (op == "lzmul" || op == "lzadd" || op == "lzsub" || op == "nradd" || op == "nrsub") {
+    // raw limbs in, raw limbs out (no Montgomery conversion): the semi-reduced primitives of field.cuh
+    Fe<P> u = parse<P>(a), v = parse<P>(b), w;
+    if (op == "lzmul") w = fe_mul_lz<P>(u, v);
+    else if (op == "lzadd") w = fe_add_lz<P>(u, v);
+    else if (op == "lzsub") w = fe_sub_lz<P>(u, v);
+    else if (op == "nradd") w = fe_add_nr<P>(u, v);
+    else w = fe_sub_nr<P>(u, v);
+    std::cout << hex<P>(w) << " " << (fe_is_zero_lz<P>(w) ? 1 : 0) << " " << hex<P>(fe_reduce_lz<P>(w)) << "\n";
+    return;
+  }
   std::cout << U<P>(r) << "\n";
 }
 template <class P> void curve_op(const std::string& op, std::istringstream& in) {
@@ -53,6 +64,21 @@ template <class P> void curve_op(const std::string& op, std::istringstream& in) 
     r = xyzz_from_affine<P>(a);
     // push acc off Z=1 so the general formulas are exercised: acc = 2a - a when a finite
     xyzz_madd<P>(r, b);
+  } else if (op == "lzchain") {   // ((2a + b) + b) - b ... with the semi-reduced mixed addition, folded at the end
+    in >> x2 >> y2;
+    Affine<P> b; b.x = M<P>(x2); b.y = M<P>(y2);
+    r = xyzz_dbl_affine<P>(a);
+    xyzz_madd_lz<P>(r, b);
+    xyzz_madd_lz<P>(r, b);
+    xyzz_madd_lz<P>(r, aff_neg<P>(a));
+    xyzz_madd_lz<P>(r, aff_neg<P>(b));
+    r = xyzz_reduce_lz<P>(r);       // = a + b
+  } else if (op == "lzmadd") {
+    in >> x2 >> y2;
+    Affine<P> b; b.x = M<P>(x2); b.y = M<P>(y2);
+    r = xyzz_from_affine<P>(a);
+    xyzz_madd_lz<P>(r, b);
+    r = xyzz_reduce_lz<P>(r);
   } else if (op == "add3") {       // (a + b) + b via full add of two non-trivial-Z points
     in >> x2 >> y2;
     Affine<P> b; b.x = M<P>(x2); b.y = M<P>(y2);

@@ -92,6 +92,60 @@ def test_csrc_field_and_curve_formulas_on_host(host_arith):
     assert not bad, bad[:3]
 
 
+def test_csrc_semi_reduced_arithmetic_on_host(host_arith):
+    """The [0, 2p) primitives (field.cuh: fe_mul_lz, fe_add_lz, fe_sub_lz, *_nr) and the semi-reduced mixed addition
+    (curve.cuh: xyzz_madd_lz) against Python integers: bounds, residues, zero test, fold -- for the three moduli
+    with 4p <= 2^(32N), at the extremes of the ranges."""
+    rng = random.Random(11)
+    lines, expect = [], []
+    F = {"fp_bn": (CURVES["bn254"]["p"], 256), "fr_bn": (CURVES["bn254"]["r"], 256), "fp_bls": (CURVES["bls12_381"]["p"], 384)}
+    for f, (q, bits) in F.items():
+        assert 4 * q <= 1 << bits
+        Rinv = pow(1 << bits, -1, q)
+        lo = [0, 1, q - 1, q, q + 1, 2 * q - 1] + [rng.randrange(2 * q) for _ in range(30)]
+        hi = [2 * q, 3 * q, 4 * q - 1] + [rng.randrange(4 * q) for _ in range(20)]
+        canon = [0, 1, q - 1] + [rng.randrange(q) for _ in range(20)]
+        pairs = [(rng.choice(lo), rng.choice(lo)) for _ in range(200)] + [(rng.choice(hi), rng.choice(canon)) for _ in range(200)]
+        pairs += [(2 * q - 1, 2 * q - 1), (4 * q - 1, q - 1), (q, q), (q, 0)]
+        for a, b in pairs:
+            lines.append(f"{f} lzmul {a:x} {b:x}"); expect.append(("mul", q, a * b * Rinv % q, None))
+        for _ in range(200):
+            a, b = rng.choice(lo), rng.choice(lo)
+            lines.append(f"{f} lzadd {a:x} {b:x}"); expect.append(("fold", q, (a + b) % q, None))
+            lines.append(f"{f} lzsub {a:x} {b:x}"); expect.append(("fold", q, (a - b) % q, None))
+            lines.append(f"{f} nradd {a:x} {b:x}"); expect.append(("exact", q, (a + b) % q, a + b))
+            lines.append(f"{f} nrsub {a:x} {b:x}"); expect.append(("exact", q, (a - b) % q, a - b + 2 * q))
+    n_field = len(lines)
+    for cn, tag in (("bn254", "bn"), ("bls12_381", "bls")):
+        c = get_curve(cn)
+        aff = lambda pt: (0, 0) if c.normalize(pt) is None else c.normalize(pt)
+        pts = [aff(c.multiply(c.G1, rng.randrange(1, c.r))) for _ in range(4)]
+        for _ in range(10):
+            a, b = rng.choice(pts), rng.choice(pts)
+            for A, B in ((a, b), (a, a), (a, (a[0], (-a[1]) % c.p)), (a, (0, 0)), ((0, 0), b)):
+                pa = (A[0], A[1], 1) if A != (0, 0) else c.Z1
+                pb = (B[0], B[1], 1) if B != (0, 0) else c.Z1
+                e = aff(c.add(pa, pb))
+                lines.append(f"{tag} lzmadd {A[0]:x} {A[1]:x} {B[0]:x} {B[1]:x}"); expect.append("%x %x" % e)
+                if A != (0, 0) and B != (0, 0):
+                    lines.append(f"{tag} lzchain {A[0]:x} {A[1]:x} {B[0]:x} {B[1]:x}"); expect.append("%x %x" % e)
+    out = subprocess.run([host_arith], input="\n".join(lines) + "\n", capture_output=True, text=True).stdout.split("\n")
+    for i, (l, e, o) in enumerate(zip(lines, expect, out)):
+        if i >= n_field:
+            assert o == e, (l, e, o)
+            continue
+        kind, q, residue, exact = e
+        raw, is_zero, folded = o.split()
+        raw, folded = int(raw, 16), int(folded, 16)
+        assert raw % q == residue, l
+        if kind == "exact":
+            assert raw == exact, l
+        else:
+            assert raw < 2 * q, l                                     # stays semi-reduced
+            assert int(is_zero) == (1 if residue == 0 else 0), l
+            assert folded == residue, l
+
+
 def test_sageshim_field_and_polynomials():
     from kzg_snark_b200.sageshim import GF, PolynomialRing
     r = CURVES["bn254"]["r"]
