@@ -361,7 +361,10 @@ def run_gpu(args):
             step_resident()
         _ffi.profile_enable(False)
         prof = {k: _ffi.profile_get(i) for k, i in (("accumulate", 0), ("sort", 2), ("reduce", 3))}
-        # e2e: host (pinned) scalars in, affine point out, every step
+        # e2e: host (pinned) scalars in, affine point out, every step (warmed up like the resident region: the chunked
+        # entry point allocates its staging buffer and second sort workspace on first use)
+        for _ in range(Wm):
+            step_e2e()
         barrier()
         t0 = time.perf_counter()
         for _ in range(K):
@@ -427,6 +430,8 @@ def run_gpu(args):
             device.ntt_dev("bn254", d, n_total, wl)
         _ffi.profile_enable(False)
         pr = _ffi.profile_get(1)
+        for _ in range(Wm):                                     # warm-up of the host-buffer entry point (staging buffer, events)
+            device.ntt("bn254", pinned.array, wl)
         barrier()
         t0 = time.perf_counter()
         for _ in range(K):
@@ -443,7 +448,7 @@ def run_gpu(args):
                     "h2d_bytes_per_step": n_total * 32 * world, "d2h_bytes_per_step": n_total * 32 * world,
                     "ms_per_step": ms_e2e / K, "host_buffers": "pinned (cudaHostAlloc)"},
             "roofline": {
-                "bound": "hbm", "kernel": "ntt_pass_kernel (all passes of one transform)",
+                "bound": "hbm", "kernel": "ntt_pass_kernel_c<FrBN254, 8, lazy> (all passes of one transform)",
                 "achieved": hbm, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": hbm / peaks.get("hbm_gbs"),
                 "traffic": load_traffic("ntt_pass_kernel") if args.logn == 24 else None, "peak_source": peak_src,
                 "model": "SURVEY 8(d): algorithmic bytes = 2 x 32 B x n (twiddles not counted)",

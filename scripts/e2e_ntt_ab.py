@@ -7,10 +7,12 @@ import sys
 import time
 
 if len(sys.argv) == 1:
-    for mode in ("plain", "overlap", "plain", "overlap"):
+    for mode in ("plain", "overlap", "strict", "plain", "overlap", "strict"):
         env = dict(os.environ)
         if mode == "plain":
             env["KZGPU_NTT_NO_OVERLAP"] = "1"
+        if mode == "strict":                                  # overlap, canonical values between passes
+            env["KZGPU_NTT_STRICT"] = "1"
         r = subprocess.run([sys.executable, __file__, mode], env=env, capture_output=True, text=True)
         print(r.stdout.strip(), r.stderr.strip()[-300:], flush=True)
     sys.exit(0)
