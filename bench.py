@@ -288,7 +288,11 @@ def run_gpu(args):
         n = n_total                           # weak: per-GPU work fixed
     start = rank * n
     if world > 1:
-        _ffi.set_stream(torch.cuda.current_stream().cuda_stream)
+        # one stream for torch (NCCL's wait lands on the current stream) and the library, so that the fold of the gathered
+        # partials is ordered after the all-gather.  It must be a side stream: torch's default stream has handle 0, which
+        # kzgpu_set_stream reads as "back to the library's own stream".
+        from kzg_snark_b200.parallel import share_stream_with_torch
+        side = share_stream_with_torch()                      # noqa: F841  (kept alive for the life of the run)
 
     def barrier():
         if dist is not None:
@@ -334,24 +338,21 @@ def run_gpu(args):
             return step_resident()
 
         for _ in range(Wm):
+            if world > 1:
+                gathered.zero_()                                 # a fold that ran ahead of the all-gather would see infinity
             out, inf = step_resident()
-        assert not inf and on_curve_bn254(out), "MSM result is not a curve point"
+            assert not inf and on_curve_bn254(out), "MSM result is not a curve point"
         # timed region: resident inputs, device clock
         sampler = ClockSampler(local)
         barrier()
         l0 = _ffi.launch_count()
-        if world == 1:
-            _ffi.timer_start()
-            for _ in range(K):
-                step_resident()
-            ms = _ffi.timer_stop()
-        else:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(K):
-                step_resident()
-            e1.record(); e1.synchronize()
-            ms = e0.elapsed_time(e1)
+        # CUDA events on the stream the library launches on (its own non-blocking stream: torch.cuda.Event on torch's
+        # current stream would not see these kernels); at N > 1 every step ends with the host-synchronous fold of the
+        # gathered partials, so the bracket covers the NCCL all-gather too
+        _ffi.timer_start()
+        for _ in range(K):
+            step_resident()
+        ms = _ffi.timer_stop()
         barrier()
         launches = _ffi.launch_count() - l0
         ms = max_over_ranks(ms)
@@ -411,17 +412,10 @@ def run_gpu(args):
         sampler = ClockSampler(local)
         barrier()
         l0 = _ffi.launch_count()
-        _ffi.timer_start() if world == 1 else None
-        if world > 1:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+        _ffi.timer_start()                                      # events on the library's launching stream, any world size
         for _ in range(K):
             device.ntt_dev("bn254", d, n_total, wl)
-        if world == 1:
-            ms = _ffi.timer_stop()
-        else:
-            e1.record(); e1.synchronize()
-            ms = e0.elapsed_time(e1)
+        ms = _ffi.timer_stop()
         barrier()
         launches = _ffi.launch_count() - l0
         ms = max_over_ranks(ms)

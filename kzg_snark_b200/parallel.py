@@ -66,10 +66,24 @@ def all_gather_bytes(local, world, dist, device="cpu"):
     return out.view(world, local.numel())
 
 
+def share_stream_with_torch():
+    """Put torch (and with it NCCL's completion wait) and the library on ONE side stream, so that library kernels that read
+    a collective's output are ordered after it.  torch's default stream will not do: its handle is 0, which
+    kzgpu_set_stream reads as "back to the library's own non-blocking stream" -- and that stream is not ordered against
+    the legacy default stream.  Call once per process, after torch.cuda.set_device."""
+    import torch
+    from . import _ffi
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    _ffi.set_stream(side.cuda_stream)
+    return side
+
+
 def sharded_msm_step(srs_shard, d_scalars, n_local, curve_id, dist, partial, gathered):
     """One point-sharded MSM on the GPU path: partial (device) -> NCCL all-gather -> fold.
     `partial` / `gathered` are pre-allocated CUDA uint8 tensors (XYZZ_BYTES, world*XYZZ_BYTES).
-    Returns (affine limbs, is_inf) on every rank."""
+    Returns (affine limbs, is_inf) on every rank.  Requires share_stream_with_torch() (the fold must not run ahead of
+    the all-gather)."""
     from . import device
     device.msm_partial_dev(srs_shard, d_scalars, n_local, _Raw(partial.data_ptr()))
     dist.all_gather_into_tensor(gathered, partial)
