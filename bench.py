@@ -334,8 +334,9 @@ def run_gpu(args):
         def step_e2e():
             if world == 1:
                 return device.msm(srs, pinned.array)       # H2D of the scalars inside the call
-            dsc.upload(pinned.array)
-            return step_resident()
+            device.msm_partial(srs, pinned.array, RawPtr(partial.data_ptr()))     # this rank's H2D inside the call, overlapped
+            dist.all_gather_into_tensor(gathered, partial)
+            return device.g1_fold("bn254", RawPtr(gathered.data_ptr()), world)
 
         for _ in range(Wm):
             if world > 1:

@@ -108,6 +108,10 @@ int kzgpu_msm_batch_dev(uint64_t handle, const uint64_t* d_scalars, size_t poly_
  * Montgomery form (4 * fp_limbs64 limbs), to be all-gathered and folded by kzgpu_g1_fold. */
 int kzgpu_msm_partial_dev(uint64_t handle, size_t first, const uint64_t* d_scalars, size_t n,
                           uint64_t* d_out_xyzz);
+/* same with this rank's slice of the scalars in host memory (the multi-GPU form of kzgpu_msm: kzg.py:112-116 over an
+ * index range, upload chunked and overlapped with the compute); the partial stays on the device for the all-gather */
+int kzgpu_msm_partial(uint64_t handle, size_t first, const uint64_t* scalars, size_t n,
+                      uint64_t* d_out_xyzz);
 /* sum of `count` XYZZ partials (device) -> canonical affine on the host */
 int kzgpu_g1_fold(int curve, const uint64_t* d_xyzz, size_t count,
                   uint64_t* out_affine_xy, int* is_inf);

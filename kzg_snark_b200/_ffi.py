@@ -65,6 +65,7 @@ SIGNATURES = {
     "kzgpu_msm_batch": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_void_p, _szp, ctypes.c_size_t, ctypes.c_void_p, _intp]),
     "kzgpu_msm_batch_dev": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, _intp]),
     "kzgpu_msm_partial_dev": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "kzgpu_msm_partial": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "kzgpu_g1_fold": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, _intp]),
     "kzgpu_g1_lincomb": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, _intp]),
     "kzgpu_ntt": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),

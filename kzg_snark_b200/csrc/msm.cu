@@ -1445,6 +1445,21 @@ int kzgpu_msm_partial_dev(uint64_t handle, size_t first, const uint64_t* d_scala
   return msm_core<BLS381Cfg>(*s, first, (const uint32_t*)d_scalars, n, 0, (uint32_t*)d_out_xyzz);
 }
 
+int kzgpu_msm_partial(uint64_t handle, size_t first, const uint64_t* scalars, size_t n, uint64_t* d_out_xyzz) {
+  KZ_REQUIRE_INIT();
+  const Srs* s = find_srs(handle);
+  if (!s) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle %llu", (unsigned long long)handle);
+  if (first + n > s->n) return kz_fail(KZGPU_ERANGE, "scalar range exceeds the SRS shard");
+  if (!d_out_xyzz || (n && !scalars)) return kz_fail(KZGPU_EINVAL, "null pointer");
+  int rc = set_smem_attrs();
+  if (rc) return rc;
+  // host scalars of this rank's shard: uploaded inside the MSM, chunked and overlapped with the compute like kzgpu_msm
+  if ((rc = g_ws.scal.ensure(n * 32 + 32))) return rc;
+  const uint32_t* d = (const uint32_t*)g_ws.scal.p;
+  if (s->curve == KZGPU_BN254) return msm_core<BN254Cfg>(*s, first, d, n, 0, (uint32_t*)d_out_xyzz, scalars);
+  return msm_core<BLS381Cfg>(*s, first, d, n, 0, (uint32_t*)d_out_xyzz, scalars);
+}
+
 int kzgpu_g1_fold(int curve, const uint64_t* d_xyzz, size_t count, uint64_t* out_affine_xy, int* is_inf) {
   KZ_REQUIRE_INIT();
   if (!d_xyzz || !out_affine_xy) return kz_fail(KZGPU_EINVAL, "null pointer");

@@ -172,6 +172,12 @@ def msm_partial_dev(srs, dbuf, n, dout, first=0):
     check(_ffi.init().kzgpu_msm_partial_dev(srs.handle, first, dbuf.ptr, n, dout.ptr))
 
 
+def msm_partial(srs, scalars, dout, first=0):
+    """Same from host scalars (numpy limb array, ideally pinned): the upload overlaps the compute inside the call."""
+    a = _scalars(scalars)
+    check(_ffi.init().kzgpu_msm_partial(srs.handle, first, ptr(a), a.shape[0], dout.ptr))
+
+
 def g1_fold(curve, dbuf, count):
     cid = curve_id(curve)
     out = _point_out(cid)

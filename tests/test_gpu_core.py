@@ -437,6 +437,38 @@ def test_point_sharded_open_equals_single_open(dev):
     srs.destroy()
 
 
+def test_point_sharded_msm_from_host_scalars(dev):
+    """kzgpu_msm_partial (each rank's slice of the scalars in host memory, upload chunked and overlapped inside the call:
+    2^21 scalars per 'rank' take the 4-chunk pipelined path) against kzgpu_msm_partial_dev and the single-GPU MSM; the
+    two 'ranks' run one after another on one GPU."""
+    import ctypes
+    from kzg_snark_b200 import _ffi
+    from kzg_snark_b200.limbs import random_scalars
+    from kzg_snark_b200.parallel import shard_range
+    cv = get_curve("bn254")
+    n, world = (1 << 22) + 12345, 2
+    srs = dev.Srs.generate("bn254", 0x1234ABCD5678EF, n)
+    sc = random_scalars(n, cv.r, seed=91)
+    sc[1000:5000] = 0
+    ref, rinf = dev.msm(srs, sc)
+
+    class At:
+        def __init__(self, base, off):
+            self.ptr = ctypes.c_void_p(base.ptr.value + off)
+
+    parts_h, parts_d = _ffi.DeviceBuffer(128 * world), _ffi.DeviceBuffer(128 * world)
+    d = _ffi.DeviceBuffer(n * 32).upload(sc)
+    for rank in range(world):
+        s0, cnt = shard_range(n, world, rank)
+        dev.msm_partial(srs, sc[s0:s0 + cnt], At(parts_h, 128 * rank), first=s0)
+        dev.msm_partial_dev(srs, At(d, 32 * s0), cnt, At(parts_d, 128 * rank), first=s0)
+    out_h, inf_h = dev.g1_fold("bn254", parts_h, world)
+    out_d, inf_d = dev.g1_fold("bn254", parts_d, world)
+    assert not rinf and not inf_h and not inf_d
+    assert (out_h == ref).all() and (out_d == ref).all()
+    d.free(); srs.destroy()
+
+
 def test_msm_batch_falls_back_per_polynomial_when_the_pass_does_not_fit(dev):
     """More polynomials than one pass takes (> 64 bucket sets): the batch entry point runs them one by one;
     same results.  Also the argument checks of the verifier-side combination."""
