@@ -107,10 +107,10 @@ template <class P> HD void xyzz_madd_lz(XYZZ<P>& acc, const Affine<P>& b) {
     else acc = xyzz_inf<P>();
     return;
   }
-  Fe<P> PP = fe_mul_lz<P>(Pd, Pd);
+  Fe<P> PP = fe_sqr_lz<P>(Pd);
   Fe<P> PPP = fe_mul_lz<P>(Pd, PP);
   Fe<P> Q = fe_mul_lz<P>(acc.x, PP);
-  Fe<P> X3 = fe_sub_lz<P>(fe_sub_lz<P>(fe_sub_lz<P>(fe_mul_lz<P>(Rd, Rd), PPP), Q), Q);
+  Fe<P> X3 = fe_sub_lz<P>(fe_sub_lz<P>(fe_sub_lz<P>(fe_sqr_lz<P>(Rd), PPP), Q), Q);
   Fe<P> Y3 = fe_sub_lz<P>(fe_mul_lz<P>(Rd, fe_sub_lz<P>(Q, X3)), fe_mul_lz<P>(acc.y, PPP));
   acc.zz = fe_mul_lz<P>(acc.zz, PP);
   acc.zzz = fe_mul_lz<P>(acc.zzz, PPP);

@@ -15,6 +15,7 @@
 // p <= 2^(32N-1) -- true for all four moduli (254/255/254/381 bits in 256/256/256/384).
 #pragma once
 #include <cstdint>
+#include <utility>
 #include "mp_prims.cuh"
 
 #ifdef __CUDACC__
@@ -226,7 +227,64 @@ template <class P> HD Fe<P> fe_reduce_lz(const Fe<P>& a) {
   return r;
 }
 
-template <class P> HD Fe<P> fe_sqr(const Fe<P>& a) { return fe_mul<P>(a, a); }
+// Montgomery square, same row structure as fe_mul_nofinal with row i reduced to the products a_i * a_j, j >= i
+// (N(N+1)/2 instead of N^2 wide multiplies): the multiplicand of row i is  [a_i | 2 * (a >> 32(i+1))], i.e. limb i is
+// a_i, limb i+1 is a_(i+1) << 1 and the limbs above are those of 2a (funnel shifts, computed once); limbs below i are
+// never read.  Needs a < 2^(32N-1) (true for canonical and for semi-reduced values of every modulus here).  Result
+// < a^2 / 2^(32N) + p like the product; the running value stays < (2a + p) * 2^32 < 2^(32(N+1)) for a < 2p <= 2^(32N)/2.
+template <class P, int I> HD void fe_sqr_row(uint32_t* E, uint32_t* O, uint32_t* Mv, const uint32_t* a, const uint32_t* mod) {
+  constexpr int N = P::N;
+  Mv[I] = a[I];
+  if constexpr (I + 1 < N) Mv[I + 1] = a[I + 1] << 1;
+  if constexpr (I & 1) {
+    Mp<N>::template shift_mad_s<I / 2>(E, O[0], Mv + 1, a[I]);
+    Mp<N>::template mad_even_s<(I + 1) / 2>(O, Mv, a[I], E[N - 1]);
+    fe_redc_row<P>(O, E, mod);
+  } else {
+    Mp<N>::template shift_mad_s<I / 2>(O, E[0], Mv + 1, a[I]);
+    Mp<N>::template mad_even_s<(I + 1) / 2>(E, Mv, a[I], O[N - 1]);
+    fe_redc_row<P>(E, O, mod);
+  }
+}
+template <class P, int... I> HD void fe_sqr_rows(uint32_t* E, uint32_t* O, uint32_t* Mv, const uint32_t* a, const uint32_t* mod,
+                                                  std::integer_sequence<int, I...>) {
+  (fe_sqr_row<P, I + 1>(E, O, Mv, a, mod), ...);
+}
+// the doubled multiplicand makes the running value < (2a + p) * 2^32: it fits the N+1 positions for a < 2p iff 5p <= 2^(32N)
+// (BN254 p and r, BLS12-381 p); BLS12-381 r squares through the general product
+template <class P> struct FeSq { static constexpr bool ok = P::mod(P::N - 1) < 0x33333333u; };
+
+template <class P> HD void fe_sqr_nofinal(uint32_t* t, const Fe<P>& a) {
+  constexpr int N = P::N;
+  if constexpr (!FeSq<P>::ok) { fe_mul_nofinal<P>(t, a, a); return; }
+  uint32_t mod[N], E[N], O[N], Mv[N];
+  fe_load_mod<P>(mod);
+  Mv[0] = a.v[0];
+  Mv[1] = a.v[1] << 1;
+#pragma unroll
+  for (int j = 2; j < N; j++) Mv[j] = (a.v[j] << 1) | (a.v[j - 1] >> 31);
+  Mp<N>::mul_even(E, Mv, a.v[0]);
+  Mp<N>::mul_even(O, Mv + 1, a.v[0]);
+  fe_redc_row<P>(E, O, mod);
+  fe_sqr_rows<P>(E, O, Mv, a.v, mod, std::make_integer_sequence<int, N - 1>{});
+  Mp<N>::merge(t, E, O);
+}
+
+template <class P> HD Fe<P> fe_sqr(const Fe<P>& a) {
+  uint32_t t[P::N];
+  fe_sqr_nofinal<P>(t, a);
+  Fe<P> r;
+  fe_final_sub<P>(r.v, t);
+  return r;
+}
+
+
+// semi-reduced square: a < 2p -> a^2 / 2^(32N) mod p in [0, 2p)
+template <class P> HD Fe<P> fe_sqr_lz(const Fe<P>& a) {
+  Fe<P> r;
+  fe_sqr_nofinal<P>(r.v, a);
+  return r;
+}
 
 template <class P> HD Fe<P> fe_to_mont(const Fe<P>& a) {
   Fe<P> r2;

@@ -75,6 +75,46 @@ def emit(N):
     w(f"        : {outs}\n        : {ins});")
     w("  }")
 
+    # squaring rows: the two chains with the first K products left out (field.cuh fe_sqr_nofinal)
+    w("  // mad_even without its first K products (chain starts at acc[2K]; K == N/2: nothing to add)")
+    w("  template <int K> static __device__ __forceinline__ void mad_even_s(uint32_t* acc, const uint32_t* a, uint32_t b, uint32_t& top) {")
+    for K in range(H):
+        cnt = H - K                       # products
+        nacc = N - 2 * K                  # accumulator limbs touched
+        s = []
+        for t in range(cnt):
+            lo = "mad.lo.cc.u32" if t == 0 else "madc.lo.cc.u32"
+            s.append(f"{lo} %{2*t}, %{nacc+1+t}, %{nacc+1+cnt}, %{2*t}; madc.hi.cc.u32 %{2*t+1}, %{nacc+1+t}, %{nacc+1+cnt}, %{2*t+1};")
+        s.append(f"addc.u32 %{nacc}, %{nacc}, 0;")
+        outs = ", ".join(f'"+r"(acc[{2*K+k}])' for k in range(nacc)) + ', "+r"(top)'
+        ins = ", ".join(f'"r"(a[{2*(K+t)}])' for t in range(cnt)) + ', "r"(b)'
+        kw = "if" if K == 0 else "else if"
+        w(f"    {kw} constexpr (K == {K}) {{")
+        w('      asm("' + '"\n          "'.join(s) + '"')
+        w(f"          : {outs}\n          : {ins});")
+        w("    }")
+    w("  }")
+    w("  // shift_mad without its first K products: those slots only pass the carry on")
+    w("  template <int K> static __device__ __forceinline__ void shift_mad_s(uint32_t* x, uint32_t& y0, const uint32_t* a, uint32_t b) {")
+    for K in range(H):
+        cnt = H - K
+        s = [f"add.cc.u32 %{N}, %{N}, %1;"]
+        for j in range(H):
+            if j < K:
+                s.append(f"addc.cc.u32 %{2*j}, %{2*j+2}, 0; addc.cc.u32 %{2*j+1}, %{2*j+3}, 0;")
+            elif j < H - 1:
+                s.append(f"madc.lo.cc.u32 %{2*j}, %{N+1+(j-K)}, %{N+1+cnt}, %{2*j+2}; madc.hi.cc.u32 %{2*j+1}, %{N+1+(j-K)}, %{N+1+cnt}, %{2*j+3};")
+            else:
+                s.append(f"madc.lo.cc.u32 %{2*j}, %{N+1+(j-K)}, %{N+1+cnt}, 0; madc.hi.u32 %{2*j+1}, %{N+1+(j-K)}, %{N+1+cnt}, 0;")
+        outs = ", ".join(f'"+r"(x[{k}])' for k in range(N)) + ', "+r"(y0)'
+        ins = ", ".join(f'"r"(a[{2*(K+t)}])' for t in range(cnt)) + ', "r"(b)'
+        kw = "if" if K == 0 else "else if"
+        w(f"    {kw} constexpr (K == {K}) {{")
+        w('      asm("' + '"\n          "'.join(s) + '"')
+        w(f"          : {outs}\n          : {ins});")
+        w("    }")
+    w("  }")
+
     # merge: r[k] = o[k] + e[k+1], r[N-1] = o[N-1] + carry
     w("  // r[k] = o[k] + e[k+1] (k < N-1), r[N-1] = o[N-1] + carry")
     w("  static __device__ __forceinline__ void merge(uint32_t* r, const uint32_t* o, const uint32_t* e) {")

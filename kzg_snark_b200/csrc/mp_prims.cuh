@@ -38,6 +38,26 @@ template <int N> struct MpPrimsHost {
       x[j] = (uint32_t)t; x[j + 1] = (uint32_t)(t >> 32); c = (uint64_t)(t >> 64);
     }
   }
+  // squaring rows (field.cuh fe_sqr_nofinal): the same two chains with the first K products left out
+  template <int K> static inline void mad_even_s(uint32_t* acc, const uint32_t* a, uint32_t b, uint32_t& top) {
+    uint64_t c = 0;
+    for (int j = 2 * K; j < N; j += 2) {
+      unsigned __int128 t = (unsigned __int128)((uint64_t)a[j] * b) + (((uint64_t)acc[j + 1] << 32) | acc[j]) + c;
+      acc[j] = (uint32_t)t; acc[j + 1] = (uint32_t)(t >> 32); c = (uint64_t)(t >> 64);
+    }
+    top += (uint32_t)c;
+  }
+  template <int K> static inline void shift_mad_s(uint32_t* x, uint32_t& y0, const uint32_t* a, uint32_t b) {
+    uint64_t s = (uint64_t)y0 + x[1];
+    y0 = (uint32_t)s;
+    uint64_t c = s >> 32;
+    for (int j = 0; j < N; j += 2) {
+      uint64_t add = (j + 2 < N) ? ((((uint64_t)x[j + 3]) << 32) | x[j + 2]) : 0;
+      uint64_t prod = j >= 2 * K ? (uint64_t)a[j] * b : 0;
+      unsigned __int128 t = (unsigned __int128)prod + add + c;
+      x[j] = (uint32_t)t; x[j + 1] = (uint32_t)(t >> 32); c = (uint64_t)(t >> 64);
+    }
+  }
   static inline void merge(uint32_t* r, const uint32_t* o, const uint32_t* e) {
     uint64_t c = 0;
     for (int k = 0; k < N; k++) {

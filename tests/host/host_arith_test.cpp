@@ -37,13 +37,15 @@ template <class P> void field_op(const std::string& op, std::istringstream& in) 
   in >> b;
   Fe<P> x = M<P>(a), y = M<P>(b), r;
   if (op == "mul") r = fe_mul<P>(x, y);
+  else if (op == "sqr") r = fe_sqr<P>(x);
   else if (op == "add") r = fe_add<P>(x, y);
   else if (op == "sub") r = fe_sub<P>(x, y);
   else if (op == "rawmul") { std::cout << hex<P>(fe_mul<P>(parse<P>(a), parse<P>(b))) << "\n"; return; }
-  else if (op == "lzmul" || op == "lzadd" || op == "lzsub" || op == "nradd" || op == "nrsub") {
+  else if (op == "lzmul" || op == "lzadd" || op == "lzsub" || op == "nradd" || op == "nrsub" || op == "lzsqr") {
     // raw limbs in, raw limbs out (no Montgomery conversion): the semi-reduced primitives of field.cuh
     Fe<P> u = parse<P>(a), v = parse<P>(b), w;
     if (op == "lzmul") w = fe_mul_lz<P>(u, v);
+    else if (op == "lzsqr") w = fe_sqr_lz<P>(u);
     else if (op == "lzadd") w = fe_add_lz<P>(u, v);
     else if (op == "lzsub") w = fe_sub_lz<P>(u, v);
     else if (op == "nradd") w = fe_add_nr<P>(u, v);

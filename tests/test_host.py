@@ -68,7 +68,8 @@ def test_csrc_field_and_curve_formulas_on_host(host_arith):
         vals = [0, 1, 2, q - 1, q - 2, (q - 1) // 2] + [rng.randrange(q) for _ in range(20)]
         for _ in range(150):
             a, b = rng.choice(vals), rng.choice(vals)
-            for op, fn in (("mul", lambda a, b: a * b % q), ("add", lambda a, b: (a + b) % q), ("sub", lambda a, b: (a - b) % q)):
+            for op, fn in (("mul", lambda a, b: a * b % q), ("sqr", lambda a, b: a * a % q), ("add", lambda a, b: (a + b) % q),
+                           ("sub", lambda a, b: (a - b) % q)):
                 lines.append(f"{f} {op} {a:x} {b:x}"); expect.append("%x" % fn(a, b))
         for _ in range(3):
             a = rng.randrange(1, q); lines.append(f"{f} inv {a:x}"); expect.append("%x" % pow(a, -1, q))
@@ -109,6 +110,8 @@ def test_csrc_semi_reduced_arithmetic_on_host(host_arith):
         pairs += [(2 * q - 1, 2 * q - 1), (4 * q - 1, q - 1), (q, q), (q, 0)]
         for a, b in pairs:
             lines.append(f"{f} lzmul {a:x} {b:x}"); expect.append(("mul", q, a * b * Rinv % q, None))
+        for a in lo + [(1 << (bits - 2)) - 1, 2 * q - 2] + [rng.randrange(2 * q) for _ in range(200)]:
+            lines.append(f"{f} lzsqr {a:x} 0"); expect.append(("mul", q, a * a * Rinv % q, None))
         for _ in range(200):
             a, b = rng.choice(lo), rng.choice(lo)
             lines.append(f"{f} lzadd {a:x} {b:x}"); expect.append(("fold", q, (a + b) % q, None))
