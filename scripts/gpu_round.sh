@@ -12,3 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-fi
 cat gpurun_out/bench_$TAG.json
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 if [ "$2" = "full" ]; then bash scripts/gpu_ncu_full.sh $TAG; fi
+# host topology of the box (explains e2e variance between boxes: PCIe link, NUMA node of the GPU)
+{ nvidia-smi --query-gpu=pci.bus_id,pcie.link.gen.current,pcie.link.width.current --format=csv; nvidia-smi topo -m; \
+  for d in /sys/bus/pci/devices/*; do if [ "$(cat $d/class 2>/dev/null)" = "0x030200" ]; then echo "$d numa_node=$(cat $d/numa_node)"; fi; done; \
+  ls /sys/devices/system/node/ | grep -c '^node'; nproc; } > gpurun_out/topo_$TAG.txt 2>&1
