@@ -38,6 +38,9 @@ TAU = 0x2545F4914F6CDD1D9E3779B97F4A7C15F39CC0605CEDC834 % R_BN254      # fixed 
 MODEL_IMAD_PER_POINT = 43520
 IMAD32_PER_MODMUL = 272
 MODMUL_PER_MADD = 10
+# what the accumulate kernel executes per mixed addition: 8 general products (64 + 64 + 8 wide multiplies = 272 IMAD32 each) and
+# 2 dedicated squarings (36 + 64 + 8 wide = 216 IMAD32 each, field.cuh fe_sqr_nofinal)
+IMAD32_EXECUTED_PER_MADD = 8 * 272 + 2 * 216
 
 
 def load_traffic(kernel):
@@ -391,7 +394,7 @@ def run_gpu(args):
                 "traffic": load_traffic("msm_accumulate_kernel") if args.logn == 24 else None,
                 "model": "SURVEY 8(d): 43,520 32-bit IMAD per point (16 windows x 10 modmul x 272); "
                          "peak = live IMAD.WIDE.U32 microbenchmark x 2",
-                "executed_frac": madds * MODMUL_PER_MADD * IMAD32_PER_MODMUL / (acc_ms * 1e-3) / imad32_peak,
+                "executed_frac": madds * IMAD32_EXECUTED_PER_MADD / (acc_ms * 1e-3) / imad32_peak,
                 "kernel_ms": acc_ms, "kernel_share_of_step": acc["ms"] / max(sum(p["ms"] for p in prof.values()), 1e-9),
                 "hbm_algorithmic_gbs": n * 96 / (acc_ms * 1e-3) / 1e9,
                 "hbm_peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src,
