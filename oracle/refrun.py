@@ -12,7 +12,7 @@ What is real and what is a stand-in when the reference runs here:
             plonk/{encoder,indexer,prover,verifier}.py, marlin/{...}.py -- imported from
             /root/reference by file path, byte-for-byte the reference's code;
   stand-in  `sage.all` (GF, PolynomialRing, vector, prod, matrix) -> kzg_snark_b200/sageshim.py,
-            `py_ecc.optimized_bn128` -> oracle/pyecc_standin.py.  Both third-party packages are
+            `py_ecc.optimized_bn128` -> oracle/pyecc_standin.py, `py_ecc.optimized_bls12_381` -> oracle/pyecc_standin_bls.py.  Both third-party packages are
             un-pinned pip/conda dependencies of the reference that cannot be installed here.
 
 The trace therefore pins the oracle (and the CUDA path) against the reference's own control
@@ -38,7 +38,7 @@ def available():
 
 def _install_standins():
     from kzg_snark_b200 import sageshim
-    from . import pyecc_standin
+    from . import pyecc_standin, pyecc_standin_bls
 
     sage = types.ModuleType("sage")
     sage_all = types.ModuleType("sage.all")
@@ -50,9 +50,10 @@ def _install_standins():
     sage.all = sage_all
     py_ecc = types.ModuleType("py_ecc")
     py_ecc.optimized_bn128 = pyecc_standin
-    saved = {k: sys.modules.get(k) for k in ("sage", "sage.all", "py_ecc", "py_ecc.optimized_bn128")}
+    py_ecc.optimized_bls12_381 = pyecc_standin_bls
+    saved = {k: sys.modules.get(k) for k in ("sage", "sage.all", "py_ecc", "py_ecc.optimized_bn128", "py_ecc.optimized_bls12_381")}
     sys.modules.update({"sage": sage, "sage.all": sage_all, "py_ecc": py_ecc,
-                        "py_ecc.optimized_bn128": pyecc_standin})
+                        "py_ecc.optimized_bn128": pyecc_standin, "py_ecc.optimized_bls12_381": pyecc_standin_bls})
     return saved
 
 

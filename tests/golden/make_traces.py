@@ -14,6 +14,7 @@ reference's outputs (points normalised to affine):
                          polynomial, the main.py:17-36 demo, and kzg.py's edge behaviour (zero
                          polynomial, zero coefficients, list inputs, multi-poly open, degree
                          overflow message)
+  ref_trace_kzg_bls.json the same KZG demo and edge inputs through KZG(curve_type="bls12_381") (kzg.py:32-35), degree 2^8
   ref_trace_fft.json     fft_ff / ifft_ff / fft_ff_interpolation from fft_ff.py on n = 1 .. 2^8 (fft_ff also 2^10)
   ref_trace_plonk.json   main.py:64-94: Indexer.preprocess, Prover.prove, Verifier.verify (accepts)
   ref_trace_marlin.json  main.py:39-61 likewise
@@ -89,6 +90,38 @@ def trace_kzg():
         assert notes["demo_check"] and notes["config0_check"] and notes["batch_check"] and not notes["demo_check_wrong_eval"]
         dump("ref_trace_kzg.json", {"source": "reference kzg.py run by oracle/refrun.py", "seed": SEED, "curve": "bn254",
                                     "notes": notes, "keys": rr.keys, "calls": rr.trace})
+
+
+def trace_kzg_bls():
+    """The same demo on the reference's second curve (kzg.py:32-35): KZG("bls12_381") setup -> commit -> open -> check
+    (accept / reject), edge inputs, batch_check, and a degree-2^8 polynomial."""
+    with refrun.ReferenceRun(seed=SEED + 7) as rr:
+        kzg = rr.kzg.KZG(curve_type="bls12_381")
+        Fq, R, X = kzg.Fq, kzg.R, kzg.X
+        notes = {}
+        ck, rk = kzg.setup(max_degree=10)
+        polys = [1 + 2 * X + 3 * X**2, 4 + 5 * X**3]
+        comm = kzg.commit(ck, polys)
+        proof = kzg.open(ck, polys, 7, 42)
+        notes["demo_check"] = bool(kzg.check(rk, comm, 7, [p(7) for p in polys], proof, 42))
+        notes["demo_check_wrong_eval"] = bool(kzg.check(rk, comm, 7, [polys[0](7) + 1, polys[1](7)], proof, 42))
+        edge = [R(0), R([0, 0, 5, 0, Fq(-1)]), R([Fq.random_element() for _ in range(11)]), R(3)]
+        kzg.commit(ck, edge)
+        kzg.commit(ck, [[1, 2, 3], [0, 0, 0, 7]])
+        kzg.open(ck, edge, Fq.random_element(), Fq.random_element())
+        kzg.open(ck, [edge[3]], 5, 9)
+        notes["batch_check"] = bool(kzg.batch_check(
+            rk, [comm, comm[:1]], [7, 3], [[p(7) for p in polys], [polys[0](3)]],
+            [proof, kzg.open(ck, polys[:1], 3, 11)], [42, 11]))
+        ck2, rk2 = kzg.setup(max_degree=1 << 8)
+        big = R([Fq.random_element() for _ in range((1 << 8) + 1)])
+        z, xi = Fq.random_element(), Fq.random_element()
+        c2 = kzg.commit(ck2, [big])
+        pr2 = kzg.open(ck2, [big], z, xi)
+        notes["deg256_check"] = bool(kzg.check(rk2, c2, z, [big(z)], pr2, xi))
+        assert notes["demo_check"] and notes["deg256_check"] and notes["batch_check"] and not notes["demo_check_wrong_eval"]
+        dump("ref_trace_kzg_bls.json", {"source": "reference kzg.py (curve_type='bls12_381') run by oracle/refrun.py", "seed": SEED + 7,
+                                        "curve": "bls12_381", "notes": notes, "keys": rr.keys, "calls": rr.trace})
 
 
 def trace_fft():
@@ -323,7 +356,12 @@ def trace_plonk_normalized():
 
 if __name__ == "__main__":
     assert refrun.available(), "/root/reference not mounted"
+    if len(sys.argv) > 1:                                  # regenerate selected fixtures only: make_traces.py trace_kzg_bls ...
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     trace_kzg()
+    trace_kzg_bls()
     trace_fft()
     trace_plonk()
     trace_marlin()

@@ -168,7 +168,8 @@ def test_tau_identity_large(logn):
         s.destroy()
 
 
-@pytest.mark.parametrize("name", ["ref_trace_kzg.json", "ref_trace_fft.json", "ref_trace_plonk.json", "ref_trace_marlin.json"])
+@pytest.mark.parametrize("name", ["ref_trace_kzg.json", "ref_trace_kzg_bls.json", "ref_trace_fft.json", "ref_trace_plonk.json",
+                                  "ref_trace_marlin.json"])
 def test_dropin_reproduces_reference_trace(name):
     """Every commit / open / fft_ff / ifft_ff / fft_ff_interpolation call the reference's own
     kzg.py, plonk and marlin provers made (recorded in the build container by
@@ -177,14 +178,15 @@ def test_dropin_reproduces_reference_trace(name):
     from trace_replay import load, replay
     from kzg_snark_b200.kzg import KZG
     from kzg_snark_b200.fft_ff import fft_ff, ifft_ff, fft_ff_interpolation
-    cv = get_curve("bn254")
-    kzg = KZG("bn254")
+    trace = load(name)
+    curve = trace.get("curve", "bn254")                  # ref_trace_kzg_bls.json: the reference's KZG("bls12_381") run
+    cv = get_curve(curve)
+    kzg = KZG(curve)
     F, fq = kzg.Fq, kzg._codec.fq
 
     def poly_ints(p):
         return [int(c) for c in (p.list() if hasattr(p, "list") else p)]
 
-    trace = load(name)
     n = replay(
         trace,
         make_key=lambda pts: [kzg.Z1 if p is None else (fq(p[0]), fq(p[1]), fq(1)) for p in pts],

@@ -20,13 +20,14 @@ from oracle.params import CURVES
 from trace_replay import H, load, replay
 
 R = CURVES["bn254"]["r"]
-TRACES = ["ref_trace_kzg.json", "ref_trace_fft.json", "ref_trace_plonk.json", "ref_trace_marlin.json"]
+TRACES = ["ref_trace_kzg.json", "ref_trace_kzg_bls.json", "ref_trace_fft.json", "ref_trace_plonk.json", "ref_trace_marlin.json"]
 
 
 def oracle_replay(trace):
-    ko = KZGOracle("bn254")
-    cv = get_curve("bn254")
-    F = GFp(R)
+    curve = trace.get("curve", "bn254")                  # ref_trace_kzg_bls.json: the reference's KZG("bls12_381")
+    ko = KZGOracle(curve)
+    cv = get_curve(curve)
+    F = GFp(CURVES[curve]["r"])
     return replay(
         trace,
         make_key=lambda pts: [cv.Z1 if p is None else (p[0], p[1], 1) for p in pts],
@@ -70,8 +71,12 @@ def test_config0_is_in_the_kzg_trace():
     assert len(big) == 1 and t["calls"][-1]["fn"] == "open" and len(t["calls"][-1]["polys"][0]) == 1025
 
 
-def test_pairing_standin_is_bilinear():
-    from oracle import pyecc_standin as E
+@pytest.mark.parametrize("modname", ["pyecc_standin", "pyecc_standin_bls"])
+def test_pairing_standin_is_bilinear(modname):
+    import importlib
+    E = importlib.import_module("oracle." + modname)
+    tx, ty = E._twist(E.normalize(E.G2))                 # the twist map lands on E(Fp12): y^2 = x^3 + b
+    assert ty * ty - tx * tx * tx == E.FQ12([E.b.n] + [0] * 11)
     assert E.is_on_curve(E.G2, E.b2) and E.is_inf(E.multiply(E.G2, E.curve_order))
     e1 = E.pairing(E.G2, E.G1)
     assert e1 != E.FQ12.one() and e1 ** E.curve_order == E.FQ12.one()
