@@ -16,6 +16,7 @@ reference's outputs (points normalised to affine):
                          overflow message)
   ref_trace_kzg_bls.json the same KZG demo and edge inputs through KZG(curve_type="bls12_381") (kzg.py:32-35), degree 2^8
   ref_trace_fft.json     fft_ff / ifft_ff / fft_ff_interpolation from fft_ff.py on n = 1 .. 2^8 (fft_ff also 2^10)
+  ref_trace_fft_bls.json the same over the BLS12-381 scalar field
   ref_trace_plonk.json   main.py:64-94: Indexer.preprocess, Prover.prove, Verifier.verify (accepts)
   ref_trace_marlin.json  main.py:39-61 likewise
   ref_marlin_loops.json  the reference's `_compute_t_polynomial` / `_compute_f2_polynomial` (marlin/prover.py:248-301,
@@ -153,6 +154,26 @@ def trace_fft():
                 notes[key] = str(e)
         dump("ref_trace_fft.json", {"source": "reference fft_ff.py run by oracle/refrun.py", "seed": SEED + 1,
                                     "field": "bn254_r", "notes": notes, "calls": rr.trace})
+
+
+def trace_fft_bls():
+    """fft_ff.py over the BLS12-381 scalar field (the field KZG("bls12_381") hands to its callers): n = 1 .. 2^8, and 2^10."""
+    with refrun.ReferenceRun(seed=SEED + 8) as rr:
+        kzg = rr.kzg.KZG(curve_type="bls12_381")
+        Fq = kzg.Fq
+        q = Fq.order()
+        for logn in (0, 1, 2, 3, 4, 5, 6, 7, 8, 10):
+            n = 1 << logn
+            w = Fq(7) ** ((q - 1) // n)                               # 7 generates the multiplicative group of r_bls
+            vals = [Fq.random_element() for _ in range(n)]
+            rr.fft_ff.fft_ff(vals, w, Fq)
+            if logn > 8:
+                continue
+            rr.fft_ff.ifft_ff(vals, w, Fq)
+            if n >= 2:
+                rr.fft_ff.fft_ff_interpolation(vals, w, Fq)
+        dump("ref_trace_fft_bls.json", {"source": "reference fft_ff.py over GF(r_bls12_381) run by oracle/refrun.py", "seed": SEED + 8,
+                                        "curve": "bls12_381", "field": "bls12_381_r", "calls": rr.trace})
 
 
 def _plonk_inputs(Fq):
@@ -363,6 +384,7 @@ if __name__ == "__main__":
     trace_kzg()
     trace_kzg_bls()
     trace_fft()
+    trace_fft_bls()
     trace_plonk()
     trace_marlin()
     marlin_loops()

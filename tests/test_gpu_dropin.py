@@ -168,7 +168,7 @@ def test_tau_identity_large(logn):
         s.destroy()
 
 
-@pytest.mark.parametrize("name", ["ref_trace_kzg.json", "ref_trace_kzg_bls.json", "ref_trace_fft.json", "ref_trace_plonk.json",
+@pytest.mark.parametrize("name", ["ref_trace_kzg.json", "ref_trace_kzg_bls.json", "ref_trace_fft.json", "ref_trace_fft_bls.json", "ref_trace_plonk.json",
                                   "ref_trace_marlin.json"])
 def test_dropin_reproduces_reference_trace(name):
     """Every commit / open / fft_ff / ifft_ff / fft_ff_interpolation call the reference's own

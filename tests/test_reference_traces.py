@@ -20,7 +20,7 @@ from oracle.params import CURVES
 from trace_replay import H, load, replay
 
 R = CURVES["bn254"]["r"]
-TRACES = ["ref_trace_kzg.json", "ref_trace_kzg_bls.json", "ref_trace_fft.json", "ref_trace_plonk.json", "ref_trace_marlin.json"]
+TRACES = ["ref_trace_kzg.json", "ref_trace_kzg_bls.json", "ref_trace_fft.json", "ref_trace_fft_bls.json", "ref_trace_plonk.json", "ref_trace_marlin.json"]
 
 
 def oracle_replay(trace):
