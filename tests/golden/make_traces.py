@@ -27,6 +27,9 @@ reference's outputs (points normalised to affine):
                          canonical affine points produces -- with the blinding scalars, challenges'
                          inputs and the full proof, for the bit-exact check of kzg_snark_b200.plonk
 
+  ref_plonk_normalized_bls.json
+                         the same with curve_type="bls12_381" (kzg.py:32-35) on the bundled circuit, residues read as signed integers
+
 All fixtures are deterministic (seeded) and small (< 1 MB together).
 """
 import json
@@ -178,7 +181,10 @@ def trace_fft_bls():
 
 def _plonk_inputs(Fq):
     inst = fixtures.load_plonk_instance(os.path.join(REF_CS, "PLONK_ARITHMETIZATION_INSTANCE.pkl"))
-    f = lambda v: [Fq(x) for x in v]                                     # noqa: E731
+    r0 = inst["modulus"] if "modulus" in inst else 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    # the pickle holds residues mod r_bn254 (small values and -1); read them as signed integers so that the same circuit
+    # is also satisfied over the BLS12-381 scalar field (identity for Fq = GF(r_bn254))
+    f = lambda v: [Fq(x if x <= r0 // 2 else x - r0) for x in v]         # noqa: E731
     w = f(inst["w"])
     return [f(inst[k]) for k in ("qM", "qL", "qR", "qO", "qC")], list(inst["perm"]), w[:5], w[5:]
 
@@ -322,11 +328,12 @@ def trace_marlin_normalized():
             "proof": pr, "notes": {"verify": bool(ok)}})
 
 
-def trace_plonk_normalized():
+def trace_plonk_normalized(curve="bn254"):
     """Reference prover + indexer with KZG.commit / KZG.open outputs normalised to (x, y, 1): the
     transcript then hashes what a canonical-affine drop-in returns, so kzg_snark_b200.plonk can be
     compared bit for bit (commitments, evaluations, opening proofs)."""
-    from oracle import pyecc_standin as E
+    from oracle import pyecc_standin, pyecc_standin_bls
+    E = pyecc_standin if curve == "bn254" else pyecc_standin_bls
     with refrun.ReferenceRun(seed=SEED + 4) as rr:
         KZG = rr.kzg.KZG
 
@@ -349,21 +356,21 @@ def trace_plonk_normalized():
 
         sageshim.GFShim.random_element = rand
         try:
-            Fq = KZG("bn254").Fq
+            Fq = KZG(curve).Fq
             sel, perm, x, wit = _plonk_inputs(Fq)
             n = len(sel[0])
-            ipk, ivk = rr.load("plonk.indexer").Indexer(curve_type="bn254").preprocess(*sel, perm, max_degree=n + 5)
+            ipk, ivk = rr.load("plonk.indexer").Indexer(curve_type=curve).preprocess(*sel, perm, max_degree=n + 5)
             n_index_draws = len(draws)
-            proof = rr.load("plonk.prover").Prover(curve_type="bn254").prove(ipk, x, wit)
+            proof = rr.load("plonk.prover").Prover(curve_type=curve).prove(ipk, x, wit)
             n_prove_draws = len(draws)
-            ok = rr.load("plonk.verifier").Verifier(curve_type="bn254").verify(ivk, x, proof)
+            ok = rr.load("plonk.verifier").Verifier(curve_type=curve).verify(ivk, x, proof)
         finally:
             sageshim.GFShim.random_element = orig_rand
         assert ok
         sub = ipk["subgroups"]
-        dump("ref_plonk_normalized.json", {
+        dump("ref_plonk_normalized.json" if curve == "bn254" else "ref_plonk_normalized_bls.json", {
             "source": "reference plonk prover with commitments normalised to (x,y,1) before the transcript",
-            "seed": SEED + 4, "curve": "bn254", "n": n,
+            "seed": SEED + 4, "curve": curve, "n": n,
             "index_draws": draws[:n_index_draws],                 # tau, k1, k2 ... (kzg.py:67, plonk/encoder.py:83-84)
             # the prover's Encoder.update_state draws a throw-away k1, k2 first (plonk/prover.py:63,
             # plonk/encoder.py:80-91); the last 11 draws are b1..b9 (:72-75) and b10, b11 (:346)
@@ -373,6 +380,12 @@ def trace_plonk_normalized():
             "index_polys": {k: rr.enc_poly(v) for k, v in ipk["polynomials"].items()},
             "keys": rr.keys, "x": [rr.enc_scalar(v) for v in x], "w": [rr.enc_scalar(v) for v in wit],
             "proof": enc_proof(rr, proof), "notes": {"verify": bool(ok)}})
+
+
+def trace_plonk_normalized_bls():
+    """The reference's PLONK indexer / prover / verifier with curve_type="bls12_381" on the bundled circuit (its residues read as
+    signed integers, see _plonk_inputs): the bit-exact target of kzg_snark_b200.plonk on the second curve."""
+    trace_plonk_normalized("bls12_381")
 
 
 if __name__ == "__main__":
@@ -390,3 +403,4 @@ if __name__ == "__main__":
     marlin_loops()
     trace_marlin_normalized()
     trace_plonk_normalized()
+    trace_plonk_normalized_bls()

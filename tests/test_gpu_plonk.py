@@ -30,18 +30,25 @@ def aff(pt):
     return None if z == 0 else (x, y)
 
 
-def test_prover_matches_the_reference_prover_bit_for_bit():
+@pytest.mark.parametrize("fixture", ["ref_plonk_normalized.json", "ref_plonk_normalized_bls.json"])
+def test_prover_matches_the_reference_prover_bit_for_bit(fixture):
+    """Both curves of kzg.py:26-35: the reference's plonk/{indexer,prover}.py were run with curve_type "bn254" and "bls12_381" on
+    the bundled circuit (tests/golden/make_traces.py); key, index polynomials and the whole proof must be identical."""
     from kzg_snark_b200.plonk import Indexer, Prover
-    d = load("ref_plonk_normalized.json")
+    d = load(fixture)
+    curve = d["curve"]
+    rq, r_bn = CURVES[curve]["r"], CURVES["bn254"]["r"]
+    nl = CURVES[curve]["fp_limbs32"] // 2                                  # 64-bit limbs per base-field coordinate
     inst = json.load(open(os.path.join(GOLD, "plonk_instance.json")))
-    sel = [[H(v) for v in inst[k]] for k in ("qM", "qL", "qR", "qO", "qC")]
+    signed = lambda v: (v if v <= r_bn // 2 else v - r_bn) % rq          # noqa: E731  (the pickle's residues as signed integers)
+    sel = [[signed(H(v)) for v in inst[k]] for k in ("qM", "qL", "qR", "qO", "qC")]
     perm = [H(v) for v in inst["perm"]]
     n = d["n"]
-    idx = Indexer("bn254")
+    idx = Indexer(curve)
     ipk, ivk = idx.preprocess(*sel, perm, max_degree=n + 5, tau=H(d["index_draws"][0]), k1=H(d["k1"]), k2=H(d["k2"]))
     # the device-generated key is the reference's key
     key = ipk["ck"].read(0, n + 6)
-    assert [tuple(int.from_bytes(row[4 * j:4 * j + 4].tobytes(), "little") for j in (0, 1)) for row in key] == \
+    assert [tuple(int.from_bytes(row[nl * j:nl * j + nl].tobytes(), "little") for j in (0, 1)) for row in key] == \
         [(H(p[0]), H(p[1])) for p in d["keys"][0]]
     # index polynomials (plonk/encoder.py:99-141) and sigma_star
     for name, coeffs in d["index_polys"].items():
@@ -53,7 +60,7 @@ def test_prover_matches_the_reference_prover_bit_for_bit():
     Fq = idx.kzg.Fq
     x = [Fq(H(v)) for v in d["x"]]
     w = [H(v) for v in d["w"]]
-    prover = Prover("bn254")
+    prover = Prover(curve)
     proof = prover.prove(ipk, x, w, blinders=[H(b) for b in d["prover_draws"][-11:]])
     assert prover.last_r_zeta == 0 and not any(prover.last_t_top)
     exp = d["proof"]
