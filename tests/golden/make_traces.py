@@ -27,8 +27,8 @@ reference's outputs (points normalised to affine):
                          canonical affine points produces -- with the blinding scalars, challenges'
                          inputs and the full proof, for the bit-exact check of kzg_snark_b200.plonk
 
-  ref_plonk_normalized_bls.json
-                         the same with curve_type="bls12_381" (kzg.py:32-35) on the bundled circuit, residues read as signed integers
+  ref_plonk_normalized_bls.json, ref_marlin_normalized_bls.json
+                         the same two with curve_type="bls12_381" (kzg.py:32-35) on the bundled instances, residues read as signed integers
 
 All fixtures are deterministic (seeded) and small (< 1 MB together).
 """
@@ -276,11 +276,14 @@ def marlin_loops():
             "t": rr.enc_poly(t), "f2": rr.enc_poly(f2)})
 
 
-def trace_marlin_normalized():
+def trace_marlin_normalized(curve="bn254"):
     """Reference Marlin indexer + prover + verifier with commitments normalised to (x, y, 1) before the transcript (what a
     canonical-affine drop-in returns): random draws, the polynomials of every commit / open call and the proof -- the
     fixture for a device Marlin prover."""
-    from oracle import pyecc_standin as E
+    from oracle import pyecc_standin, pyecc_standin_bls
+    E = pyecc_standin if curve == "bn254" else pyecc_standin_bls
+    r_bn = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    sg = lambda v: v if v <= r_bn // 2 else v - r_bn               # noqa: E731  (the pickle's residues as signed integers)
     with refrun.ReferenceRun(seed=SEED + 6) as rr:
         KZG = rr.kzg.KZG
 
@@ -303,29 +306,35 @@ def trace_marlin_normalized():
 
         sageshim.GFShim.random_element = rand
         try:
-            Fq = KZG("bn254").Fq
+            Fq = KZG(curve).Fq
             inst = fixtures.load_r1cs_instance(os.path.join(REF_CS, "R1CS_INSTANCE.pkl"))
-            A, B, C = (sageshim.matrix(Fq, inst[k]) for k in "ABC")
-            z = [Fq(v) for v in inst["z"]]
+            A, B, C = (sageshim.matrix(Fq, [[sg(v) for v in row] for row in inst[k]]) for k in "ABC")
+            z = [Fq(sg(v)) for v in inst["z"]]
             x, w = z[:5], z[5:]
-            ipk, ivk = rr.load("marlin.indexer").Indexer(curve_type="bn254").preprocess(A, B, C, max_degree=200)
+            ipk, ivk = rr.load("marlin.indexer").Indexer(curve_type=curve).preprocess(A, B, C, max_degree=200)
             n_index_draws, n_index_calls = len(draws), len(rr.trace)
-            proof = rr.load("marlin.prover").Prover(curve_type="bn254").prove(ipk, x, w)
+            proof = rr.load("marlin.prover").Prover(curve_type=curve).prove(ipk, x, w)
             n_prove_draws = len(draws)
-            ok = rr.load("marlin.verifier").Verifier(curve_type="bn254").verify(ivk, x, proof)
+            ok = rr.load("marlin.verifier").Verifier(curve_type=curve).verify(ivk, x, proof)
         finally:
             sageshim.GFShim.random_element = orig_rand
         assert ok
         pr = {"commitments": {k: [rr.enc_point(c) for c in v] for k, v in proof["commitments"].items()},
               "evaluations": {k: [rr.enc_scalar(e) for e in v] for k, v in proof["evaluations"].items()},
               "kzg_proofs": {k: rr.enc_point(v) for k, v in proof["kzg_proofs"].items()}}
-        dump("ref_marlin_normalized.json", {
+        dump("ref_marlin_normalized.json" if curve == "bn254" else "ref_marlin_normalized_bls.json", {
             "source": "reference marlin indexer + prover with commitments normalised to (x,y,1) before the transcript",
-            "seed": SEED + 6, "curve": "bn254", "index_draws": draws[:n_index_draws],
+            "seed": SEED + 6, "curve": curve, "index_draws": draws[:n_index_draws],
             "prover_draws": draws[n_index_draws:n_prove_draws], "keys": rr.keys,
             "x": [rr.enc_scalar(v) for v in x], "w": [rr.enc_scalar(v) for v in w],
             "prover_calls": [{k: v for k, v in c.items() if k != "out" or c["fn"] != "x"} for c in rr.trace[n_index_calls:]],
             "proof": pr, "notes": {"verify": bool(ok)}})
+
+
+def trace_marlin_normalized_bls():
+    """The reference's Marlin indexer / prover / verifier with curve_type="bls12_381" on the bundled R1CS instance (residues read as
+    signed integers): the bit-exact target of kzg_snark_b200.marlin on the second curve."""
+    trace_marlin_normalized("bls12_381")
 
 
 def trace_plonk_normalized(curve="bn254"):
@@ -404,3 +413,4 @@ if __name__ == "__main__":
     trace_marlin_normalized()
     trace_plonk_normalized()
     trace_plonk_normalized_bls()
+    trace_marlin_normalized_bls()

@@ -336,18 +336,23 @@ def test_marlin_indexer_matches_the_reference_indexer():
         assert ipk["evals"][kind].read_ints() == [H(v) for M in "ABC" for v in d["evals"][f"{kind}_{M}"]]
 
 
-def test_marlin_prover_matches_the_reference_prover_bit_for_bit():
+@pytest.mark.parametrize("fixture", ["ref_marlin_normalized.json", "ref_marlin_normalized_bls.json"])
+def test_marlin_prover_matches_the_reference_prover_bit_for_bit(fixture):
     """marlin/prover.py on the bundled R1CS instance (configs[4]), run by the reference itself with commitments normalised
-    to (x, y, 1) before the transcript (tests/golden/ref_marlin_normalized.json): the device prover, fed the same SRS and
-    the same 41 random draws, must produce the same polynomials in every round and the same proof."""
+    to (x, y, 1) before the transcript (tests/golden/ref_marlin_normalized*.json, curve_type "bn254" and "bls12_381"): the
+    device prover, fed the same SRS and the same 41 random draws, must produce the same polynomials in every round and the
+    same proof."""
     from kzg_snark_b200 import marlin
-    d = load("ref_marlin_normalized.json")
+    d = load(fixture)
+    curve = d["curve"]
+    rq, r_bn = CURVES[curve]["r"], CURVES["bn254"]["r"]
+    signed = lambda v: (v if v <= r_bn // 2 else v - r_bn) % rq          # noqa: E731  (the pickle's residues as signed integers)
     inst = json.load(open(os.path.join(GOLD, "r1cs_instance.json")))
-    A, B, C = ([[H(v) for v in row] for row in inst[k]] for k in "ABC")
-    idx = marlin.Indexer("bn254")
+    A, B, C = ([[signed(H(v)) for v in row] for row in inst[k]] for k in "ABC")
+    idx = marlin.Indexer(curve)
     ipk, _ = idx.preprocess(A, B, C, max_degree=200, tau=H(d["index_draws"][0]))
     Fq = idx.kzg.Fq
-    prover = marlin.Prover("bn254")
+    prover = marlin.Prover(curve)
     prover.capture = True
     proof = prover.prove(ipk, [Fq(H(v)) for v in d["x"]], [H(v) for v in d["w"]], draws=[H(v) for v in d["prover_draws"]])
     calls = [c for c in d["prover_calls"] if c["fn"] in ("commit", "open")]
