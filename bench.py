@@ -2,22 +2,22 @@
 """bench.py -- the driver's measurement contract for the KZG-MSM / NTT hot path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-                    [--workload msm|ntt] [--logn 24] [--scaling weak|strong]
+                    [--workload msm|ntt|sweep|plonk|marlin] [--curve bn254|bls12_381] [--logn 24]
 
-Default workload (`msm`): one step = one KZG commit of a 2^24-coefficient polynomial, i.e. one
-BN254 G1 MSM of 2^24 points against the device-resident SRS (BASELINE.json metric "G1 MSM
-points/s ... at 2^24"; configs[2]).  The same line also carries the NTT half of the metric
-(`"ntt"`: BN254 scalar-field NTT of 2^24 elements, configs[1]) with its own roofline.
-`--workload ntt` makes the NTT the primary metric instead.
+Default workload (`msm`): one step = one KZG commit of a 2^24-coefficient polynomial, i.e. one BN254 G1 MSM of 2^24
+points against the device-resident SRS (BASELINE.json metric "G1 MSM points/s ... at 2^24 (1/2/4/8 B200)"; configs[2]).
+The same line also carries the NTT half of the metric (`"ntt"`: scalar-field NTT of 2^24 elements, configs[1]) with its
+own roofline, and at N = 1 the PLONK / Marlin provers (configs[3], configs[4]).
 
-N > 1 (torchrun, one process per GPU, NCCL): the SRS points and the scalars are sharded by
-index range, every rank reduces its shard to one XYZZ partial sum, the partials are
-all-gathered over NCCL (128 B per rank) and folded.  Default scaling is "weak" (2^logn points
-per GPU); `--scaling strong` splits 2^logn points across the ranks.
+N > 1 (torchrun, one process per GPU, NCCL): the metric's own configuration -- ONE 2^24-point MSM split over the N
+ranks ("scaling": "strong"): SRS points and scalars are sharded by contiguous index range, every rank reduces its
+2^24/N points to one XYZZ partial sum, the partials are all-gathered over NCCL (128 B per rank) and folded.  `value` is
+2^24 points / step time.  The independent-shards variant (2^24 points per GPU) is reported beside it as `"weak"`.
 
-`--impl reference` times the reference algorithm's CPU restatement (oracle/: py_ecc-style
-double-and-add commit loop, kzg.py:112-116, recursive fft_ff, fft_ff.py:3-37) on all host
-cores, on a bounded sample of the same workload.
+`--workload sweep` prints configs[1] / configs[2] as tables (NTT 2^12..2^26, MSM 2^16..2^26: device-resident, host-buffer
+and CPU-port columns, a correctness check per size).  `--impl reference` times the reference's own `KZG.commit` loop
+(kzg.py:112-116, imported unmodified from baseline/_ref or /root/reference; SageMath / py_ecc replaced by the stand-ins
+of oracle/refrun.py) on all host cores, on a bounded sample of the same workload.
 """
 
 import argparse
@@ -32,25 +32,43 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 R_BN254 = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+R_BLS = 52435875175126190479447740508185965837690552500527637822603658699938581184513
+FR = {"bn254": R_BN254, "bls12_381": R_BLS}
+GEN = {"bn254": 5, "bls12_381": 7}                   # least primitive roots of the two scalar fields
+FP_BITS = {"bn254": 254, "bls12_381": 381}
 TAU = 0x2545F4914F6CDD1D9E3779B97F4A7C15F39CC0605CEDC834 % R_BN254      # fixed synthetic trapdoor
 
 # SURVEY.md section 8(d) work model: 16 windows x (8M+2S = 10 modmul) x 272 32-bit IMADs
 MODEL_IMAD_PER_POINT = 43520
 IMAD32_PER_MODMUL = 272
-MODMUL_PER_MADD = 10
-# what the accumulate kernel executes per mixed addition: 8 general products (64 + 64 + 8 wide multiplies = 272 IMAD32 each) and
-# 2 dedicated squarings (36 + 64 + 8 wide = 216 IMAD32 each, field.cuh fe_sqr_nofinal)
-IMAD32_EXECUTED_PER_MADD = 8 * 272 + 2 * 216
+# What the kernels EXECUTE, per N-limb Montgomery operation (field.cuh / mp_prims_gen.cuh; checked against the SASS of the
+# accumulate loop with scripts/sass_loop.py and against ncu's smsp__inst_executed): a general product issues 2N^2 - N
+# IMAD.WIDE (32x32+64 -> 64, one per 2 issue slots of the multiplier pipe) and 2N narrow IMAD / IMAD.HI (one slot: half
+# the cost); the dedicated squaring N(N+1)/2 + N^2 - N wide and 2N narrow.
+def wide_slots(nlimbs, products, squarings):
+    """multiplier-pipe work in IMAD.WIDE equivalents (narrow multiplies counted at half)."""
+    n = nlimbs
+    gen = (2 * n * n - n) + 0.5 * (2 * n)
+    sqr = (n * (n + 1) // 2 + n * n - n) + 0.5 * (2 * n)
+    return products * gen + squarings * sqr
+
+
+MADD = (8, 2)             # XYZZ mixed addition: 8 products + 2 squarings (curve.cuh xyzz_madd_lz)
+FULL_ADD = (12, 2)        # XYZZ + XYZZ
 
 
 def load_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture
-    (profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            return json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
-    except Exception:
-        return None
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` captures
+    (profiles/r2_traffic.json, else r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                v = json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
+            if v:
+                return v
+        except Exception:
+            pass
+    return None
 
 
 def load_peaks():
@@ -106,53 +124,85 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------- CPU arms
 def _cpu_commit_chunk(args):
-    """Worker: reference commit loop (kzg.py:112-116) over a slice of (scalar, index) pairs."""
-    seed, start, count, tau = args
+    """Worker: the commit loop kzg.py:112-116 over `count` (coefficient, SRS point) pairs.
+    kind "reference": the reference's OWN kzg.py (KZG.commit, imported unmodified) on the SageMath / py_ecc stand-ins;
+    kind "port": the oracle's restatement of the same loop."""
+    seed, count, tau, kind, curve = args
     import random
     from oracle.kzg import KZGOracle
-    ko = KZGOracle("bn254")
+    ko = KZGOracle(curve)
     rng = random.Random(seed)
-    # SRS slice via the oracle's shared-doubling setup (not timed by the caller? it is part of
-    # producing inputs) -- points tau^i * G1
-    ck = ko.setup_fast(count - 1, tau)
+    ck = ko.setup_fast(count - 1, tau)                   # input preparation (not timed): points tau^i * G1
     coeffs = [rng.randrange(ko.curve_order) for _ in range(count)]
+    if kind == "reference":
+        from oracle import refrun
+        with refrun.ReferenceRun(seed=seed, record=False) as rr:
+            kzg = rr.kzg.KZG(curve_type=curve)           # reference kzg.py:18
+            from oracle import pyecc_standin, pyecc_standin_bls
+            E = pyecc_standin if curve == "bn254" else pyecc_standin_bls
+            rck = [tuple(E.FQ(int(c)) for c in pt) for pt in ck]
+            poly = kzg.R([kzg.Fq(c) for c in coeffs])
+            t0 = time.perf_counter()
+            c = kzg.commit(rck, [poly])[0]               # reference kzg.py:80-120
+            dt = time.perf_counter() - t0
+        return dt, ko.cv.normalize(tuple(int(v) for v in c))
     t0 = time.perf_counter()
     c = ko.commit(ck, [coeffs])[0]
     dt = time.perf_counter() - t0
     return dt, ko.cv.normalize(c)
 
 
-def cpu_msm_rate(points_per_core, cores):
-    """points/s of the restated reference commit loop using `cores` processes."""
-    jobs = [(1000 + i, 0, points_per_core, TAU) for i in range(cores)]
+def reference_kind():
+    """("reference", note) when the reference's own sources are reachable, else ("port", note)."""
+    try:
+        from oracle import refrun
+        if refrun.available():
+            return "reference", ("reference kzg.py / fft_ff.py imported unmodified from " + refrun.REFERENCE_ROOT +
+                                 "; SageMath and py_ecc (not installable in this image) replaced by the stand-ins of oracle/refrun.py")
+    except Exception:
+        pass
+    return "port", "restated reference algorithm on CPython ints (oracle/): no reference tree on this box"
+
+
+def cpu_msm_rate(points_per_core, cores, kind="port", curve="bn254"):
+    """points/s of the reference commit loop using `cores` processes."""
+    jobs = [(1000 + i, points_per_core, TAU, kind, curve) for i in range(cores)]
     if cores == 1:
         res = [_cpu_commit_chunk(jobs[0])]
-        wall = res[0][0]
     else:
         import multiprocessing as mp
         with mp.get_context("fork").Pool(cores) as pool:
             res = pool.map(_cpu_commit_chunk, jobs)
-        wall = max(r[0] for r in res)          # commit loop time only (inputs prepared before)
+    wall = max(r[0] for r in res)              # commit loop time only (inputs prepared before)
     return points_per_core * cores / wall, wall
 
 
 def _cpu_ntt_chunk(args):
-    seed, logn = args
+    seed, logn, kind, curve = args
     import random
-    from oracle.fft_ff import fft_ff_int
+    r = FR[curve]
     rng = random.Random(seed)
     n = 1 << logn
-    x = [rng.randrange(R_BN254) for _ in range(n)]
-    w = pow(5, (R_BN254 - 1) // n, R_BN254)
+    x = [rng.randrange(r) for _ in range(n)]
+    w = pow(GEN[curve], (r - 1) // n, r)
+    if kind == "reference":
+        from oracle import refrun
+        with refrun.ReferenceRun(seed=seed, record=False) as rr:
+            F = rr.kzg.KZG(curve_type=curve).Fq
+            xs, ws = [F(v) for v in x], F(w)
+            t0 = time.perf_counter()
+            rr.fft_ff.fft_ff(xs, ws, F)                  # reference fft_ff.py:3-37
+            return time.perf_counter() - t0
+    from oracle.fft_ff import fft_ff_int
     t0 = time.perf_counter()
-    fft_ff_int(x, w, R_BN254)
+    fft_ff_int(x, w, r)
     return time.perf_counter() - t0
 
 
-def cpu_ntt_rate(logn, cores):
-    """elements/s of the restated recursive fft_ff; `cores` independent vectors in parallel
+def cpu_ntt_rate(logn, cores, kind="port", curve="bn254"):
+    """elements/s of the recursive fft_ff; `cores` independent vectors in parallel
     (the reference itself is single-threaded: batched vectors are its only parallelism)."""
-    jobs = [(2000 + i, logn) for i in range(cores)]
+    jobs = [(2000 + i, logn, kind, curve) for i in range(cores)]
     if cores == 1:
         wall = _cpu_ntt_chunk(jobs[0])
     else:
@@ -205,8 +255,42 @@ def dropin_hotpath(name):
     return {"dropin_hotpath_s": best[0], "calls": best[1], "reference_prove_s": best[2]}
 
 
-def cpu_plonk_hotpath():
-    return cpu_hotpath("plonk")
+def reference_prover_on_gpu_dropin(name):
+    """SURVEY.md 8(d) config 4 / 5 as defined there: the reference's UNMODIFIED plonk/ or marlin/ indexer, prover and verifier
+    (imported from baseline/_ref or /root/reference) with `kzg` / `fft_ff` resolved to the GPU drop-in; wall seconds of
+    `Prover.prove`, verifier must accept and the reference's tamper test must reject.  None without a reference tree."""
+    import pickle
+    from oracle import refrun
+    if not refrun.available():
+        return None
+    with refrun.ReferenceRun(seed=11, record=False, gpu_dropin=True) as rr:
+        Fq = rr.kzg.KZG("bn254").Fq
+        cs = os.path.join(refrun.REFERENCE_ROOT, "constraint-system")
+        if name == "plonk":
+            inst = pickle.load(open(os.path.join(cs, "PLONK_ARITHMETIZATION_INSTANCE.pkl"), "rb"))       # main.py:68-69
+            sel = [inst[k] for k in ("qM", "qL", "qR", "qO", "qC")]
+            w = [Fq(v) for v in inst["w"]]
+            x, wit = w[:5], w[5:]
+            ipk, ivk = rr.load("plonk.indexer").Indexer(curve_type="bn254").preprocess(*sel, inst["perm"], max_degree=len(sel[0]) + 5)
+            prover, V = rr.load("plonk.prover").Prover(curve_type="bn254"), rr.load("plonk.verifier").Verifier
+            tamper = lambda p: {**p, "evaluations": {**p["evaluations"], "a": p["evaluations"]["a"] + 1}}       # noqa: E731
+        else:
+            inst = pickle.load(open(os.path.join(cs, "R1CS_INSTANCE.pkl"), "rb"))                            # main.py:43-44
+            z = [Fq(v) for v in inst["z"]]
+            x, wit = z[:5], z[5:]
+            ipk, ivk = rr.load("marlin.indexer").Indexer(curve_type="bn254").preprocess(inst["A"], inst["B"], inst["C"], max_degree=200)
+            prover, V = rr.load("marlin.prover").Prover(curve_type="bn254"), rr.load("marlin.verifier").Verifier
+            tamper = lambda p: {**p, "evaluations": {**p["evaluations"], "beta1": [p["evaluations"]["beta1"][0] + 1] + list(p["evaluations"]["beta1"][1:])}}  # noqa: E731
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            proof = prover.prove(ipk, x, wit)
+            ts.append(time.perf_counter() - t0)
+        ok = bool(V(curve_type="bn254").verify(ivk, x, proof))
+        rejected = not V(curve_type="bn254").verify(ivk, x, tamper(proof))
+    return {"prove_s": min(ts), "verifier_accepts": ok, "tampered_rejected": bool(rejected),
+            "note": f"reference {name}/prover.py unmodified (from {refrun.REFERENCE_ROOT}) on the GPU kzg / fft_ff drop-in; host side = "
+                    "the reference's Python polynomial algebra on the Sage stand-in, so this is dominated by host work"}
 
 
 def run_reference(args):
@@ -214,38 +298,43 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
+    kind, note = reference_kind()
+    if args.force_port:
+        kind, note = "port", "restated reference algorithm on CPython ints (oracle/), forced with --force-port"
     vals, t_all = [], 0.0
-    if args.workload == "msm":
+    curve = args.curve
+    if args.workload in ("msm", "sweep", "plonk", "marlin"):
         per_core = 256
         unit, metric = "points/s", "g1_msm_points_per_s"
         for i in range(args.warmup + args.steps):
-            v, wall = cpu_msm_rate(per_core, cores)
+            v, wall = cpu_msm_rate(per_core, cores, kind, curve)
             if i >= args.warmup:
                 vals.append(v); t_all += wall
-        sample = f"{per_core * cores} random BN254 scalars x SRS points per step ({per_core}/core), commit loop kzg.py:112-116"
-        workload = f"BN254 G1 MSM (KZG commit) of 2^{args.logn} points"
+        sample = (f"{per_core * cores} random scalars x SRS points per step ({per_core} per core, {cores} processes), "
+                  f"KZG.commit loop kzg.py:112-116; the loop is strictly linear in the number of points")
+        workload = f"{curve} G1 MSM (KZG commit) of 2^{args.logn} points"
     else:
-        logn_s = 15
+        logn_s = 13
         unit, metric = "elements/s", "ntt_elements_per_s"
         for i in range(args.warmup + args.steps):
-            v, wall = cpu_ntt_rate(logn_s, cores)
+            v, wall = cpu_ntt_rate(logn_s, cores, kind, curve)
             if i >= args.warmup:
                 vals.append(v); t_all += wall
         sample = f"{cores} vectors of 2^{logn_s} elements per step (one per core), recursive fft_ff.py:3-37"
-        workload = f"BN254 scalar-field NTT of 2^{args.logn} elements"
+        workload = f"{curve} scalar-field NTT of 2^{args.logn} elements"
     value = sum(vals) / len(vals)
     line = {
         "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
-        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-        "dtype": "u32x8 (256-bit modular integers)", "data": "synthetic",
-        "config": {"workload": workload, "curve": "bn254", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample,
-                         "note": "restated reference algorithm on CPython ints (SageMath/py_ecc are not installable here)"},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32x8 (256-bit modular integers)" if curve == "bn254" else "u32x12 / u32x8 (384 / 256-bit modular integers)",
+        "data": "synthetic",
+        "config": {"workload": workload, "curve": curve, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind, "sample": sample, "note": note},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     return 0
 
 
@@ -256,11 +345,39 @@ class RawPtr:
         self.ptr = ctypes.c_void_p(p)
 
 
-def on_curve_bn254(out):
+def on_curve(out, curve):
+    from kzg_snark_b200 import device
     from kzg_snark_b200.limbs import limbs_to_ints
-    p = 21888242871839275222246405745257275088696311157297823662689037894645226208583
-    x, y = limbs_to_ints(out.reshape(2, 4))
-    return (y * y - x * x * x - 3) % p == 0
+    cid = device.curve_id(curve)
+    p, L = device.FP[cid], device.FP_LIMBS[cid]
+    x, y = limbs_to_ints(out.reshape(2, L))
+    return (y * y - x * x * x - (3 if cid == 0 else 4)) % p == 0
+
+
+def horner_dev(curve, dbuf, n, x):
+    """p(x) of the device-resident coefficient vector (kzgpu_poly_eval_dev): the scalar side of the tau-identity."""
+    import ctypes
+    import numpy as np
+    from kzg_snark_b200 import _ffi, device
+    from kzg_snark_b200.limbs import ints_to_limbs, limbs_to_int
+    cid = device.curve_id(curve)
+    out = np.zeros(4, dtype=np.uint64)
+    xl = ints_to_limbs([x], device.FR[cid])[0]
+    _ffi.check(_ffi._lib.kzgpu_poly_eval_dev(cid, dbuf.ptr, n, _ffi.ptr(xl), _ffi.ptr(out)))
+    return limbs_to_int(out)
+
+
+def tau_identity(curve, out, inf, e):
+    """commit(ck, p) == p(tau) * G1 (kzg.py:108) with e = p(tau): one device-side scalar multiplication of the generator."""
+    import numpy as np
+    from kzg_snark_b200 import device
+    from kzg_snark_b200.limbs import ints_to_limbs
+    from kzg_snark_b200.kzg import _G1
+    cid = device.curve_id(curve)
+    L = device.FP_LIMBS[cid]
+    g = np.concatenate([ints_to_limbs([c], device.FP[cid], L)[0] for c in _G1[curve]]).reshape(1, 2 * L)
+    exp, einf = device.g1_lincomb(cid, g, ints_to_limbs([e], device.FR[cid]))
+    return bool(inf) == bool(einf) and (bool(inf) or bool((exp == out).all()))
 
 
 def run_gpu(args):
@@ -274,8 +391,8 @@ def run_gpu(args):
     dist = None
     torch = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+        # NCCL_DEBUG is left as the caller set it (the harness reads the communicator lines); the result line is printed
+        # last, on its own line, by rank 0
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -284,12 +401,11 @@ def run_gpu(args):
     info = _ffi.device_info()
     peaks, peak_src = load_peaks()
     K, Wm = args.steps, args.warmup
+    curve = args.curve
+    cid = device.curve_id(curve)
+    r_mod = FR[curve]
+    nl = 8 if curve == "bn254" else 12                    # base-field limbs (32-bit)
     n_total = 1 << args.logn
-    if world > 1 and args.scaling == "strong":
-        n = n_total // world
-    else:
-        n = n_total                           # weak: per-GPU work fixed
-    start = rank * n
     if world > 1:
         # one stream for torch (NCCL's wait lands on the current stream) and the library, so that the fold of the gathered
         # partials is ordered after the all-gather.  It must be a side stream: torch's default stream has handle 0, which
@@ -309,43 +425,57 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    result = {}
-
     # ------------------------------------------------------------------ integer roofline (live)
     sm = info["sm_count"]
     ms_i, ops_i = _ffi.microbench(0, sm * 4, 256, 2000)
-    imad_wide_peak = ops_i / ms_i * 1e3                   # IMAD.WIDE.U32 / s
-    imad32_peak = 2.0 * imad_wide_peak                    # one wide = two 32-bit multiply-add slots
+    imad_wide_peak = ops_i / ms_i * 1e3                   # IMAD.WIDE.U32 / s, measured now on this GPU
+    imad32_peak = 2.0 * imad_wide_peak                    # one wide = two 32-bit multiply-add slots (the SURVEY model's unit)
 
     # ------------------------------------------------------------------ MSM
-    def bench_msm():
-        srs = device.Srs.generate("bn254", TAU, n, start=start)
+    def msm_case(n, start, seed, want_e2e=True, want_profile=True, pageable=False):
+        """One rank's share: `n` points [start, start + n) of the key; world ranks together form one MSM."""
+        t0 = time.perf_counter()
+        srs = device.Srs.generate(curve, TAU, n, start=start)
+        _ffi.check(_ffi._lib.kzgpu_sync())
+        build_s = time.perf_counter() - t0
+        key = srs.info()
         pinned = _ffi.PinnedArray((n, 4))
-        pinned.array[:] = random_scalars(n, R_BN254, seed=args.logn * 100 + rank)
+        pinned.array[:] = random_scalars(n, r_mod, seed=seed)
         dsc = _ffi.DeviceBuffer(n * 32).upload(pinned.array)
+        xyzz = 4 * nl * 4
         if world > 1:
-            partial = torch.zeros(128, dtype=torch.uint8, device="cuda")
-            gathered = torch.zeros(128 * world, dtype=torch.uint8, device="cuda")
+            partial = torch.zeros(xyzz, dtype=torch.uint8, device="cuda")
+            gathered = torch.zeros(xyzz * world, dtype=torch.uint8, device="cuda")
+
+        def fold():
+            dist.all_gather_into_tensor(gathered, partial)
+            return device.g1_fold(curve, RawPtr(gathered.data_ptr()), world)
 
         def step_resident():
             if world == 1:
                 return device.msm_dev(srs, dsc, n)
             device.msm_partial_dev(srs, dsc, n, RawPtr(partial.data_ptr()))
-            dist.all_gather_into_tensor(gathered, partial)
-            return device.g1_fold("bn254", RawPtr(gathered.data_ptr()), world)
+            return fold()
 
-        def step_e2e():
+        def step_e2e(host):
             if world == 1:
-                return device.msm(srs, pinned.array)       # H2D of the scalars inside the call
-            device.msm_partial(srs, pinned.array, RawPtr(partial.data_ptr()))     # this rank's H2D inside the call, overlapped
-            dist.all_gather_into_tensor(gathered, partial)
-            return device.g1_fold("bn254", RawPtr(gathered.data_ptr()), world)
+                return device.msm(srs, host)                  # H2D of the scalars inside the call
+            device.msm_partial(srs, host, RawPtr(partial.data_ptr()))       # this rank's H2D inside the call, overlapped
+            return fold()
 
         for _ in range(Wm):
             if world > 1:
                 gathered.zero_()                                 # a fold that ran ahead of the all-gather would see infinity
             out, inf = step_resident()
-            assert not inf and on_curve_bn254(out), "MSM result is not a curve point"
+            assert not inf and on_curve(out, curve), "MSM result is not a curve point"
+        # the tau-identity at full size (kzg.py:108): sum over the ranks of p_rank(tau) * tau^start
+        e = horner_dev(curve, dsc, n, TAU % r_mod) * pow(TAU, start, r_mod) % r_mod
+        if dist is not None:
+            parts = [None] * world
+            dist.all_gather_object(parts, e)
+            e = sum(parts) % r_mod
+        check_ok = tau_identity(curve, out, inf, e)
+        assert check_ok, "MSM result violates the tau-identity commit == p(tau) * G1"
         # timed region: resident inputs, device clock
         sampler = ClockSampler(local)
         barrier()
@@ -360,103 +490,256 @@ def run_gpu(args):
         barrier()
         launches = _ffi.launch_count() - l0
         ms = max_over_ranks(ms)
-        # per-kernel profile (second region, CUDA events around the kernels on the launching stream)
-        _ffi.profile_reset(); _ffi.profile_enable(True)
-        for _ in range(K):
-            step_resident()
-        _ffi.profile_enable(False)
-        prof = {k: _ffi.profile_get(i) for k, i in (("accumulate", 0), ("sort", 2), ("reduce", 3))}
-        # e2e: host (pinned) scalars in, affine point out, every step (warmed up like the resident region: the chunked
-        # entry point allocates its staging buffer and second sort workspace on first use)
-        for _ in range(Wm):
-            step_e2e()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(K):
-            step_e2e()
-        barrier()
-        ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
-        clocks = sampler.stop()                                  # sampled over the timed, per-kernel and e2e regions
+        res = {"ms": ms, "launches": launches, "key": key, "build_s": build_s, "n": n, "check": bool(check_ok)}
+        if want_profile:
+            # per-kernel profile (second region, CUDA events around the kernels on the launching stream)
+            _ffi.profile_reset(); _ffi.profile_enable(True)
+            for _ in range(K):
+                step_resident()
+            _ffi.profile_enable(False)
+            res["prof"] = {k: _ffi.profile_get(i) for k, i in (("accumulate", 0), ("sort", 2), ("reduce", 3))}
+        if want_e2e:
+            # e2e: host scalars in, affine point out, every step (warmed up like the resident region: the chunked entry
+            # point allocates its staging buffer and second sort workspace on first use)
+            for _ in range(Wm):
+                step_e2e(pinned.array)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(K):
+                step_e2e(pinned.array)
+            barrier()
+            res["ms_e2e"] = max_over_ranks((time.perf_counter() - t0) * 1e3)
+            if pageable:
+                # the same call from an ordinary (pageable) numpy array -- what the Python drop-in hands over
+                heap = np.array(pinned.array, copy=True)
+                for _ in range(2):
+                    step_e2e(heap)
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(K):
+                    step_e2e(heap)
+                barrier()
+                res["ms_e2e_pageable"] = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        res["clocks"] = sampler.stop()                           # sampled over the timed, per-kernel and e2e regions
+        srs.destroy(); dsc.free(); pinned.free()
+        return res
+
+    def bench_msm():
+        strong = world > 1
+        n = n_total // world if strong else n_total
+        r = msm_case(n, rank * n, seed=args.logn * 100 + rank, pageable=(world == 1))
+        ms, prof = r["ms"], r["prof"]
         acc = prof["accumulate"]                                 # the bucket-accumulate kernel alone, one launch per MSM
         acc_ms = acc["ms"] / max(acc["launches"], 1)
         madds = acc["work"] / max(acc["launches"], 1)            # mixed additions per launch (n * windows upper bound)
-        pts_per_s = world * n * K / (ms * 1e-3)
+        red = prof["reduce"]
+        buckets = red["work"] / max(red["launches"], 1)          # buckets of the pass: 2 full additions each in the reduce
+        acc_slots = madds * wide_slots(nl, *MADD)
+        step_slots = acc_slots + 2.0 * buckets * wide_slots(nl, *FULL_ADD)
+        total_pts = world * n
+        pts_per_s = total_pts * K / (ms * 1e-3)
+        frac = acc_slots / (acc_ms * 1e-3) / imad_wide_peak
         res = {
-            "value": pts_per_s, "ms": ms, "launches": launches, "clocks": clocks,
-            "e2e": {"value": world * n * K / (ms_e2e * 1e-3), "unit": "points/s",
-                    "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": (64 + 4) * world,
-                    "ms_per_step": ms_e2e / K, "host_buffers": "pinned (cudaHostAlloc)"},
+            "value": pts_per_s, "ms": ms, "launches": r["launches"], "clocks": r["clocks"], "n_per_rank": n, "key": r["key"],
+            "build_s": r["build_s"], "check": r["check"],
+            "e2e": {"value": total_pts * K / (r["ms_e2e"] * 1e-3), "unit": "points/s",
+                    "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": (2 * nl * 4 + 4) * world,
+                    "ms_per_step": r["ms_e2e"] / K, "host_buffers": "pinned (cudaHostAlloc)"},
             "roofline": {
                 "bound": "imad", "kernel": "msm_accumulate_kernel",
-                "achieved": (n / (acc_ms * 1e-3)) * MODEL_IMAD_PER_POINT / 1e9,
-                "peak": imad32_peak / 1e9, "unit": "G IMAD32/s",
-                "frac": (n / (acc_ms * 1e-3)) * MODEL_IMAD_PER_POINT / imad32_peak,
-                "traffic": load_traffic("msm_accumulate_kernel") if args.logn == 24 else None,
-                "model": "SURVEY 8(d): 43,520 32-bit IMAD per point (16 windows x 10 modmul x 272); "
-                         "peak = live IMAD.WIDE.U32 microbenchmark x 2",
-                "executed_frac": madds * IMAD32_EXECUTED_PER_MADD / (acc_ms * 1e-3) / imad32_peak,
+                "achieved": acc_slots / (acc_ms * 1e-3) / 1e9, "peak": imad_wide_peak / 1e9, "unit": "G IMAD.WIDE/s",
+                "frac": frac,
+                "traffic": load_traffic("msm_accumulate_kernel") if (args.logn == 24 and world == 1 and curve == "bn254") else None,
+                "model": f"executed multiplier work: {madds / n:.0f} mixed additions per point (fixed-base tables, c = {r['key']['c']}) x "
+                         f"{wide_slots(nl, *MADD):.0f} IMAD.WIDE-equivalents (8 products + 2 squarings on {nl} limbs; narrow IMAD / IMAD.HI "
+                         "counted at half) / kernel time / IMAD.WIDE.U32 issue rate measured live (kzgpu_microbench 0); "
+                         "compare ncu sm__pipe_fma_cycles_active / 50 % in profiles/",
+                "step_frac": step_slots / (ms / K * 1e-3) / imad_wide_peak,
+                "model_frac": (n / (acc_ms * 1e-3)) * MODEL_IMAD_PER_POINT / imad32_peak,
+                "model_frac_note": "SURVEY 8(d) model figure (16 windows x 10 modmul x 272 IMAD32 per point) / (2 x IMAD.WIDE peak); "
+                                   "exceeds 1 because the kernel executes fewer windows and cheaper squarings than the model charges",
                 "kernel_ms": acc_ms, "kernel_share_of_step": acc["ms"] / max(sum(p["ms"] for p in prof.values()), 1e-9),
-                "hbm_algorithmic_gbs": n * 96 / (acc_ms * 1e-3) / 1e9,
+                "hbm_algorithmic_gbs": n * (2 * nl * 4 + 32) / (acc_ms * 1e-3) / 1e9,
                 "hbm_peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src,
             },
             "profile_ms_per_step": {k: v["ms"] / K for k, v in prof.items()},
         }
-        srs.destroy(); dsc.free(); pinned.free()
+        if "ms_e2e_pageable" in r:
+            res["e2e"]["pageable"] = {"value": total_pts * K / (r["ms_e2e_pageable"] * 1e-3), "ms_per_step": r["ms_e2e_pageable"] / K,
+                                      "host_buffers": "pageable numpy array (cudaMemcpyAsync stages through the driver's bounce buffer)"}
+        if strong:
+            # the independent-shards variant beside it: 2^logn points per GPU
+            wr = msm_case(n_total, rank * n_total, seed=args.logn * 100 + 50 + rank, want_e2e=True, want_profile=False)
+            res["weak"] = {"scaling": "weak", "points_per_gpu": n_total, "value": world * n_total * K / (wr["ms"] * 1e-3),
+                           "ms_per_step": wr["ms"] / K, "key": wr["key"],
+                           "e2e": {"value": world * n_total * K / (wr["ms_e2e"] * 1e-3), "ms_per_step": wr["ms_e2e"] / K,
+                                   "h2d_bytes_per_step": n_total * 32 * world}}
         return res
 
     # ------------------------------------------------------------------ NTT
     def bench_ntt():
-        w = pow(5, (R_BN254 - 1) // n_total, R_BN254)
-        wl = ints_to_limbs([w], R_BN254)[0]
+        w = pow(GEN[curve], (r_mod - 1) // n_total, r_mod)
+        wl = ints_to_limbs([w], r_mod)[0]
         pinned = _ffi.PinnedArray((n_total, 4))
-        pinned.array[:] = random_scalars(n_total, R_BN254, seed=args.logn + 7 * rank)
+        pinned.array[:] = random_scalars(n_total, r_mod, seed=args.logn + 7 * rank)
         d = _ffi.DeviceBuffer(n_total * 32).upload(pinned.array)
         for _ in range(Wm):
-            device.ntt_dev("bn254", d, n_total, wl)
+            device.ntt_dev(curve, d, n_total, wl)
         sampler = ClockSampler(local)
         barrier()
         l0 = _ffi.launch_count()
         _ffi.timer_start()                                      # events on the library's launching stream, any world size
         for _ in range(K):
-            device.ntt_dev("bn254", d, n_total, wl)
+            device.ntt_dev(curve, d, n_total, wl)
         ms = _ffi.timer_stop()
         barrier()
         launches = _ffi.launch_count() - l0
         ms = max_over_ranks(ms)
         _ffi.profile_reset(); _ffi.profile_enable(True)
         for _ in range(K):
-            device.ntt_dev("bn254", d, n_total, wl)
+            device.ntt_dev(curve, d, n_total, wl)
         _ffi.profile_enable(False)
         pr = _ffi.profile_get(1)
         for _ in range(Wm):                                     # warm-up of the host-buffer entry point (staging buffer, events)
-            device.ntt("bn254", pinned.array, wl)
+            device.ntt(curve, pinned.array, wl)
         barrier()
         t0 = time.perf_counter()
         for _ in range(K):
-            device.ntt("bn254", pinned.array, wl)            # H2D + kernels + D2H inside the call
+            device.ntt(curve, pinned.array, wl)              # H2D + kernels + D2H inside the call
         barrier()
         ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        # the transfers alone (same bytes, same buffers, all ranks at once): the host-side ceiling of the e2e number
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            d.upload(pinned.array)
+            d.download(pinned.array)
+        barrier()
+        ms_copy = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        e2e = {"value": world * n_total * K / (ms_e2e * 1e-3), "unit": "elements/s",
+               "h2d_bytes_per_step": n_total * 32 * world, "d2h_bytes_per_step": n_total * 32 * world,
+               "ms_per_step": ms_e2e / K, "host_buffers": "pinned (cudaHostAlloc)",
+               "copy_only_ms_per_step": ms_copy / K,
+               "copy_only_note": "H2D + D2H of the same buffers with no kernel, all ranks at once: every output depends on every "
+                                 "input, so a single vector cannot overlap its two transfers; e2e - copy_only is what the NTT adds"}
+        if world == 1:
+            heap = np.array(pinned.array, copy=True)
+            for _ in range(2):
+                device.ntt(curve, heap, wl)
+            t0 = time.perf_counter()
+            for _ in range(K):
+                device.ntt(curve, heap, wl)
+            msp = (time.perf_counter() - t0) * 1e3
+            e2e["pageable"] = {"value": n_total * K / (msp * 1e-3), "ms_per_step": msp / K, "host_buffers": "pageable numpy array"}
+            # batched host vectors: vector k's download overlaps vector k+1's upload (full duplex)
+            nb, bl = 4, args.logn - 2
+            wb = ints_to_limbs([pow(GEN[curve], (r_mod - 1) >> bl, r_mod)], r_mod)[0]
+            batch = pinned.array.reshape(nb, (1 << bl), 4)
+            for _ in range(2):
+                device.ntt(curve, batch.reshape(-1, 4), wb, batch=nb)
+            t0 = time.perf_counter()
+            for _ in range(K):
+                device.ntt(curve, batch.reshape(-1, 4), wb, batch=nb)
+            msb = (time.perf_counter() - t0) * 1e3
+            e2e["batched"] = {"vectors": nb, "logn": bl, "value": n_total * K / (msb * 1e-3), "ms_per_step": msb / K,
+                              "note": "kzgpu_ntt_batch from pinned host memory: per-vector pipeline, uploads and downloads on separate copy streams"}
         clocks = sampler.stop()
         ntt_ms = pr["ms"] / K                                   # all passes of one transform
         hbm = 64.0 * n_total / (ntt_ms * 1e-3) / 1e9
         modmuls = 0.5 * n_total * args.logn
         res = {
-            "value": world * n_total * K / (ms * 1e-3), "ms": ms, "launches": launches, "clocks": clocks,
-            "e2e": {"value": world * n_total * K / (ms_e2e * 1e-3), "unit": "elements/s",
-                    "h2d_bytes_per_step": n_total * 32 * world, "d2h_bytes_per_step": n_total * 32 * world,
-                    "ms_per_step": ms_e2e / K, "host_buffers": "pinned (cudaHostAlloc)"},
+            "value": world * n_total * K / (ms * 1e-3), "ms": ms, "launches": launches, "clocks": clocks, "e2e": e2e,
             "roofline": {
-                "bound": "hbm", "kernel": "ntt_pass_kernel_c<FrBN254, 8, lazy> (all passes of one transform)",
+                "bound": "hbm", "kernel": f"ntt_pass_kernel_c<Fr {curve}, 8> (all passes of one transform)",
                 "achieved": hbm, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": hbm / peaks.get("hbm_gbs"),
-                "traffic": load_traffic("ntt_pass_kernel") if args.logn == 24 else None, "peak_source": peak_src,
+                "traffic": load_traffic("ntt_pass_kernel") if (args.logn == 24 and curve == "bn254") else None, "peak_source": peak_src,
                 "model": "SURVEY 8(d): algorithmic bytes = 2 x 32 B x n (twiddles not counted)",
                 "passes": pr["launches"] // K, "kernel_ms": ntt_ms,
-                "imad_frac": modmuls * IMAD32_PER_MODMUL / (ntt_ms * 1e-3) / imad32_peak,
-                "imad_model": "SURVEY 8(d): (n/2) log2 n modmul x 272 IMAD32; the binding bound for 256-bit fields",
+                "imad_model_frac": modmuls * IMAD32_PER_MODMUL / (ntt_ms * 1e-3) / imad32_peak,
+                "imad_model": "SURVEY 8(d): (n/2) log2 n modmul x 272 IMAD32 -- the binding bound for 256-bit fields, but a MODEL: radix-8 "
+                              "butterflies have trivial twiddles the model charges for; the executed figure is ncu's "
+                              "sm__pipe_fma_cycles_active / 50 % (profiles/: 0.82 at 2^24)",
             },
         }
         d.free(); pinned.free()
         return res
+
+    # ------------------------------------------------------------------ sweeps (configs[1], configs[2])
+    def bench_sweep():
+        """NTT 2^12..2^26 and MSM 2^16..2^26 on one GPU (per rank at N > 1: independent replicas are not what this workload is for,
+        so it runs on rank 0's GPU only).  Per size: device-resident ms (CUDA events, median), host-buffer ms (pinned host arrays,
+        copies inside the call), the CPU port (measured where it finishes in ~a second, else extrapolated and marked `~`), and a
+        size-independent check: NTT -- Horner spot checks on the device + inverse round trip; MSM -- the tau-identity."""
+        rows = {"ntt": [], "msm": []}
+        med = lambda ts: sorted(ts)[len(ts) // 2]                        # noqa: E731
+        reps = max(3, min(K, 7))
+        cpu_ntt = {}
+        if not args.no_cpu:
+            for lg in (12, 14, 16):
+                cpu_ntt[lg] = (1 << lg) / cpu_ntt_rate(lg, 1, "port", curve)[0]
+            base_msm = 1.0 / cpu_msm_rate(1024, 1, "port", curve)[0]                  # seconds per point
+        for lg in range(12, min(args.sweep_max, 26) + 1, 2):
+            n = 1 << lg
+            w = pow(GEN[curve], (r_mod - 1) // n, r_mod)
+            wl = ints_to_limbs([w], r_mod)[0]
+            pin = _ffi.PinnedArray((n, 4))
+            x = random_scalars(n, r_mod, seed=lg)
+            pin.array[:] = x
+            d = _ffi.DeviceBuffer(n * 32).upload(x)
+            keep = _ffi.DeviceBuffer(n * 32).upload(x)
+            for _ in range(3):
+                device.ntt_dev(curve, d, n, wl)
+            ts = []
+            for _ in range(reps):
+                _ffi.timer_start(); device.ntt_dev(curve, d, n, wl); ts.append(_ffi.timer_stop())
+            # check: forward transform of x, out[k] == p_x(w^k) at three k (device Horner), then the inverse returns x
+            d.upload(x)
+            device.ntt_dev(curve, d, n, wl)
+            y = np.zeros_like(x); d.download(y)
+            ok = all(limbs_to_ints(y[k:k + 1])[0] == horner_dev(curve, keep, n, pow(w, k, r_mod)) for k in (0, 1, n // 2 + 3))
+            device.ntt_dev(curve, d, n, wl, inverse=True)
+            z = np.zeros_like(x); d.download(z)
+            ok = ok and bool((z == x).all())
+            for _ in range(2):
+                device.ntt(curve, pin.array, wl)
+            th = []
+            for _ in range(reps):
+                t0 = time.perf_counter(); device.ntt(curve, pin.array, wl); th.append((time.perf_counter() - t0) * 1e3)
+            cpu_s, cpu_mark = None, ""
+            if cpu_ntt:
+                if lg in cpu_ntt:
+                    cpu_s = cpu_ntt[lg]
+                else:
+                    cpu_s, cpu_mark = cpu_ntt[16] * (n * lg) / ((1 << 16) * 16), "~"        # fft_ff is Theta(n log n)
+            rows["ntt"].append({"logn": lg, "device_ms": med(ts), "host_buffer_ms": med(th), "elements_per_s": n / med(ts) * 1e3,
+                                "cpu_port_s": cpu_s, "cpu_extrapolated": cpu_mark == "~", "check": bool(ok)})
+            d.free(); keep.free(); pin.free()
+        for lg in range(16, min(args.sweep_max, 26) + 1, 2):
+            n = 1 << lg
+            t0 = time.perf_counter()
+            srs = device.Srs.generate(curve, TAU, n)
+            _ffi.check(_ffi._lib.kzgpu_sync())
+            tb = time.perf_counter() - t0
+            pin = _ffi.PinnedArray((n, 4))
+            pin.array[:] = random_scalars(n, r_mod, seed=100 + lg)
+            d = _ffi.DeviceBuffer(n * 32).upload(pin.array)
+            for _ in range(2):
+                out, inf = device.msm_dev(srs, d, n)
+            ts = []
+            for _ in range(reps):
+                _ffi.timer_start(); out, inf = device.msm_dev(srs, d, n); ts.append(_ffi.timer_stop())
+            ok = tau_identity(curve, out, inf, horner_dev(curve, d, n, TAU % r_mod))
+            for _ in range(2):
+                device.msm(srs, pin.array)
+            th = []
+            for _ in range(reps):
+                t0 = time.perf_counter(); device.msm(srs, pin.array); th.append((time.perf_counter() - t0) * 1e3)
+            key = srs.info()
+            rows["msm"].append({"logn": lg, "device_ms": med(ts), "host_buffer_ms": med(th), "points_per_s": n / med(ts) * 1e3,
+                                "cpu_port_s": None if args.no_cpu else base_msm * n, "cpu_extrapolated": not args.no_cpu,
+                                "key": key, "srs_build_s": tb, "check": bool(ok)})
+            d.free(); pin.free(); srs.destroy()
+        return rows
 
     # ------------------------------------------------------------------ PLONK prove (configs[3])
     def bench_plonk():
@@ -519,6 +802,12 @@ def run_gpu(args):
         out["marlin_bundled"] = {**dropin_hotpath("marlin"),
                                  "note": "configs[4] bundled R1CS instance: the 19 commit / open / fft_ff / fft_ff_interpolation calls "
                                          "marlin/prover.py made (tests/golden/ref_trace_marlin.json), replayed through the drop-in"}
+        if not args.no_cpu:
+            for nm, key in (("plonk", "bundled"), ("marlin", "marlin_bundled")):
+                try:
+                    out[key]["reference_prover_on_gpu_dropin"] = reference_prover_on_gpu_dropin(nm)
+                except Exception as exc:                                 # the bench line must survive a missing reference tree
+                    out[key]["reference_prover_on_gpu_dropin"] = {"error": repr(exc)[:200]}
         # configs[4]: the device Marlin prover on the bundled R1CS instance (proof compared with the reference prover's) and on a
         # synthetic R1CS of 2^marlin_rows_logn rows
         from kzg_snark_b200 import marlin
@@ -661,87 +950,129 @@ def run_gpu(args):
                 "items": {"commits": commits, "ntts": [[a, "inverse" if b else "forward"] for a, b in ntts], "opens": opens},
                 "srs_points": srs_n, "srs": srs.info()}
 
-    if args.workload == "marlin":
-        res = bench_marlin()
-        if rank == 0:
-            print(json.dumps({"metric": "marlin_kernel_workload_s", "value": res["ms"] / K / 1e3, "unit": "s", "n_gpus": world,
-                              "steps": K, "warmup": Wm, "ms_per_step": res["ms"] / K, "higher_is_better": False,
-                              "scaling": "strong", "vs_baseline": None,
-                              "dtype": "u32x8 (256-bit modular integers, Montgomery)", "data": "synthetic",
-                              "config": {"workload": f"commit/open/NTT calls of one Marlin proof, 2^{args.marlin_logn} constraints "
-                                                     f"(|H|=2^{args.marlin_logn}, |K|=2^{args.marlin_logn + 1}) on {world} GPUs: MSMs of >= 2^22 points point-sharded over all ranks, "
-                                                     "the rest assigned longest-first, SRS replicated", "items": res["items"], "srs_points": res["srs_points"],
-                                         "srs_layout": res["srs"]},
-                              "clocks": res["clocks"], "gpu_launches": res["launches"], "device": info["name"]}))
+    dtype = "u32x8 (256-bit modular integers, Montgomery)" if curve == "bn254" else \
+        "u32x12 base field / u32x8 scalars (384 / 256-bit modular integers, Montgomery)"
+
+    def finish():
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
         return 0
+
+    def emit(line):
+        sys.stdout.write("\n" + json.dumps(line) + "\n")
+        sys.stdout.flush()
+
+    if args.workload == "marlin":
+        res = bench_marlin()
+        if rank == 0:
+            emit({"metric": "marlin_kernel_workload_s", "value": res["ms"] / K / 1e3, "unit": "s", "n_gpus": world,
+                  "steps": K, "warmup": Wm, "ms_per_step": res["ms"] / K, "higher_is_better": False,
+                  "scaling": "strong", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+                  "config": {"workload": f"commit/open/NTT calls of one Marlin proof, 2^{args.marlin_logn} constraints "
+                                         f"(|H|=2^{args.marlin_logn}, |K|=2^{args.marlin_logn + 1}) on {world} GPUs: MSMs of >= 2^22 points point-sharded over all ranks, "
+                                         "the rest assigned longest-first, SRS replicated", "items": res["items"], "srs_points": res["srs_points"],
+                             "srs_layout": res["srs"]},
+                  "clocks": res["clocks"], "gpu_launches": res["launches"], "device": info["name"]})
+        return finish()
+
+    if args.workload == "sweep":
+        rows = bench_sweep() if rank == 0 else None
+        if rank == 0:
+            top = rows["msm"][-1] if rows["msm"] else {"points_per_s": 0.0, "device_ms": 0.0}
+            emit({"metric": "g1_msm_points_per_s", "value": top["points_per_s"], "unit": "points/s", "n_gpus": 1, "steps": K, "warmup": Wm,
+                  "ms_per_step": top["device_ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype,
+                  "data": "synthetic",
+                  "config": {"workload": f"configs[1] + configs[2] sweeps on one GPU, {curve}: NTT 2^12..2^{min(args.sweep_max, 26)}, MSM 2^16..2^{min(args.sweep_max, 26)}; "
+                                         "value = the largest MSM of the sweep", "curve": curve,
+                             "columns": "device_ms: resident inputs, CUDA events, median; host_buffer_ms: pinned host arrays in / result out, wall clock; "
+                                        "cpu_port_s: oracle port on 1 core (cpu_extrapolated marks n log n / linear extrapolation); "
+                                        "check: NTT Horner spot checks + inverse round trip, MSM tau-identity commit == p(tau) * G1"},
+                  "sweep": rows, "device": info["name"]})
+            sys.stderr.write("\n| NTT n | device ms | host-buffer ms | elements/s | CPU port s | check |\n|---|---|---|---|---|---|\n")
+            for r_ in rows["ntt"]:
+                cpu = "-" if r_["cpu_port_s"] is None else f"{'~' if r_['cpu_extrapolated'] else ''}{r_['cpu_port_s']:.3g}"
+                sys.stderr.write(f"| 2^{r_['logn']} | {r_['device_ms']:.3f} | {r_['host_buffer_ms']:.3f} | {r_['elements_per_s']:.3e} | {cpu} | {'ok' if r_['check'] else 'FAIL'} |\n")
+            sys.stderr.write("\n| MSM n | device ms | host-buffer ms | points/s | CPU port s | key | build s | check |\n|---|---|---|---|---|---|---|---|\n")
+            for r_ in rows["msm"]:
+                cpu = "-" if r_["cpu_port_s"] is None else f"~{r_['cpu_port_s']:.3g}"
+                k_ = r_["key"]
+                sys.stderr.write(f"| 2^{r_['logn']} | {r_['device_ms']:.3f} | {r_['host_buffer_ms']:.3f} | {r_['points_per_s']:.3e} | {cpu} | "
+                                 f"c={k_['c']} W={k_['tables']} {k_['bytes'] / 2**30:.2f} GiB | {r_['srs_build_s']:.2f} | {'ok' if r_['check'] else 'FAIL'} |\n")
+        return finish()
 
     primary = bench_msm() if args.workload == "msm" else (bench_ntt() if args.workload == "ntt" else None)
     secondary = None
     if args.workload == "msm" and not args.no_secondary:
         secondary = bench_ntt()
     plonk = None
-    if world == 1 and (args.workload == "plonk" or not args.no_secondary):
+    if world == 1 and curve == "bn254" and (args.workload == "plonk" or not args.no_secondary):
         plonk = bench_plonk()
     if args.workload == "plonk":
         if rank == 0:
-            print(json.dumps({"metric": "plonk_prove_s", "value": plonk["synthetic"]["prove_s"], "unit": "s", "n_gpus": 1,
-                              "steps": 5, "warmup": 3, "ms_per_step": 1e3 * plonk["synthetic"]["prove_s"],
-                              "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
-                              "dtype": "u32x8 (256-bit modular integers, Montgomery)", "data": "synthetic",
-                              "config": {"workload": f"PLONK prove, synthetic circuit of 2^{args.plonk_logn} gates, BN254"},
-                              "plonk": plonk, "device": info["name"]}))
-        return 0
+            emit({"metric": "plonk_prove_s", "value": plonk["synthetic"]["prove_s"], "unit": "s", "n_gpus": 1,
+                  "steps": 5, "warmup": 3, "ms_per_step": 1e3 * plonk["synthetic"]["prove_s"],
+                  "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+                  "config": {"workload": f"PLONK prove, synthetic circuit of 2^{args.plonk_logn} gates, BN254"},
+                  "plonk": plonk, "device": info["name"]})
+        return finish()
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         if args.workload == "msm":
-            v, wall = cpu_msm_rate(4096, 1)
+            v, wall = cpu_msm_rate(4096 if curve == "bn254" else 1536, 1, "port", curve)
             cpu = {"value": v, "unit": "points/s", "cores": 1, "kind": "port",
-                   "sample": f"4096-point commit (kzg.py:112-116 loop on the restated py_ecc arithmetic), {wall:.1f} s",
+                   "sample": f"{4096 if curve == 'bn254' else 1536}-point commit (kzg.py:112-116 loop on the restated py_ecc arithmetic), {wall:.1f} s",
                    "host_cpus": os.cpu_count()}
             if secondary is not None:
-                v2, wall2 = cpu_ntt_rate(17, 1)
+                v2, wall2 = cpu_ntt_rate(17, 1, "port", curve)
                 secondary["cpu_baseline"] = {"value": v2, "unit": "elements/s", "cores": 1, "kind": "port",
                                              "sample": f"2^17-element recursive fft_ff (fft_ff.py:3-37 on CPython ints), {wall2:.1f} s"}
         else:
-            v, wall = cpu_ntt_rate(18, 1)
+            v, wall = cpu_ntt_rate(18, 1, "port", curve)
             cpu = {"value": v, "unit": "elements/s", "cores": 1, "kind": "port",
                    "sample": f"2^18-element recursive fft_ff (fft_ff.py:3-37 on CPython ints), {wall:.1f} s",
                    "host_cpus": os.cpu_count()}
 
     cpu_plonk = None
     if rank == 0 and world == 1 and not args.no_cpu and plonk is not None:
-        cpu_plonk = cpu_plonk_hotpath()
+        cpu_plonk = cpu_hotpath("plonk")
 
     if rank == 0:
         if args.workload == "msm":
             metric, unit = "g1_msm_points_per_s", "points/s"
-            workload = (f"BN254 G1 MSM (KZG commit) of 2^{args.logn} points" +
-                        (f" per GPU, SRS/scalars sharded by index range over {world} GPUs, NCCL all-gather of XYZZ partials"
-                         if world > 1 and args.scaling == "weak" else
-                         (f" split over {world} GPUs" if world > 1 else "")))
-            footprint = "inputs 1.5 GiB/GPU (SRS 1 GiB + scalars 512 MiB at 2^24) exceed the 126 MB L2"
+            key = primary["key"]
+            workload = (f"{curve} G1 MSM (KZG commit) of 2^{args.logn} points" +
+                        (f", ONE MSM split over {world} GPUs: SRS / scalars sharded by contiguous index range ({primary['n_per_rank']} points per rank), "
+                         "NCCL all-gather of the XYZZ partials + fold" if world > 1 else ""))
+            pt = 2 * nl * 4
+            footprint = (f"inputs per GPU: SRS {primary['n_per_rank'] * pt / 2**20:.0f} MiB (x {key['tables']} window tables = {key['bytes'] / 2**30:.2f} GiB) "
+                         f"+ scalars {primary['n_per_rank'] * 32 / 2**20:.0f} MiB; the accumulate kernel gathers from the tables, far larger than the 126 MB L2")
+            scaling = "strong"
         else:
             metric, unit = "ntt_elements_per_s", "elements/s"
-            workload = f"BN254 scalar-field NTT of 2^{args.logn} elements" + (f", one vector per GPU ({world} replicas)" if world > 1 else "")
+            workload = f"{curve} scalar-field NTT of 2^{args.logn} elements" + (f", one vector per GPU ({world} replicas)" if world > 1 else "")
             footprint = "512 MiB vector at 2^24 exceeds the 126 MB L2"
+            scaling = "weak"
         line = {
             "metric": metric, "value": primary["value"], "unit": unit, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": primary["ms"] / K, "higher_is_better": True,
-            "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
-            "dtype": "u32x8 (256-bit modular integers, Montgomery)", "data": "synthetic",
-            "config": {"workload": workload, "curve": "bn254", "logn": args.logn, "l2": footprint,
+            "scaling": scaling, "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": {"workload": workload, "curve": curve, "logn": args.logn, "l2": footprint,
                        "srs": "tau^i*G1 generated on device from a fixed tau", "scalars": "uniform in [0,r), numpy PCG64"},
             "clocks": primary["clocks"], "e2e": primary["e2e"], "gpu_launches": primary["launches"],
             "roofline": primary["roofline"], "cpu_baseline": cpu,
             "imad_wide_peak_per_s": imad_wide_peak, "device": info["name"],
         }
+        if args.workload == "msm":
+            line["config"].update({"srs_window_bits": key["c"], "srs_window_tables": key["tables"], "srs_table_bytes_per_gpu": key["bytes"],
+                                   "srs_build_s": round(primary["build_s"], 3), "tau_identity_check": primary["check"],
+                                   "scaling_note": "N = 1 and N > 1 run the same total work (2^logn points): v_N / (N v_1) is strong-scaling efficiency"})
         if "profile_ms_per_step" in primary:
             line["profile_ms_per_step"] = primary["profile_ms_per_step"]
+        if "weak" in primary:
+            line["weak"] = primary["weak"]
         if plonk is not None:
             if cpu_plonk is not None:
                 plonk["bundled"]["cpu_port_hotpath_s"] = cpu_plonk
@@ -751,13 +1082,11 @@ def run_gpu(args):
             line["ntt"] = {"metric": "ntt_elements_per_s", "value": secondary["value"], "unit": "elements/s",
                            "ms_per_step": secondary["ms"] / K, "e2e": secondary["e2e"], "roofline": secondary["roofline"],
                            "gpu_launches": secondary["launches"], "clocks": secondary["clocks"],
-                           "cpu_baseline": secondary.get("cpu_baseline"),
-                           "config": {"workload": f"BN254 scalar-field NTT of 2^{args.logn} elements, natural order in/out"}}
-        print(json.dumps(line))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+                           "cpu_baseline": secondary.get("cpu_baseline"), "scaling": "weak (one vector per GPU)" if world > 1 else None,
+                           "config": {"workload": f"{curve} scalar-field NTT of 2^{args.logn} elements, natural order in/out" +
+                                                  (f", one vector per GPU ({world} replicas)" if world > 1 else "")}}
+        emit(line)
+    return finish()
 
 
 def main():
@@ -766,14 +1095,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="msm", choices=["msm", "ntt", "plonk", "marlin"])
+    ap.add_argument("--workload", default="msm", choices=["msm", "ntt", "sweep", "plonk", "marlin"])
+    ap.add_argument("--curve", default="bn254", choices=["bn254", "bls12_381"])
     ap.add_argument("--marlin-logn", type=int, default=20, help="constraints of the Marlin kernel workload (log2)")
     ap.add_argument("--marlin-rows-logn", type=int, default=16, help="rows of the synthetic R1CS for the device Marlin prover (log2)")
     ap.add_argument("--plonk-logn", type=int, default=20, help="gates of the synthetic PLONK circuit (log2)")
     ap.add_argument("--logn", type=int, default=24)
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--sweep-max", type=int, default=26, help="largest log2 size of --workload sweep")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the NTT half of the metric")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the NTT half of the metric and the provers")
+    ap.add_argument("--force-port", action="store_true", help="--impl reference: time the oracle port even when the reference tree is present")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "ours" else args.warmup

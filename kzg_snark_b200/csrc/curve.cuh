@@ -111,7 +111,7 @@ template <class P> HD void xyzz_madd_lz(XYZZ<P>& acc, const Affine<P>& b) {
   Fe<P> PPP = fe_mul_lz<P>(Pd, PP);
   Fe<P> Q = fe_mul_lz<P>(acc.x, PP);
   Fe<P> X3 = fe_sub_lz<P>(fe_sub_lz<P>(fe_sub_lz<P>(fe_sqr_lz<P>(Rd), PPP), Q), Q);
-  Fe<P> Y3 = fe_sub_lz<P>(fe_mul_lz<P>(Rd, fe_sub_lz<P>(Q, X3)), fe_mul_lz<P>(acc.y, PPP));
+  Fe<P> Y3 = fe_mulsub_lz<P>(Rd, fe_sub_lz<P>(Q, X3), acc.y, PPP);      // Rd (Q - X3) - Y1 PPP, one reduction for both products
   acc.zz = fe_mul_lz<P>(acc.zz, PP);
   acc.zzz = fe_mul_lz<P>(acc.zzz, PPP);
   acc.x = X3; acc.y = Y3;

@@ -227,6 +227,61 @@ template <class P> HD Fe<P> fe_reduce_lz(const Fe<P>& a) {
   return r;
 }
 
+// Dual product with ONE Montgomery reduction: t = (a*b + c*d + m*p) / 2^(32N) < (a*b + c*d) / 2^(32N) + p.  Same row structure as
+// fe_mul_nofinal, every row adding a*b_i and c*d_i before its reduction step, so the second product costs N^2 wide
+// multiplies instead of 2N^2 - N wide + 2N narrow.  The running value is < (a + c + p) * 2^32, which fits the N + 1 limb
+// positions iff a + c + p <= 2^(32N): for semi-reduced operands a, c <= 2p that is 5p <= 2^(32N) (FeSq<P>::ok, defined below:
+// BN254 p and r, BLS12-381 p).  For a, b, c, d <= 2p the result is < 8p^2 / 2^(32N) + p, i.e. < 2.52p for BN254 p and
+// < 1.82p for BLS12-381 p: fold with fe_fold2_lz before using it as a semi-reduced value.
+template <class P> HD void fe_mul2_nofinal(uint32_t* t, const Fe<P>& a, const Fe<P>& b, const Fe<P>& c, const Fe<P>& d) {
+  constexpr int N = P::N;
+  uint32_t mod[N], E[N], O[N];
+  fe_load_mod<P>(mod);
+  Mp<N>::mul_even(E, a.v, b.v[0]);
+  Mp<N>::mul_even(O, a.v + 1, b.v[0]);
+  Mp<N>::mad_even_nc(O, c.v + 1, d.v[0]);
+  Mp<N>::mad_even(E, c.v, d.v[0], O[N - 1]);
+  fe_redc_row<P>(E, O, mod);
+#pragma unroll
+  for (int i = 1; i < N; i += 2) {
+    Mp<N>::shift_mad(E, O[0], a.v + 1, b.v[i]);
+    Mp<N>::mad_even_nc(E, c.v + 1, d.v[i]);
+    Mp<N>::mad_even(O, a.v, b.v[i], E[N - 1]);
+    Mp<N>::mad_even(O, c.v, d.v[i], E[N - 1]);
+    fe_redc_row<P>(O, E, mod);
+    if (i + 1 < N) {
+      Mp<N>::shift_mad(O, E[0], a.v + 1, b.v[i + 1]);
+      Mp<N>::mad_even_nc(O, c.v + 1, d.v[i + 1]);
+      Mp<N>::mad_even(E, a.v, b.v[i + 1], O[N - 1]);
+      Mp<N>::mad_even(E, c.v, d.v[i + 1], O[N - 1]);
+      fe_redc_row<P>(E, O, mod);
+    }
+  }
+  Mp<N>::merge(t, E, O);
+}
+
+// x < 4p -> x or x - 2p, in [0, 2p)
+template <class P> HD Fe<P> fe_fold2_lz(const uint32_t* x) {
+  constexpr int N = P::N;
+  uint32_t m[N], t[N];
+  fe_load_mod2<P>(m);
+  uint32_t borrow = Mp<N>::sub_cc(t, x, m);
+  Fe<P> r;
+#pragma unroll
+  for (int i = 0; i < N; i++) r.v[i] = borrow ? x[i] : t[i];
+  return r;
+}
+
+// a <= 2p -> 2p - a in [0, 2p], not folded (multiplication operand only: -a up to a multiple of p)
+template <class P> HD Fe<P> fe_neg_nr(const Fe<P>& a) {
+  constexpr int N = P::N;
+  uint32_t m[N];
+  fe_load_mod2<P>(m);
+  Fe<P> r;
+  Mp<N>::sub_cc(r.v, m, a.v);
+  return r;
+}
+
 // Montgomery square, same row structure as fe_mul_nofinal with row i reduced to the products a_i * a_j, j >= i
 // (N(N+1)/2 instead of N^2 wide multiplies): the multiplicand of row i is  [a_i | 2 * (a >> 32(i+1))], i.e. limb i is
 // a_i, limb i+1 is a_(i+1) << 1 and the limbs above are those of 2a (funnel shifts, computed once); limbs below i are
@@ -278,6 +333,18 @@ template <class P> HD Fe<P> fe_sqr(const Fe<P>& a) {
   return r;
 }
 
+
+// a*b - c*d for semi-reduced operands, semi-reduced result, one Montgomery reduction (dual product with c replaced by 2p - c)
+// where the modulus leaves the headroom (5p <= 2^(32N)), two products otherwise
+template <class P> HD Fe<P> fe_mulsub_lz(const Fe<P>& a, const Fe<P>& b, const Fe<P>& c, const Fe<P>& d) {
+  if constexpr (FeSq<P>::ok) {
+    uint32_t t[P::N];
+    fe_mul2_nofinal<P>(t, a, b, fe_neg_nr<P>(c), d);
+    return fe_fold2_lz<P>(t);
+  } else {
+    return fe_sub_lz<P>(fe_mul_lz<P>(a, b), fe_mul_lz<P>(c, d));
+  }
+}
 
 // semi-reduced square: a < 2p -> a^2 / 2^(32N) mod p in [0, 2p)
 template <class P> HD Fe<P> fe_sqr_lz(const Fe<P>& a) {

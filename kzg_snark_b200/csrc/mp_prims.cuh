@@ -1,9 +1,12 @@
 // Multiprecision carry-chain primitives on 32-bit limbs.
 //
 // Device: MpPrims<N> from mp_prims_gen.cuh (inline PTX, one statement per carry chain).
-// Host:   the same contract in portable C++ (used only by tests/host_arith_test.cu to
-//         check the Montgomery / curve formulas on the CPU build box; the product
-//         library never executes field arithmetic on the host).
+// Host:   the same contract in portable C++.  Used by tests/host/host_arith_test.cu to check the
+//         Montgomery / curve formulas on the CPU build box, and by the library for MARSHALLING only:
+//         msm.cu normalises the ONE XYZZ result of an MSM to canonical affine limbs on the host
+//         (host_fe_inv / host_xyzz_to_canonical: a single inversion is ~20 us there against ~200 us
+//         for a lone GPU thread) and builds the 255-entry doubling table of the generator for
+//         kzgpu_srs_generate.  No O(n) field arithmetic ever runs on the host.
 #pragma once
 #include <cstdint>
 #ifdef __CUDACC__

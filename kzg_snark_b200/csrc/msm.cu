@@ -225,7 +225,13 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t* arr, uint32_t nbin
 // memory (count -> scan -> place), the range of every bin is reserved with ONE global atomic, and
 // the staged records are written out in order, so that a bin's run leaves the SM as consecutive
 // 8-byte stores within a few instructions (partial sectors are completed while still in L2).
-// Shared memory: cur[ncoarse] | delta[ncoarse] | scan scratch[blockDim] | stage[tile * W] (u64)
+// Shared memory: stage[tile * W] (u64) | cur[ncoarse] | delta[ncoarse] | scan scratch[blockDim]
+//
+// FAST = true (11 <= W <= 16, i.e. every key of >= 2^16 points): each thread owns at most two scalars, which stay in
+// registers between the two phases; the shared-memory atomic of the counting phase also returns the record's rank inside its
+// bin (kept as 16 bits), so the placing phase needs neither a second load of the scalar nor a second atomic.
+// FAST = false: any W; the scalar is re-read and re-ranked in the placing phase.
+template <bool FAST>
 __global__ void __launch_bounds__(512) msm_partition_kernel(const uint32_t* __restrict__ scalars, size_t n, uint32_t tile, SortGeom g,
                                                             DigitOffset off, uint32_t* __restrict__ coarse_cur,
                                                             uint64_t* __restrict__ tmp) {
@@ -237,14 +243,34 @@ __global__ void __launch_bounds__(512) msm_partition_kernel(const uint32_t* __re
   for (uint32_t b = threadIdx.x; b < g.ncoarse; b += blockDim.x) cur[b] = 0;
   __syncthreads();
   const size_t base = (size_t)blockIdx.x * tile;
-  for (uint32_t k = threadIdx.x; k < tile; k += blockDim.x) {
-    size_t i = base + k;
-    if (i >= n) break;
-    uint32_t s[8];
-    load_scalar_plus_offset(scalars, i, off, s);
-    for (uint32_t w = 0; w < g.W; w++) {
-      uint32_t key, val;
-      if (digit_entry(s, w, g, (uint32_t)i, key, val)) atomicAdd(&cur[key >> g.f], 1u);
+  constexpr int MAXW = 16, PER = 2;
+  uint32_t sreg[FAST ? PER : 1][8];
+  uint32_t rank[FAST ? PER : 1][FAST ? MAXW / 2 : 1];          // two 16-bit ranks per word
+  if constexpr (FAST) {
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+      const uint32_t k = threadIdx.x + q * blockDim.x;
+      const size_t i = base + k;
+      if (k < tile && i < n) {
+        load_scalar_plus_offset(scalars, i, off, sreg[q]);
+#pragma unroll
+        for (int w = 0; w < MAXW; w++) {
+          uint32_t key, val, r = 0;
+          if ((uint32_t)w < g.W && digit_entry(sreg[q], w, g, (uint32_t)i, key, val)) r = atomicAdd(&cur[key >> g.f], 1u);
+          if (w & 1) rank[q][w >> 1] |= r << 16; else rank[q][w >> 1] = r;
+        }
+      }
+    }
+  } else {
+    for (uint32_t k = threadIdx.x; k < tile; k += blockDim.x) {
+      size_t i = base + k;
+      if (i >= n) break;
+      uint32_t s[8];
+      load_scalar_plus_offset(scalars, i, off, s);
+      for (uint32_t w = 0; w < g.W; w++) {
+        uint32_t key, val;
+        if (digit_entry(s, w, g, (uint32_t)i, key, val)) atomicAdd(&cur[key >> g.f], 1u);
+      }
     }
   }
   __syncthreads();
@@ -257,16 +283,34 @@ __global__ void __launch_bounds__(512) msm_partition_kernel(const uint32_t* __re
   const uint32_t total = block_excl_scan(cur, g.ncoarse, scratch);
   for (uint32_t b = threadIdx.x; b < g.ncoarse; b += blockDim.x) delta[b] -= cur[b];     // global pos = local pos + delta
   __syncthreads();
-  for (uint32_t k = threadIdx.x; k < tile; k += blockDim.x) {
-    size_t i = base + k;
-    if (i >= n) break;
-    uint32_t s[8];
-    load_scalar_plus_offset(scalars, i, off, s);
-    for (uint32_t w = 0; w < g.W; w++) {
-      uint32_t key, val;
-      if (digit_entry(s, w, g, (uint32_t)i, key, val)) {
-        uint32_t pos = atomicAdd(&cur[key >> g.f], 1u);
-        stage[pos] = ((uint64_t)key << 32) | val;
+  if constexpr (FAST) {
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+      const uint32_t k = threadIdx.x + q * blockDim.x;
+      const size_t i = base + k;
+      if (k < tile && i < n) {
+#pragma unroll
+        for (int w = 0; w < MAXW; w++) {
+          uint32_t key, val;
+          if ((uint32_t)w < g.W && digit_entry(sreg[q], w, g, (uint32_t)i, key, val)) {
+            const uint32_t r = (w & 1) ? rank[q][w >> 1] >> 16 : rank[q][w >> 1] & 0xffffu;
+            stage[cur[key >> g.f] + r] = ((uint64_t)key << 32) | val;        // cur[] = start of the bin's run (exclusive scan)
+          }
+        }
+      }
+    }
+  } else {
+    for (uint32_t k = threadIdx.x; k < tile; k += blockDim.x) {
+      size_t i = base + k;
+      if (i >= n) break;
+      uint32_t s[8];
+      load_scalar_plus_offset(scalars, i, off, s);
+      for (uint32_t w = 0; w < g.W; w++) {
+        uint32_t key, val;
+        if (digit_entry(s, w, g, (uint32_t)i, key, val)) {
+          uint32_t pos = atomicAdd(&cur[key >> g.f], 1u);
+          stage[pos] = ((uint64_t)key << 32) | val;
+        }
       }
     }
   }
@@ -320,7 +364,7 @@ __global__ void __launch_bounds__(256) msm_fine_hist_kernel(const uint64_t* __re
 // pass 2b: scatter of the values into the per-key lists, staged like pass 1c: the chunk's values
 // are sorted by fine key in shared memory and every key's run is written by a group of 8 lanes.
 // Shared memory: cur[F] | gpos[F] | scan scratch[blockDim] | stage[kSortChunk] (u32)
-__global__ void __launch_bounds__(512) msm_fine_scatter_kernel(const uint64_t* __restrict__ tmp, const uint32_t* __restrict__ coarse_off,
+__global__ void __launch_bounds__(512, 2) msm_fine_scatter_kernel(const uint64_t* __restrict__ tmp, const uint32_t* __restrict__ coarse_off,
                                                                const uint32_t* __restrict__ blk_off, uint32_t ncoarse, uint32_t f,
                                                                uint32_t nkeys, uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
   extern __shared__ uint32_t sh[];
@@ -333,24 +377,37 @@ __global__ void __launch_bounds__(512) msm_fine_scatter_kernel(const uint64_t* _
   uint32_t* stage = scratch + blockDim.x;
   for (uint32_t j = threadIdx.x; j < F; j += blockDim.x) cur[j] = 0;
   __syncthreads();
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&cur[(uint32_t)(tmp[i] >> 32) & (F - 1)], 1u);
+  // counting phase: the atomic also returns the record's rank inside its key (16 bits each, kSortChunk / 512 = 32 per thread)
+  constexpr int PER = kSortChunk / 512;
+  uint32_t rank[PER / 2];
+#pragma unroll
+  for (int q = 0; q < PER; q++) {
+    const uint32_t i = lo + threadIdx.x + q * 512;
+    uint32_t r = 0;
+    if (i < hi) r = atomicAdd(&cur[(uint32_t)(tmp[i] >> 32) & (F - 1)], 1u);
+    if (q & 1) rank[q >> 1] |= r << 16; else rank[q >> 1] = r;
+  }
   __syncthreads();
   for (uint32_t j = threadIdx.x; j < F; j += blockDim.x) {
     uint32_t key = (bin << f) + j, cnt = cur[j];
     gpos[j] = (cnt && key < nkeys) ? atomicAdd(&cursor[key], cnt) : 0u;
   }
   __syncthreads();
-  block_excl_scan(cur, F, scratch);
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    uint64_t rec = tmp[i];
-    uint32_t pos = atomicAdd(&cur[(uint32_t)(rec >> 32) & (F - 1)], 1u);
-    stage[pos] = (uint32_t)rec;
+  block_excl_scan(cur, F, scratch);                      // cur[j] = start of key j's run in stage[]
+#pragma unroll
+  for (int q = 0; q < PER; q++) {
+    const uint32_t i = lo + threadIdx.x + q * 512;
+    if (i < hi) {
+      const uint64_t rec = tmp[i];                       // second read of the chunk: L2
+      const uint32_t r = (q & 1) ? rank[q >> 1] >> 16 : rank[q >> 1] & 0xffffu;
+      stage[cur[(uint32_t)(rec >> 32) & (F - 1)] + r] = (uint32_t)rec;
+    }
   }
   __syncthreads();
-  // cur[j] is now the END of key j's run in stage[]; its start is cur[j-1] (0 for j == 0)
+  // cur[j] is the START of key j's run in stage[]; its end is cur[j+1] (the chunk's record count for the last key)
   const uint32_t grp = threadIdx.x >> 3, ln = threadIdx.x & 7, ngrp = blockDim.x >> 3;
   for (uint32_t j = grp; j < F; j += ngrp) {
-    uint32_t s0 = j ? cur[j - 1] : 0u, s1 = cur[j], gp = gpos[j];
+    uint32_t s0 = cur[j], s1 = j + 1 < F ? cur[j + 1] : hi - lo, gp = gpos[j];
     for (uint32_t k = s0 + ln; k < s1; k += 8) entries[gp + (k - s0)] = stage[k];
   }
 }
@@ -566,7 +623,7 @@ __global__ void msm_clear_empty_kernel(const uint32_t* __restrict__ ntasks, uint
 // chunked running sum: thread (w, chunk) reduces CH consecutive buckets of window w to
 //   sum_b (b + 1) * B_b  over its chunk  =  acc + lo * running
 template <class Cfg>
-__global__ void __launch_bounds__(128) msm_reduce_kernel(const uint32_t* __restrict__ buckets, uint32_t B, uint32_t CH,
+__global__ void __launch_bounds__(128, (Cfg::Fp::N == 8 ? 3 : 1)) msm_reduce_kernel(const uint32_t* __restrict__ buckets, uint32_t B, uint32_t CH,
                                                         uint32_t chunks_per_window, uint32_t W, uint32_t* __restrict__ partials) {
   using P = typename Cfg::Fp;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -972,7 +1029,10 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
     KZ_LAUNCHED();
     const uint32_t ptile = kSortStage / W;                       // scalars per partition block
     const size_t psmem = (size_t)ptile * W * 8 + (2 * (size_t)ncoarse + 512) * 4;
-    msm_partition_kernel<<<(unsigned)kz_div_up(n, ptile), 512, psmem, sst>>>(d_scalars, n, ptile, geo, doff, coarse_cur, sort_tmp);
+    if (W >= 11 && W <= 16)            // ptile <= 1024: two scalars per thread, ranks in registers
+      msm_partition_kernel<true><<<(unsigned)kz_div_up(n, ptile), 512, psmem, sst>>>(d_scalars, n, ptile, geo, doff, coarse_cur, sort_tmp);
+    else
+      msm_partition_kernel<false><<<(unsigned)kz_div_up(n, ptile), 512, psmem, sst>>>(d_scalars, n, ptile, geo, doff, coarse_cur, sort_tmp);
     KZ_LAUNCHED();
     const size_t sort_blocks = (n * W) / kSortChunk + ncoarse + 1;
     msm_fine_hist_kernel<<<(unsigned)sort_blocks, 256, (4u << f), sst>>>(sort_tmp, coarse_off, blk_off, ncoarse, f, (uint32_t)nb, counts);
@@ -1138,7 +1198,8 @@ int set_smem_attrs() {
   if (done) return 0;
   KZ_CUDA(cudaFuncSetAttribute(msm_window_kernel<BLS381Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 4 * 12 * 4));
   KZ_CUDA(cudaFuncSetAttribute(g1_fold_kernel<BLS381Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 4 * 12 * 4));
-  KZ_CUDA(cudaFuncSetAttribute(msm_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortStage * 8 + (2 * kMaxCoarse + 512) * 4));
+  KZ_CUDA(cudaFuncSetAttribute(msm_partition_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortStage * 8 + (2 * kMaxCoarse + 512) * 4));
+  KZ_CUDA(cudaFuncSetAttribute(msm_partition_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortStage * 8 + (2 * kMaxCoarse + 512) * 4));
   KZ_CUDA(cudaFuncSetAttribute(msm_fine_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 << 13) + (512 + kSortChunk) * 4));
   done = true;
   return 0;

@@ -102,9 +102,16 @@ class Srs:
         return out
 
     def destroy(self):
-        if self.handle:
-            _ffi.load_library().kzgpu_srs_destroy(self.handle)
-            self.handle = 0
+        """Release the device copy (idempotent; also run when the object is garbage collected)."""
+        h, self.handle = self.handle, 0
+        if h and _ffi._lib is not None and _ffi._inited:
+            _ffi._lib.kzgpu_srs_destroy(h)
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:                                 # interpreter shutdown: the library may already be gone
+            pass
 
 
 def _point_out(cid):

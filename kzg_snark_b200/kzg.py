@@ -13,6 +13,9 @@ SURVEY.md section 8b); device copies of commitment keys are cached per `ck` list
 There is no CPU fallback for commit/open/setup.
 """
 
+import collections
+import weakref
+
 import numpy as np
 
 from . import device
@@ -34,8 +37,17 @@ _G1 = {"bn254": (1, 2), "bls12_381": (
 
 class CommitmentKey(list):
     """ck = [tau^i * G1] as a plain list of py_ecc-shaped points (what kzg.py:69-72 returns),
-    carrying the handle of its device-resident copy so commit/open never re-upload it."""
+    carrying the handle of its device-resident copy so commit/open never re-upload it.  `_snapshot`
+    is the list of point objects the device copy was built from: a key edited in place (ck[i] = ...)
+    no longer equals it and is uploaded again, as the reference would read the new ck[i] (kzg.py:115).
+    The device copy is released when the key is garbage collected."""
     srs = None
+    _snapshot = None
+
+    def attach(self, srs):
+        self.srs = srs
+        self._snapshot = list(self)
+        weakref.finalize(self, srs.destroy)
 
 
 def _needs_py_ecc(name):
@@ -46,8 +58,11 @@ def _needs_py_ecc(name):
     return stub
 
 
-# device copies of commitment keys handed in as plain lists: id(ck) -> (fingerprint, Srs)
-_SRS_CACHE = {}
+# Device copies of commitment keys handed in as plain lists: id(ck) -> (snapshot, Srs).  The snapshot is a shallow copy of
+# the list, so (i) it keeps every point object alive -- a recycled id() cannot alias an entry -- and (ii) `snapshot == ck`
+# (C-level list comparison: identity first, value equality of the coordinates otherwise) detects any in-place edit of the
+# caller's list at ~5 ns per unchanged point.  The cache owns its Srs objects; eviction releases the device memory.
+_SRS_CACHE = collections.OrderedDict()
 _SRS_CACHE_MAX = 8
 
 
@@ -131,19 +146,19 @@ class KZG:
 
     def _device_srs(self, ck):
         srs = getattr(ck, "srs", None)
-        if srs is not None and srs.handle and srs.n == len(ck):
+        if srs is not None and srs.handle and srs.curve == self._cid and ck._snapshot == ck:
             return srs
-        n = len(ck)
-        aff = self._codec.to_affine_ints
-        fp = (n, aff(ck[0]) if n else None, aff(ck[n // 2]) if n else None, aff(ck[-1]) if n else None, self._cid)
-        hit = _SRS_CACHE.get(id(ck))
-        if hit is not None and hit[0] == fp and hit[1].handle:
+        key = (id(ck), self._cid)
+        hit = _SRS_CACHE.get(key)
+        if hit is not None and hit[1].handle and hit[0] == ck:
+            _SRS_CACHE.move_to_end(key)
             return hit[1]
+        if hit is not None:                               # same list object, edited since: drop the stale copy
+            _SRS_CACHE.pop(key)[1].destroy()
         srs = device.Srs.from_affine(self._cid, self._codec.points_to_limbs(ck))
-        if len(_SRS_CACHE) >= _SRS_CACHE_MAX:
-            old = next(iter(_SRS_CACHE))
-            _SRS_CACHE.pop(old)[1].destroy()
-        _SRS_CACHE[id(ck)] = (fp, srs)
+        while len(_SRS_CACHE) >= _SRS_CACHE_MAX:
+            _SRS_CACHE.popitem(last=False)[1][1].destroy()
+        _SRS_CACHE[key] = (list(ck), srs)
         return srs
 
     # ------------------------------------------------------------------ setup (kzg.py:56-78)
@@ -157,7 +172,7 @@ class KZG:
         srs = device.Srs.generate(self._cid, t, max_degree + 1)
         rows = srs.read(0, max_degree + 1)
         ck = CommitmentKey(self._codec.from_device(r, not r.any()) for r in rows)
-        ck.srs = srs
+        ck.attach(srs)
         rk = self.multiply(self.G2, t) if self.have_py_ecc else None
         return (ck, rk)
 

@@ -161,7 +161,8 @@ class Indexer:
                "vanishing_polys": {"v_H": ("X^n - 1", n), "v_K": ("X^m - 1", m)}}
         rk = kzg.multiply(kzg.G2, tau) if (kzg.have_py_ecc and tau is not None) else None
         ivk = {"rk": rk, "commitments": commitments, "subgroups": {"n": n, "m": m, "g_H": kzg.Fq(g_H)},
-               "vanishing_polys": ipk["vanishing_polys"], "tau": tau}
+               "vanishing_polys": ipk["vanishing_polys"]}      # rk only, never the trapdoor (marlin/indexer.py:109-110)
+        del tau
         return ipk, ivk
 
     @staticmethod

@@ -301,7 +301,9 @@ class Indexer:
         }
         # rk = tau * G2 needs G2 arithmetic, which stays with py_ecc as in the reference (kzg.py:75); None without it
         rk = kzg.multiply(kzg.G2, tau) if (kzg.have_py_ecc and tau is not None) else None
-        ivk = {"rk": rk, "commitments": commitments, "subgroups": sub, "tau": tau}
+        # the trapdoor never leaves this function: the verifier key carries rk = tau * G2 only (plonk/indexer.py:109-110)
+        ivk = {"rk": rk, "commitments": commitments, "subgroups": sub}
+        del tau
         return ipk, ivk
 
 

@@ -1,8 +1,11 @@
 """Restated oracle of the reference's fft_ff.py (radix-2 NTT / iNTT).
 
-Oracle / test infrastructure only (see oracle/__init__.py).  "parity unpinned":
-the reference has no test or vector for this module (fft_ff.py:1-85); the oracle
-is pinned by the DFT definition out[k] = sum_j c[j] * w^(j*k) (tests/test_oracle.py).
+Oracle / test infrastructure only (see oracle/__init__.py).  Parity is PINNED: the reference
+ships no test or vector for this module (fft_ff.py:1-85), so its own fft_ff.py is run
+unmodified (oracle/refrun.py; BN254 and BLS12-381 scalar fields) and every call is recorded in
+tests/golden/ref_trace_fft*.json; this restatement reproduces all of them bit for bit
+(tests/test_reference_traces.py) and also satisfies the DFT definition
+out[k] = sum_j c[j] * w^(j*k) (tests/test_oracle.py).
 
 Two flavours of the same recursion:
   * fft_ff / ifft_ff / fft_ff_interpolation -- element-generic, statement for

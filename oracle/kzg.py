@@ -1,8 +1,9 @@
 """Restated oracle of the reference's KZG.setup / commit / open (kzg.py:56-159).
 
-Oracle / test infrastructure only (see oracle/__init__.py).  "parity unpinned"
-(no golden vectors in the reference); pinned by the
-tau-identity commit(ck, p) == p(tau)*G1 (kzg.py:108) and the pairing-free form
+Oracle / test infrastructure only (see oracle/__init__.py).  Parity is PINNED against runs of the
+reference's own kzg.py (oracle/refrun.py -> tests/golden/ref_trace_kzg*.json, reproduced bit for bit by
+tests/test_reference_traces.py); the reference itself holds no golden vectors.
+Also checked by the tau-identity commit(ck, p) == p(tau)*G1 (kzg.py:108) and the pairing-free form
 of `check` (kzg.py:161-211) that a known tau allows:
     e(C - v*G1, G2) == e(pi, tau*G2 - z*G2)   <=>   C - v*G1 == (tau - z) * pi.
 

@@ -3,9 +3,13 @@
 hot-path boundary as a trace.
 
 Oracle / test infrastructure only (see oracle/__init__.py).  /root/reference exists only in the
-build container, so this module is used (a) by tests/golden/make_traces.py to generate the
-committed fixtures tests/golden/ref_trace_*.json and (b) by `-m "not gpu"` tests that skip when
-/root/reference is absent.  Nothing on the GPU box imports the reference.
+build container; `__graft_entry__.build()` stages a byte-identical, git-ignored copy under
+baseline/_ref/ (oracle/refstage.py) that travels to the GPU box.  This module is used (a) by
+tests/golden/make_traces.py to generate the committed fixtures tests/golden/ref_trace_*.json,
+(b) by `-m "not gpu"` tests, (c) by the `-m gpu` test that runs the reference's UNMODIFIED
+main.py / plonk / marlin on top of the GPU drop-in (`ReferenceRun(gpu_dropin=True)`: `kzg` and
+`fft_ff` then resolve to kzg_snark_b200/dropin/, everything else to the reference), and (d) by
+`bench.py --impl reference`, which times the reference's own kzg.py commit loop.
 
 What is real and what is a stand-in when the reference runs here:
   real      kzg.py (setup/commit/open/check/batch_check), fft_ff.py, transcript.py,
@@ -27,12 +31,17 @@ import random
 import sys
 import types
 
-REFERENCE_ROOT = "/root/reference"
-_REF_MODULES = ("kzg", "fft_ff", "transcript", "plonk", "plonk.encoder", "plonk.indexer", "plonk.prover",
+from . import refstage
+
+REFERENCE_ROOT = refstage.root() or refstage.SOURCE
+DROPIN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "kzg_snark_b200", "dropin")
+_REF_MODULES = ("main", "kzg", "fft_ff", "transcript", "plonk", "plonk.encoder", "plonk.indexer", "plonk.prover",
                 "plonk.verifier", "marlin", "marlin.encoder", "marlin.indexer", "marlin.prover", "marlin.verifier")
 
 
 def available():
+    global REFERENCE_ROOT
+    REFERENCE_ROOT = refstage.root() or refstage.SOURCE
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "kzg.py"))
 
 
@@ -51,9 +60,17 @@ def _install_standins():
     py_ecc = types.ModuleType("py_ecc")
     py_ecc.optimized_bn128 = pyecc_standin
     py_ecc.optimized_bls12_381 = pyecc_standin_bls
-    saved = {k: sys.modules.get(k) for k in ("sage", "sage.all", "py_ecc", "py_ecc.optimized_bn128", "py_ecc.optimized_bls12_381")}
-    sys.modules.update({"sage": sage, "sage.all": sage_all, "py_ecc": py_ecc,
+    # py_ecc.fields: the FQ classes a drop-in builds its result points from (kzg_snark_b200/points.py:fq_class)
+    fields = types.ModuleType("py_ecc.fields")
+    fields.optimized_bn128_FQ = pyecc_standin.FQ
+    fields.optimized_bls12_381_FQ = pyecc_standin_bls.FQ
+    py_ecc.fields = fields
+    names = ("sage", "sage.all", "py_ecc", "py_ecc.optimized_bn128", "py_ecc.optimized_bls12_381", "py_ecc.fields")
+    saved = {k: sys.modules.get(k) for k in names}
+    sys.modules.update({"sage": sage, "sage.all": sage_all, "py_ecc": py_ecc, "py_ecc.fields": fields,
                         "py_ecc.optimized_bn128": pyecc_standin, "py_ecc.optimized_bls12_381": pyecc_standin_bls})
+    from . import sagepickle
+    sagepickle.install()                                 # main.py:43-44,68-69 un-pickle Sage objects
     return saved
 
 
@@ -63,9 +80,10 @@ class ReferenceRun:
     sys.path are restored so the repo's own drop-in modules named `kzg` / `fft_ff` are not
     shadowed for other tests."""
 
-    def __init__(self, seed=0, record=True):
+    def __init__(self, seed=0, record=True, gpu_dropin=False):
         self.seed = seed
         self.record = record
+        self.gpu_dropin = gpu_dropin          # `kzg` / `fft_ff` = the GPU drop-in (INTEGRATION.md section 1) instead of the reference's
         self.trace = []
         self._depth = 0
 
@@ -94,21 +112,36 @@ class ReferenceRun:
         self._saved_std = _install_standins()
         self._saved_ref = {k: sys.modules.pop(k, None) for k in _REF_MODULES}
         self._saved_path = list(sys.path)
+        self._saved_cwd = os.getcwd()
         sys.path.insert(0, REFERENCE_ROOT)
+        hot_root = REFERENCE_ROOT
+        if self.gpu_dropin:                       # the zero-edit substitution: the drop-in directory precedes the reference
+            sys.path.insert(0, DROPIN_DIR)
+            hot_root = DROPIN_DIR
+            # the drop-in builds its points from py_ecc's FQ class when py_ecc is importable -- re-resolve it now that
+            # the stand-in is installed
+            importlib.invalidate_caches()
         from kzg_snark_b200 import sageshim
         sageshim.seed(self.seed)
         random.seed(self.seed)
 
         self.fft_ff = importlib.import_module("fft_ff")
-        assert self.fft_ff.__file__.startswith(REFERENCE_ROOT)
+        assert self.fft_ff.__file__.startswith(hot_root), self.fft_ff.__file__
         if self.record:
             self._wrap_fft()
         self.kzg = importlib.import_module("kzg")
-        assert self.kzg.__file__.startswith(REFERENCE_ROOT)
+        assert self.kzg.__file__.startswith(hot_root), self.kzg.__file__
         if self.record:
             self._wrap_kzg()
         self.transcript = importlib.import_module("transcript")
+        assert self.transcript.__file__.startswith(REFERENCE_ROOT)
         return self
+
+    def main(self):
+        """The reference's main.py, imported unmodified; its demos open the fixtures with cwd-relative paths
+        (main.py:43,68), so the working directory is the reference root until the context exits."""
+        os.chdir(REFERENCE_ROOT)
+        return self.load("main")
 
     def load(self, name):
         m = importlib.import_module(name)
@@ -127,6 +160,9 @@ class ReferenceRun:
             else:
                 sys.modules[k] = v
         sys.path[:] = self._saved_path
+        os.chdir(self._saved_cwd)
+        from . import sagepickle
+        sagepickle.uninstall()
         return False
 
     # -- tracing wrappers: only outermost boundary calls are recorded (fft_ff_interpolation calls
@@ -179,10 +215,10 @@ class ReferenceRun:
         KZG, run = self.kzg.KZG, self
         orig_commit, orig_open, orig_setup = KZG.commit, KZG.open, KZG.setup
 
-        def setup(kself, max_degree):
+        def setup(kself, max_degree, *a, **kw):
             run._depth += 1
             try:
-                ck, rk = orig_setup(kself, max_degree)
+                ck, rk = orig_setup(kself, max_degree, *a, **kw)
             finally:
                 run._depth -= 1
             return ck, rk

@@ -35,6 +35,12 @@ template <class P> void field_op(const std::string& op, std::istringstream& in) 
   std::string a, b; in >> a;
   if (op == "inv") { std::cout << U<P>(fe_inv<P>(M<P>(a))) << "\n"; return; }
   in >> b;
+  if (op == "lzmulsub") {        // a*b - c*d on raw semi-reduced limbs: dual product with one reduction (field.cuh fe_mulsub_lz)
+    std::string c, d; in >> c >> d;
+    Fe<P> w = fe_mulsub_lz<P>(parse<P>(a), parse<P>(b), parse<P>(c), parse<P>(d));
+    std::cout << hex<P>(w) << " " << (fe_is_zero_lz<P>(w) ? 1 : 0) << " " << hex<P>(fe_reduce_lz<P>(w)) << "\n";
+    return;
+  }
   Fe<P> x = M<P>(a), y = M<P>(b), r;
   if (op == "mul") r = fe_mul<P>(x, y);
   else if (op == "sqr") r = fe_sqr<P>(x);

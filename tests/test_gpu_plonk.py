@@ -89,13 +89,15 @@ def test_synthetic_circuit_proof_is_accepted_and_tamper_rejected(logn, n_pub):
     qM, qL, qR, qO, qC, perm, w = synthetic_circuit(n, n_pub, R, seed=logn)
     rng = random.Random(100 + logn)
     idx = Indexer("bn254")
-    ipk, ivk = idx.preprocess(qM, qL, qR, qO, qC, perm, max_degree=n + 5, rng=rng)
+    tau = random.Random(500 + logn).randrange(1, R)                      # the test's own trapdoor (never part of ivk)
+    ipk, ivk = idx.preprocess(qM, qL, qR, qO, qC, perm, max_degree=n + 5, rng=rng, tau=tau)
+    assert "tau" not in ivk
     x, wit = w[:n_pub], w[n_pub:]
     prover = Prover("bn254")
     proof = prover.prove(ipk, [idx.kzg.Fq(v) for v in x], wit)
     assert prover.last_r_zeta == 0 and not any(prover.last_t_top)
     vk = {"commitments": {k: aff(c) for k, c in ivk["commitments"].items()}, "n": n, "g": int(ivk["subgroups"]["g"]),
-          "k1": int(ivk["subgroups"]["k1"]), "k2": int(ivk["subgroups"]["k2"]), "tau": ivk["tau"]}
+          "k1": int(ivk["subgroups"]["k1"]), "k2": int(ivk["subgroups"]["k2"]), "tau": tau}
     pf = {"commitments": {k: aff(c) for k, c in proof["commitments"].items()},
           "evaluations": {k: int(v) for k, v in proof["evaluations"].items()},
           "kzg_proofs": {k: aff(c) for k, c in proof["kzg_proofs"].items()}}
@@ -123,12 +125,13 @@ def test_bls12_381_prover_accepted_by_the_trapdoor_verifier(logn):
     n, n_pub = 1 << logn, 3
     qM, qL, qR, qO, qC, perm, w = synthetic_circuit(n, n_pub, rq, seed=40 + logn)
     idx = Indexer("bls12_381")
-    ipk, ivk = idx.preprocess(qM, qL, qR, qO, qC, perm, max_degree=n + 5, rng=random.Random(7 + logn))
+    tau = random.Random(600 + logn).randrange(1, rq)
+    ipk, ivk = idx.preprocess(qM, qL, qR, qO, qC, perm, max_degree=n + 5, rng=random.Random(7 + logn), tau=tau)
     prover = Prover("bls12_381")
     proof = prover.prove(ipk, [idx.kzg.Fq(v) for v in w[:n_pub]], w[n_pub:])
     assert prover.last_r_zeta == 0 and not any(prover.last_t_top)
     vk = {"commitments": {k: aff(c) for k, c in ivk["commitments"].items()}, "n": n, "g": int(ivk["subgroups"]["g"]),
-          "k1": int(ivk["subgroups"]["k1"]), "k2": int(ivk["subgroups"]["k2"]), "tau": ivk["tau"]}
+          "k1": int(ivk["subgroups"]["k1"]), "k2": int(ivk["subgroups"]["k2"]), "tau": tau}
     pf = {"commitments": {k: aff(c) for k, c in proof["commitments"].items()},
           "evaluations": {k: int(v) for k, v in proof["evaluations"].items()},
           "kzg_proofs": {k: aff(c) for k, c in proof["kzg_proofs"].items()}}
@@ -288,7 +291,8 @@ def test_product_verifier_with_the_oracle_pairing_in_py_eccs_role():
     n, n_pub = 1 << 9, 4
     qM, qL, qR, qO, qC, perm, w = synthetic_circuit(n, n_pub, R, seed=9)
     idx = Indexer("bn254")
-    ipk, ivk = idx.preprocess(qM, qL, qR, qO, qC, perm, max_degree=n + 5, rng=random.Random(31))
+    tau = random.Random(32).randrange(1, R)
+    ipk, ivk = idx.preprocess(qM, qL, qR, qO, qC, perm, max_degree=n + 5, rng=random.Random(31), tau=tau)
     x = [idx.kzg.Fq(v) for v in w[:n_pub]]
     proof = Prover("bn254").prove(ipk, x, w[n_pub:])
     ver = Verifier("bn254")
@@ -296,7 +300,7 @@ def test_product_verifier_with_the_oracle_pairing_in_py_eccs_role():
         pytest.skip("py_ecc present: the verifier already uses it")
     ver.kzg.G2 = E.G2
     ver.kzg.pairing = lambda Q, P: E.pairing(Q, tuple(E.FQ(int(c)) for c in P))
-    ivk = {**ivk, "rk": E.multiply(E.G2, ivk["tau"])}
+    ivk = {**ivk, "rk": E.multiply(E.G2, tau)}
     assert ver.verify(ivk, x, proof)
     bad = {**proof, "evaluations": {**proof["evaluations"], "b": proof["evaluations"]["b"] + 1}}
     assert not ver.verify(ivk, x, bad)

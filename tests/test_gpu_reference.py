@@ -1,0 +1,124 @@
+"""GPU: the reference's OWN, UNMODIFIED callers -- main.py's three demos, plonk/{indexer,prover,verifier}.py and
+marlin/{indexer,prover,verifier}.py -- running on top of the GPU drop-in (SURVEY.md section 8(d) config 4 / 5 as
+defined there; INTEGRATION.md section 1's zero-edit path).  `kzg` and `fft_ff` resolve to kzg_snark_b200/dropin/
+(module shadowing on sys.path), every other module is imported byte for byte from the reference tree
+(/root/reference in the build container, its staged copy baseline/_ref/ on the GPU box; oracle/refstage.py).
+SageMath and py_ecc cannot be installed in this image, so they are the stand-ins of oracle/refrun.py, exactly as
+when the golden traces were recorded.
+
+Because the drop-in returns canonical affine points (x, y, 1), the transcript hashes what
+tests/golden/ref_{plonk,marlin}_normalized.json recorded from the reference prover running on its own CPU kzg.py with
+normalised commitments: with the same seed the GPU-backed proof must equal that proof bit for bit, the reference's
+verifier must accept it, and the reference's own tamper tests (plonk/verifier.py:277-290, marlin/verifier.py:272-285)
+must reject."""
+import contextlib
+import io
+import json
+import os
+import pickle
+
+import pytest
+
+from oracle import refrun
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SEED = 20261018                       # tests/golden/make_traces.py
+
+
+def H(v):
+    return int(v, 16)
+
+
+def _need_reference():
+    if not refrun.available():
+        pytest.skip("reference tree not staged (run __graft_entry__.build() in the build container)")
+
+
+def test_reference_main_demos_on_the_gpu_dropin():
+    """main.py:16-94, imported and run as is: KZG, PLONK and Marlin demos must print PASS, with the GPU doing the
+    commits, openings and NTTs (kernel launches counted)."""
+    _need_reference()
+    from kzg_snark_b200 import _ffi
+    with refrun.ReferenceRun(seed=SEED, record=True, gpu_dropin=True) as rr:
+        import kzg_snark_b200.kzg as gk
+        assert rr.kzg.KZG is gk.KZG, "the reference's `from kzg import KZG` did not resolve to the GPU drop-in"
+        main = rr.main()
+        assert main.KZG is gk.KZG and main.PlonkProver.__module__ == "plonk.prover"
+        assert main.__file__.startswith(refrun.REFERENCE_ROOT)
+        _ffi.init()
+        l0 = _ffi.launch_count()
+        out = io.StringIO()
+        with contextlib.redirect_stdout(out):
+            main.demo_kzg()
+            main.demo_plonk()
+            main.demo_marlin()
+        text = out.getvalue()
+        launches = _ffi.launch_count() - l0
+        calls = [c["fn"] for c in rr.trace]
+    assert text.count("PASS") == 3 and "FAIL" not in text, text
+    assert launches > 100, "the demos did not reach the GPU"
+    assert calls.count("commit") >= 1 + 4 + 4 and calls.count("open") >= 1 + 2 + 2 and "fft_ff_interpolation" in calls
+
+
+def _pickle(name):
+    with open(os.path.join(refrun.REFERENCE_ROOT, "constraint-system", name), "rb") as f:
+        return pickle.load(f)                 # the stock loader of main.py:43-44,68-69 (Sage classes stubbed by oracle/sagepickle.py)
+
+
+def _same_point(got, exp):
+    x, y, z = (int(c) for c in got)
+    return (exp is None and z == 0) or (z == 1 and [x, y] == [H(exp[0]), H(exp[1])])
+
+
+def test_reference_plonk_prover_on_the_gpu_dropin_is_bit_exact():
+    """plonk/indexer.py, plonk/prover.py:24-212 and plonk/verifier.py unmodified + GPU kzg / fft_ff == the reference on its own
+    CPU kzg.py (ref_plonk_normalized.json, same seed): every commitment, evaluation and opening proof; verifier accepts;
+    tampered evaluation rejected (plonk/verifier.py:277-290)."""
+    _need_reference()
+    d = json.load(open(os.path.join(GOLD, "ref_plonk_normalized.json")))
+    with refrun.ReferenceRun(seed=d["seed"], record=True, gpu_dropin=True) as rr:
+        inst = _pickle("PLONK_ARITHMETIZATION_INSTANCE.pkl")
+        sel = [inst[k] for k in ("qM", "qL", "qR", "qO", "qC")]
+        Fq = rr.kzg.KZG("bn254").Fq
+        w = [Fq(v) for v in inst["w"]]            # field elements, as when the golden proof was recorded (make_traces._plonk_inputs)
+        x, wit = w[:5], w[5:]                                                   # main.py:79-80
+        n = len(sel[0])
+        ipk, ivk = rr.load("plonk.indexer").Indexer(curve_type="bn254").preprocess(*sel, inst["perm"], max_degree=n + 5)
+        assert [int(v) for v in (ipk["subgroups"]["k1"], ipk["subgroups"]["k2"])] == [H(d["k1"]), H(d["k2"])], "draw order differs"
+        proof = rr.load("plonk.prover").Prover(curve_type="bn254").prove(ipk, x, wit)
+        V = rr.load("plonk.verifier").Verifier
+        assert V(curve_type="bn254").verify(ivk, x, proof)
+        bad = {**proof, "evaluations": {**proof["evaluations"], "a": proof["evaluations"]["a"] + 1}}
+        assert not V(curve_type="bn254").verify(ivk, x, bad)
+        assert type(rr.kzg.KZG("bn254")).__module__ == "kzg_snark_b200.kzg"
+    for sec, body in d["proof"].items():
+        for k, v in body.items():
+            got = proof[sec][k]
+            assert (_same_point(got, v) if isinstance(v, list) or v is None else int(got) == H(v)), f"{sec}.{k} differs from the reference's proof"
+
+
+def test_reference_marlin_prover_on_the_gpu_dropin_is_bit_exact():
+    """marlin/{indexer,prover,verifier}.py unmodified + GPU kzg / fft_ff == ref_marlin_normalized.json; verifier accepts;
+    tampered evaluation rejected (marlin/verifier.py:272-285)."""
+    _need_reference()
+    d = json.load(open(os.path.join(GOLD, "ref_marlin_normalized.json")))
+    with refrun.ReferenceRun(seed=d["seed"], record=True, gpu_dropin=True) as rr:
+        inst = _pickle("R1CS_INSTANCE.pkl")
+        Fq = rr.kzg.KZG("bn254").Fq
+        A, B, C, z = inst["A"], inst["B"], inst["C"], [Fq(v) for v in inst["z"]]
+        x, w = z[:5], z[5:]                                                     # main.py:46-48
+        ipk, ivk = rr.load("marlin.indexer").Indexer(curve_type="bn254").preprocess(A, B, C, max_degree=200)
+        proof = rr.load("marlin.prover").Prover(curve_type="bn254").prove(ipk, x, w)
+        V = rr.load("marlin.verifier").Verifier
+        assert V(curve_type="bn254").verify(ivk, x, proof)
+        ev = proof["evaluations"]
+        bad = {**proof, "evaluations": {**ev, "beta1": [ev["beta1"][0] + 1] + list(ev["beta1"][1:])}}         # marlin/verifier.py:274-277
+        assert not V(curve_type="bn254").verify(ivk, x, bad)
+    g = d["proof"]
+    for k, pts in g["commitments"].items():
+        assert all(_same_point(p, q) for p, q in zip(proof["commitments"][k], pts)) and len(pts) == len(proof["commitments"][k]), k
+    for k, vals in g["evaluations"].items():
+        assert [int(e) for e in proof["evaluations"][k]] == [H(v) for v in vals], k
+    for k, v in g["kzg_proofs"].items():
+        assert _same_point(proof["kzg_proofs"][k], v), k

@@ -112,6 +112,12 @@ def test_csrc_semi_reduced_arithmetic_on_host(host_arith):
             lines.append(f"{f} lzmul {a:x} {b:x}"); expect.append(("mul", q, a * b * Rinv % q, None))
         for a in lo + [(1 << (bits - 2)) - 1, 2 * q - 2] + [rng.randrange(2 * q) for _ in range(200)]:
             lines.append(f"{f} lzsqr {a:x} 0"); expect.append(("mul", q, a * a * Rinv % q, None))
+        # a*b - c*d with one Montgomery reduction (fe_mulsub_lz -> fe_mul2_nofinal): all four operands semi-reduced, extremes included
+        quads = [tuple(rng.choice(lo) for _ in range(4)) for _ in range(300)]
+        quads += [(2 * q - 1,) * 4, (2 * q - 1, 2 * q - 1, 0, 2 * q - 1), (2 * q - 1, 2 * q - 1, 1, 2 * q - 1), (0, 0, 2 * q - 1, 2 * q - 1),
+                  (q, q, q, q), (1, 1, 1, 1), (5, 7, 7, 5)]
+        for a, b, c, d in quads:
+            lines.append(f"{f} lzmulsub {a:x} {b:x} {c:x} {d:x}"); expect.append(("fold", q, (a * b - c * d) * Rinv % q, None))
         for _ in range(200):
             a, b = rng.choice(lo), rng.choice(lo)
             lines.append(f"{f} lzadd {a:x} {b:x}"); expect.append(("fold", q, (a + b) % q, None))
