@@ -45,16 +45,19 @@ IMAD32_PER_MODMUL = 272
 # accumulate loop with scripts/sass_loop.py and against ncu's smsp__inst_executed): a general product issues 2N^2 - N
 # IMAD.WIDE (32x32+64 -> 64, one per 2 issue slots of the multiplier pipe) and 2N narrow IMAD / IMAD.HI (one slot: half
 # the cost); the dedicated squaring N(N+1)/2 + N^2 - N wide and 2N narrow.
-def wide_slots(nlimbs, products, squarings):
+# The mixed addition's last coordinate, Y3 = R (Q - X3) - Y1 PPP, is a DUAL product with one reduction (fe_mul2_nofinal):
+# 3N^2 - N wide and 2N narrow instead of two general products.
+def wide_slots(nlimbs, products, squarings, duals=0):
     """multiplier-pipe work in IMAD.WIDE equivalents (narrow multiplies counted at half)."""
     n = nlimbs
     gen = (2 * n * n - n) + 0.5 * (2 * n)
     sqr = (n * (n + 1) // 2 + n * n - n) + 0.5 * (2 * n)
-    return products * gen + squarings * sqr
+    dual = (3 * n * n - n) + 0.5 * (2 * n)
+    return products * gen + squarings * sqr + duals * dual
 
 
-MADD = (8, 2)             # XYZZ mixed addition: 8 products + 2 squarings (curve.cuh xyzz_madd_lz)
-FULL_ADD = (12, 2)        # XYZZ + XYZZ
+MADD = (6, 2, 1)          # XYZZ mixed addition: 6 products + 2 squarings + 1 dual product (curve.cuh xyzz_madd_lz)
+FULL_ADD = (12, 2)        # XYZZ + XYZZ (canonical arithmetic, bucket reduction)
 
 
 def load_traffic(kernel):
@@ -427,7 +430,7 @@ def run_gpu(args):
 
     # ------------------------------------------------------------------ integer roofline (live)
     sm = info["sm_count"]
-    ms_i, ops_i = _ffi.microbench(0, sm * 4, 256, 2000)
+    ms_i, ops_i = _ffi.microbench(0, sm * 4, 256, 2000, device=local)
     imad_wide_peak = ops_i / ms_i * 1e3                   # IMAD.WIDE.U32 / s, measured now on this GPU
     imad32_peak = 2.0 * imad_wide_peak                    # one wide = two 32-bit multiply-add slots (the SURVEY model's unit)
 
@@ -551,7 +554,7 @@ def run_gpu(args):
                 "frac": frac,
                 "traffic": load_traffic("msm_accumulate_kernel") if (args.logn == 24 and world == 1 and curve == "bn254") else None,
                 "model": f"executed multiplier work: {madds / n:.0f} mixed additions per point (fixed-base tables, c = {r['key']['c']}) x "
-                         f"{wide_slots(nl, *MADD):.0f} IMAD.WIDE-equivalents (8 products + 2 squarings on {nl} limbs; narrow IMAD / IMAD.HI "
+                         f"{wide_slots(nl, *MADD):.0f} IMAD.WIDE-equivalents (6 products + 2 squarings + 1 dual product on {nl} limbs; narrow IMAD / IMAD.HI "
                          "counted at half) / kernel time / IMAD.WIDE.U32 issue rate measured live (kzgpu_microbench 0); "
                          "compare ncu sm__pipe_fma_cycles_active / 50 % in profiles/",
                 "step_frac": step_slots / (ms / K * 1e-3) / imad_wide_peak,

@@ -16,8 +16,11 @@
  *    (0, 0) (py_ecc's Z1 = (1, 1, 0), kzg.py:42, is mapped to it by the host shim).
  *  - pointers are caller-owned host buffers unless the name starts with d_ (device
  *    pointers obtained from kzgpu_alloc).
- *  - one caller thread at a time; one CUDA device per process (the multi-GPU layout is
- *    one process per GPU).
+ *  - one caller thread at a time.  The library drives one device (kzgpu_init; also the layout of the one-process-per-GPU
+ *    torchrun harness) or several (kzgpu_init_multi): then the entry points that shard naturally -- kzgpu_msm,
+ *    kzgpu_msm_dev, kzgpu_msm_batch, kzgpu_ntt_batch, kzgpu_open* -- spread their work over the devices from this one
+ *    process, with no PyTorch and no launcher.  Device pointers (d_*) and
+ *    everything else always refer to the FIRST device of the list.
  */
 #ifndef KZGPU_H
 #define KZGPU_H
@@ -42,6 +45,19 @@ extern "C" {
 
 /* ---- context ----------------------------------------------------------------------- */
 int kzgpu_init(int device);                  /* cudaSetDevice + streams; idempotent */
+/* SURVEY.md 8(b)'s kzgpu_init(ndev, devs): initialise on `ndev` devices (devs == NULL: devices 0 .. ndev-1; ndev <= 0: every
+ * visible device).  devs[0] is the primary device.  One worker thread per further device; peer access is enabled where
+ * the hardware offers it (NVLink / NVSwitch), otherwise peer copies stage through the host.
+ *   kzgpu_msm / kzgpu_msm_dev / kzgpu_open*: an MSM of >= KZGPU_SHARD_MIN points (env, default 2^20) is point-sharded:
+ *     device d owns the contiguous range d of the key (with window tables sized for the SHARD), reduces it to one XYZZ
+ *     partial sum, writes it peer-to-peer into the primary device's gather buffer, and the primary folds the ndev partials
+ *     (kzg.py:112-116 is a plain sum, so any partition of the index range is exact).
+ *   kzgpu_msm_batch: the k polynomials of one commit() (kzg.py:102) are placed whole, longest first, on the least
+ *     loaded device (each holds a replica of the key); polynomials of >= KZGPU_SHARD_MIN coefficients are point-sharded.
+ *   kzgpu_ntt_batch: whole vectors per device.
+ * Shards and replicas of a key are built on first use from the primary device's copy (peer copies + local table build). */
+int kzgpu_init_multi(int ndev, const int* devs);
+int kzgpu_device_count(int* ndev);           /* devices the library is initialised on */
 int kzgpu_shutdown(void);                    /* frees SRS handles, NTT plans, workspaces */
 int kzgpu_last_error(char* buf, size_t cap);
 int kzgpu_device_info(char* name, size_t cap, int* sm_count, size_t* total_mem);
@@ -230,14 +246,7 @@ int kzgpu_marlin_t_evals_dev(int field, size_t n, size_t m, const uint32_t* d_ro
  * which: 0 = Fp(curve), 1 = Fr(curve); op: 0 mul, 1 add, 2 sub, 3 inverse(a). */
 int kzgpu_field_op(int curve, int which, int op, const uint64_t* a, const uint64_t* b,
                    uint64_t* out, size_t n);
-/* throughput microbenchmarks (DESIGN.md "integer roofline"): runs `iters` dependent
- * operations per thread on blocks*threads threads and returns the elapsed device ms.
- * kind: 0 = IMAD.WIDE.U32 carry chain (raw pipe), 1 = Fp(BN254) Montgomery mul,
- *       2 = Fp(BLS12-381) Montgomery mul, 3 = XYZZ mixed add BN254, 4 = XYZZ mixed add BLS,
- *       5..11 = issue-slot probes (ALU / FP64 beside IMAD.WIDE), 12 / 13 = batched-affine pair additions with one
- *       inversion per thread over `iters` pairs, operands consecutive (12) or gathered from an 8 GiB table (13);
- *       *ops = additions */
-int kzgpu_microbench(int kind, int blocks, int threads, int iters, float* ms, double* ops);
+/* (the throughput microbenchmarks live in their own library: include/kzgpu_bench.h, libkzgpu_bench.so) */
 /* per-kernel device timing (CUDA events on the launching stream) for bench.py's roofline:
  * which: 0 = MSM bucket-accumulate kernel, 1 = NTT pass kernel, 2 = MSM sort (histogram+scatter),
  *        3 = MSM bucket reduction + window fold.  Accumulates while enabled. */

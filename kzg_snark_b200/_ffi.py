@@ -37,6 +37,8 @@ _intp = ctypes.POINTER(ctypes.c_int)
 # (tests/test_abi.py cross-checks this table against the header).
 SIGNATURES = {
     "kzgpu_init": (ctypes.c_int, [ctypes.c_int]),
+    "kzgpu_init_multi": (ctypes.c_int, [ctypes.c_int, _intp]),
+    "kzgpu_device_count": (ctypes.c_int, [_intp]),
     "kzgpu_shutdown": (ctypes.c_int, []),
     "kzgpu_last_error": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t]),
     "kzgpu_device_info": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, _intp, _szp]),
@@ -87,7 +89,6 @@ SIGNATURES = {
     "kzgpu_marlin_f2_evals_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t] + [ctypes.c_void_p] * 8),
     "kzgpu_marlin_t_evals_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t] + [ctypes.c_void_p] * 8),
     "kzgpu_field_op": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
-    "kzgpu_microbench": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]),
     "kzgpu_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "kzgpu_profile_reset": (ctypes.c_int, []),
     "kzgpu_profile_get": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), _u64p, ctypes.POINTER(ctypes.c_double)]),
@@ -124,16 +125,44 @@ def check(rc):
 
 
 def init(device=None):
-    """Initialise the process-wide GPU context (a singleton, not per-KZG)."""
+    """Initialise the process-wide GPU context (a singleton, not per-KZG).
+
+    One device by default (`device`, else $KZGPU_DEVICE, else $LOCAL_RANK, else 0).  $KZGPU_DEVICES = "all" or a comma
+    separated list ("0,1,2,3") initialises the library on several devices of this ONE process (kzgpu_init_multi): large
+    MSMs are then point-sharded and batched commits / NTTs spread over them inside the library, no launcher involved."""
     global _inited
     lib = load_library()
     if _inited:
         return lib
+    multi = os.environ.get("KZGPU_DEVICES") if device is None else None
+    if multi and "LOCAL_RANK" not in os.environ:
+        return init_multi(None if multi.strip().lower() == "all" else [int(x) for x in multi.split(",")])
     if device is None:
         device = int(os.environ.get("KZGPU_DEVICE", os.environ.get("LOCAL_RANK", "0")))
     check(lib.kzgpu_init(device))
     _inited = True
     return lib
+
+
+def init_multi(devices=None):
+    """Initialise on several devices of this process: `devices` = list of CUDA ordinals (first = primary), None = all."""
+    global _inited
+    lib = load_library()
+    if _inited:
+        return lib
+    if devices is None:
+        check(lib.kzgpu_init_multi(0, None))
+    else:
+        arr = (ctypes.c_int * len(devices))(*devices)
+        check(lib.kzgpu_init_multi(len(devices), arr))
+    _inited = True
+    return lib
+
+
+def device_count():
+    n = ctypes.c_int(0)
+    load_library().kzgpu_device_count(ctypes.byref(n))
+    return n.value
 
 
 def shutdown():
@@ -209,11 +238,26 @@ def timer_stop():
     return ms.value
 
 
-def microbench(kind, blocks, threads, iters):
-    lib = init()
+BENCH_LIB_PATH = os.path.join(_HERE, "libkzgpu_bench.so")
+_bench_lib = None
+
+
+def microbench(kind, blocks, threads, iters, device=None):
+    """Throughput microbenchmark from the separate measurement library (include/kzgpu_bench.h; not part of the product ABI)."""
+    global _bench_lib
+    if _bench_lib is None:
+        if not os.path.exists(BENCH_LIB_PATH):
+            raise KzgpuError(E_NOTINIT, f"{BENCH_LIB_PATH} not built; run `python -m kzg_snark_b200.build`")
+        _bench_lib = ctypes.CDLL(BENCH_LIB_PATH)
+        _bench_lib.kzgpu_microbench.restype = ctypes.c_int
+        _bench_lib.kzgpu_microbench.argtypes = [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]
+    if device is None:
+        device = int(os.environ.get("KZGPU_DEVICE", os.environ.get("LOCAL_RANK", "0")))
     ms = ctypes.c_float(0)
     ops = ctypes.c_double(0)
-    check(lib.kzgpu_microbench(kind, blocks, threads, iters, ctypes.byref(ms), ctypes.byref(ops)))
+    rc = _bench_lib.kzgpu_microbench(device, kind, blocks, threads, iters, ctypes.byref(ms), ctypes.byref(ops))
+    if rc:
+        raise KzgpuError(rc, "kzgpu_microbench failed")
     return ms.value, ops.value
 
 

@@ -12,7 +12,9 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libkzgpu.so")
+OUT_BENCH = os.path.join(HERE, "libkzgpu_bench.so")          # microbenchmarks: measurement tooling, separate from the product library
 SOURCES = ["context.cu", "ntt.cu", "msm.cu", "poly.cu", "plonk.cu"]
+BENCH_SOURCES = ["microbench.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -23,15 +25,15 @@ FLAGS = [
 
 
 def _needs_rebuild():
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or not os.path.exists(OUT_BENCH):
         return True
     t = os.path.getmtime(OUT)
     for root, _, files in os.walk(CSRC):
         for f in files:
             if f.endswith((".cu", ".cuh")) and os.path.getmtime(os.path.join(root, f)) > t:
                 return True
-    inc = os.path.join(os.path.dirname(HERE), "include", "kzgpu.h")
-    return os.path.getmtime(inc) > t
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    return max(os.path.getmtime(os.path.join(inc, f)) for f in os.listdir(inc)) > t
 
 
 def build(force=False, verbose=False):
@@ -41,7 +43,7 @@ def build(force=False, verbose=False):
     os.makedirs(objdir, exist_ok=True)
 
     hdr_t = max([os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC) if f.endswith(".cuh")] +
-                [os.path.getmtime(os.path.join(os.path.dirname(HERE), "include", "kzgpu.h"))])
+                [os.path.getmtime(os.path.join(os.path.dirname(HERE), "include", f)) for f in ("kzgpu.h", "kzgpu_bench.h")])
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
@@ -58,12 +60,13 @@ def build(force=False, verbose=False):
             sys.stderr.write(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=4) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
-    cmd = [NVCC, "-shared", "-o", OUT, *objs, "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with ThreadPoolExecutor(max_workers=6) as ex:
+        objs = list(ex.map(compile_one, SOURCES + BENCH_SOURCES))
+    for out, parts in ((OUT, objs[:len(SOURCES)]), (OUT_BENCH, objs[len(SOURCES):])):
+        cmd = [NVCC, "-shared", "-o", out, *parts, "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return OUT
 
 

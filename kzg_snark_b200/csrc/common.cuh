@@ -5,9 +5,23 @@
 #include <cstdio>
 #include <cstdarg>
 #include <string>
+#include <functional>
 #include "../../include/kzgpu.h"
 #include "params_gen.cuh"
 #include "curve.cuh"
+
+// Devices: the library is initialised on 1 .. KZ_MAX_DEV devices (kzgpu_init / kzgpu_init_multi).  Every device has a
+// SLOT with its own context (streams, events, error text) and its own workspaces in each translation unit.  Slot 0 is the
+// primary device and belongs to the caller's thread; slots >= 1 each belong to a worker thread of context.cu that has
+// made its device current once and for all.  kz_slot() is the calling thread's slot, so the single-device code paths run
+// unchanged on any slot; multi-device entry points fan out with kz_parallel().
+constexpr int KZ_MAX_DEV = 16;
+int kz_slot();
+int kz_ndev();
+int kz_device_of(int slot);
+// fn(slot) on every slot < ndev concurrently (slot 0 on the calling thread); returns the first non-zero code, whose message
+// is copied into slot 0's error text
+int kz_parallel(const std::function<int(int)>& fn);
 
 struct KzgpuCtx {
   bool inited = false;
@@ -17,6 +31,7 @@ struct KzgpuCtx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t own_stream = nullptr;
   cudaStream_t copy_stream = nullptr;     // chunked host->device uploads overlapped with compute
+  cudaStream_t d2h_stream = nullptr;      // batched NTTs: download of vector k while vector k+1 uploads (full duplex)
   cudaEvent_t copy_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t sort_stream = nullptr;     // MSM: sort of chunk k+1 (HBM/LSU-bound) overlapped with the accumulate of chunk k (multiplier-bound)
   cudaEvent_t sort_ev[2] = {nullptr, nullptr}, acc_ev[2] = {nullptr, nullptr}, start_ev = nullptr;
@@ -29,7 +44,8 @@ struct KzgpuCtx {
   double prof_work[4] = {0, 0, 0, 0};
 };
 
-KzgpuCtx& kz_ctx();
+KzgpuCtx& kz_ctx();                        // context of the calling thread's slot
+KzgpuCtx& kz_ctx_of(int slot);
 int kz_fail(int code, const char* fmt, ...);
 
 // scoped CUDA-event timer around one or more launches of a profiled kernel class
@@ -56,6 +72,13 @@ struct KzProf {
 
 #define KZ_REQUIRE_INIT() \
   do { if (!kz_ctx().inited) return kz_fail(KZGPU_ENOTINIT, "kzgpu_init has not been called"); } while (0)
+
+// per-slot instance of a translation unit's global state
+template <class T> struct KzPerSlot {
+  T v[KZ_MAX_DEV];
+  T& get() { return v[kz_slot()]; }
+  T& of(int slot) { return v[slot]; }
+};
 
 #define KZ_CUDA(expr) \
   do { cudaError_t e__ = (expr); \

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include <map>
 #include <vector>
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -28,27 +29,39 @@ struct BLS381Cfg { using Fp = FpBLS381; using Fr = FrBLS381; static constexpr in
 // per-window bucket sets nor the final Horner chain of c*W doublings.  Costs W x the key's
 // footprint (12 GiB for 2^24 BN254 points at c = 22) -- what the 180 GB of HBM3e is for -- and a
 // one-off build.  c_tab == 0: plain key (tables disabled or too large), per-call window choice.
+struct SrsPart {          // one device's copy of the index range [first, first + n) of a key
+  uint32_t* d_points = nullptr;     // affine, Montgomery form, [x | y] per point; W_tab tables of n points
+  size_t first = 0, n = 0;
+  uint32_t c_tab = 0, W_tab = 1;
+  int slot = 0;
+};
 struct Srs {
   int curve;
   size_t n;
-  uint32_t* d_points;     // affine, Montgomery form, [x | y] per point; W_tab tables of n points
-  uint32_t c_tab = 0, W_tab = 1;
+  SrsPart full;                      // the whole key on the primary device (slot 0)
+  // multi-device layouts, built on first use from `full` (peer copy of the plain points, local table build):
+  bool has_shards = false, has_replicas = false;
+  SrsPart shard[KZ_MAX_DEV];         // slot d owns the contiguous range d of the key, tables sized for the SHARD
+  SrsPart replica[KZ_MAX_DEV];       // the whole key, tables included, on every slot (replica[0] aliases full)
 };
 
 std::map<uint64_t, Srs> g_srs;
 uint64_t g_next_handle = 1;
 
 struct MsmWs {                         // shared by all chunks of a call
-  KzScratch buckets, partials, winsums, result, flag, scal;
+  KzScratch buckets, partials, winsums, result, flag, scal, gather;
 };
-MsmWs g_ws;
+KzPerSlot<MsmWs> g_ws_slots;
+#define g_ws (g_ws_slots.get())
 // what the sort + task phase of one chunk produces and its accumulate / merge consumes: two sets, so that the
 // sort of chunk k+1 (sort stream) runs while chunk k is accumulated (main stream)
 struct MsmSortWs {
   KzScratch counts, offsets, cursor, entries, blocksums;
   KzScratch ntasks, task_off, size_hist, t_start, t_len, t_dest, tparts, multi, sort_tmp, coarse;
 };
-MsmSortWs g_sw[2];
+struct MsmSortPair { MsmSortWs w[2]; };
+KzPerSlot<MsmSortPair> g_sw_slots;
+#define g_sw (g_sw_slots.get().w)
 
 // ---------------------------------------------------------------- device helpers
 template <class P> __device__ __forceinline__ void ld_words(uint32_t* dst, const uint32_t* src) {
@@ -225,13 +238,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t* arr, uint32_t nbin
 // memory (count -> scan -> place), the range of every bin is reserved with ONE global atomic, and
 // the staged records are written out in order, so that a bin's run leaves the SM as consecutive
 // 8-byte stores within a few instructions (partial sectors are completed while still in L2).
-// Shared memory: stage[tile * W] (u64) | cur[ncoarse] | delta[ncoarse] | scan scratch[blockDim]
-//
-// FAST = true (11 <= W <= 16, i.e. every key of >= 2^16 points): each thread owns at most two scalars, which stay in
-// registers between the two phases; the shared-memory atomic of the counting phase also returns the record's rank inside its
-// bin (kept as 16 bits), so the placing phase needs neither a second load of the scalar nor a second atomic.
-// FAST = false: any W; the scalar is re-read and re-ranked in the placing phase.
-template <bool FAST>
+// Shared memory: cur[ncoarse] | delta[ncoarse] | scan scratch[blockDim] | stage[tile * W] (u64)
 __global__ void __launch_bounds__(512) msm_partition_kernel(const uint32_t* __restrict__ scalars, size_t n, uint32_t tile, SortGeom g,
                                                             DigitOffset off, uint32_t* __restrict__ coarse_cur,
                                                             uint64_t* __restrict__ tmp) {
@@ -243,34 +250,14 @@ __global__ void __launch_bounds__(512) msm_partition_kernel(const uint32_t* __re
   for (uint32_t b = threadIdx.x; b < g.ncoarse; b += blockDim.x) cur[b] = 0;
   __syncthreads();
   const size_t base = (size_t)blockIdx.x * tile;
-  constexpr int MAXW = 16, PER = 2;
-  uint32_t sreg[FAST ? PER : 1][8];
-  uint32_t rank[FAST ? PER : 1][FAST ? MAXW / 2 : 1];          // two 16-bit ranks per word
-  if constexpr (FAST) {
-#pragma unroll
-    for (int q = 0; q < PER; q++) {
-      const uint32_t k = threadIdx.x + q * blockDim.x;
-      const size_t i = base + k;
-      if (k < tile && i < n) {
-        load_scalar_plus_offset(scalars, i, off, sreg[q]);
-#pragma unroll
-        for (int w = 0; w < MAXW; w++) {
-          uint32_t key, val, r = 0;
-          if ((uint32_t)w < g.W && digit_entry(sreg[q], w, g, (uint32_t)i, key, val)) r = atomicAdd(&cur[key >> g.f], 1u);
-          if (w & 1) rank[q][w >> 1] |= r << 16; else rank[q][w >> 1] = r;
-        }
-      }
-    }
-  } else {
-    for (uint32_t k = threadIdx.x; k < tile; k += blockDim.x) {
-      size_t i = base + k;
-      if (i >= n) break;
-      uint32_t s[8];
-      load_scalar_plus_offset(scalars, i, off, s);
-      for (uint32_t w = 0; w < g.W; w++) {
-        uint32_t key, val;
-        if (digit_entry(s, w, g, (uint32_t)i, key, val)) atomicAdd(&cur[key >> g.f], 1u);
-      }
+  for (uint32_t k = threadIdx.x; k < tile; k += blockDim.x) {
+    size_t i = base + k;
+    if (i >= n) break;
+    uint32_t s[8];
+    load_scalar_plus_offset(scalars, i, off, s);
+    for (uint32_t w = 0; w < g.W; w++) {
+      uint32_t key, val;
+      if (digit_entry(s, w, g, (uint32_t)i, key, val)) atomicAdd(&cur[key >> g.f], 1u);
     }
   }
   __syncthreads();
@@ -283,34 +270,16 @@ __global__ void __launch_bounds__(512) msm_partition_kernel(const uint32_t* __re
   const uint32_t total = block_excl_scan(cur, g.ncoarse, scratch);
   for (uint32_t b = threadIdx.x; b < g.ncoarse; b += blockDim.x) delta[b] -= cur[b];     // global pos = local pos + delta
   __syncthreads();
-  if constexpr (FAST) {
-#pragma unroll
-    for (int q = 0; q < PER; q++) {
-      const uint32_t k = threadIdx.x + q * blockDim.x;
-      const size_t i = base + k;
-      if (k < tile && i < n) {
-#pragma unroll
-        for (int w = 0; w < MAXW; w++) {
-          uint32_t key, val;
-          if ((uint32_t)w < g.W && digit_entry(sreg[q], w, g, (uint32_t)i, key, val)) {
-            const uint32_t r = (w & 1) ? rank[q][w >> 1] >> 16 : rank[q][w >> 1] & 0xffffu;
-            stage[cur[key >> g.f] + r] = ((uint64_t)key << 32) | val;        // cur[] = start of the bin's run (exclusive scan)
-          }
-        }
-      }
-    }
-  } else {
-    for (uint32_t k = threadIdx.x; k < tile; k += blockDim.x) {
-      size_t i = base + k;
-      if (i >= n) break;
-      uint32_t s[8];
-      load_scalar_plus_offset(scalars, i, off, s);
-      for (uint32_t w = 0; w < g.W; w++) {
-        uint32_t key, val;
-        if (digit_entry(s, w, g, (uint32_t)i, key, val)) {
-          uint32_t pos = atomicAdd(&cur[key >> g.f], 1u);
-          stage[pos] = ((uint64_t)key << 32) | val;
-        }
+  for (uint32_t k = threadIdx.x; k < tile; k += blockDim.x) {
+    size_t i = base + k;
+    if (i >= n) break;
+    uint32_t s[8];
+    load_scalar_plus_offset(scalars, i, off, s);
+    for (uint32_t w = 0; w < g.W; w++) {
+      uint32_t key, val;
+      if (digit_entry(s, w, g, (uint32_t)i, key, val)) {
+        uint32_t pos = atomicAdd(&cur[key >> g.f], 1u);
+        stage[pos] = ((uint64_t)key << 32) | val;
       }
     }
   }
@@ -364,7 +333,7 @@ __global__ void __launch_bounds__(256) msm_fine_hist_kernel(const uint64_t* __re
 // pass 2b: scatter of the values into the per-key lists, staged like pass 1c: the chunk's values
 // are sorted by fine key in shared memory and every key's run is written by a group of 8 lanes.
 // Shared memory: cur[F] | gpos[F] | scan scratch[blockDim] | stage[kSortChunk] (u32)
-__global__ void __launch_bounds__(512, 2) msm_fine_scatter_kernel(const uint64_t* __restrict__ tmp, const uint32_t* __restrict__ coarse_off,
+__global__ void __launch_bounds__(512) msm_fine_scatter_kernel(const uint64_t* __restrict__ tmp, const uint32_t* __restrict__ coarse_off,
                                                                const uint32_t* __restrict__ blk_off, uint32_t ncoarse, uint32_t f,
                                                                uint32_t nkeys, uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
   extern __shared__ uint32_t sh[];
@@ -377,37 +346,24 @@ __global__ void __launch_bounds__(512, 2) msm_fine_scatter_kernel(const uint64_t
   uint32_t* stage = scratch + blockDim.x;
   for (uint32_t j = threadIdx.x; j < F; j += blockDim.x) cur[j] = 0;
   __syncthreads();
-  // counting phase: the atomic also returns the record's rank inside its key (16 bits each, kSortChunk / 512 = 32 per thread)
-  constexpr int PER = kSortChunk / 512;
-  uint32_t rank[PER / 2];
-#pragma unroll
-  for (int q = 0; q < PER; q++) {
-    const uint32_t i = lo + threadIdx.x + q * 512;
-    uint32_t r = 0;
-    if (i < hi) r = atomicAdd(&cur[(uint32_t)(tmp[i] >> 32) & (F - 1)], 1u);
-    if (q & 1) rank[q >> 1] |= r << 16; else rank[q >> 1] = r;
-  }
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&cur[(uint32_t)(tmp[i] >> 32) & (F - 1)], 1u);
   __syncthreads();
   for (uint32_t j = threadIdx.x; j < F; j += blockDim.x) {
     uint32_t key = (bin << f) + j, cnt = cur[j];
     gpos[j] = (cnt && key < nkeys) ? atomicAdd(&cursor[key], cnt) : 0u;
   }
   __syncthreads();
-  block_excl_scan(cur, F, scratch);                      // cur[j] = start of key j's run in stage[]
-#pragma unroll
-  for (int q = 0; q < PER; q++) {
-    const uint32_t i = lo + threadIdx.x + q * 512;
-    if (i < hi) {
-      const uint64_t rec = tmp[i];                       // second read of the chunk: L2
-      const uint32_t r = (q & 1) ? rank[q >> 1] >> 16 : rank[q >> 1] & 0xffffu;
-      stage[cur[(uint32_t)(rec >> 32) & (F - 1)] + r] = (uint32_t)rec;
-    }
+  block_excl_scan(cur, F, scratch);
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    uint64_t rec = tmp[i];
+    uint32_t pos = atomicAdd(&cur[(uint32_t)(rec >> 32) & (F - 1)], 1u);
+    stage[pos] = (uint32_t)rec;
   }
   __syncthreads();
-  // cur[j] is the START of key j's run in stage[]; its end is cur[j+1] (the chunk's record count for the last key)
+  // cur[j] is now the END of key j's run in stage[]; its start is cur[j-1] (0 for j == 0)
   const uint32_t grp = threadIdx.x >> 3, ln = threadIdx.x & 7, ngrp = blockDim.x >> 3;
   for (uint32_t j = grp; j < F; j += ngrp) {
-    uint32_t s0 = cur[j], s1 = j + 1 < F ? cur[j + 1] : hi - lo, gp = gpos[j];
+    uint32_t s0 = j ? cur[j - 1] : 0u, s1 = cur[j], gp = gpos[j];
     for (uint32_t k = s0 + ln; k < s1; k += 8) entries[gp + (k - s0)] = stage[k];
   }
 }
@@ -623,7 +579,7 @@ __global__ void msm_clear_empty_kernel(const uint32_t* __restrict__ ntasks, uint
 // chunked running sum: thread (w, chunk) reduces CH consecutive buckets of window w to
 //   sum_b (b + 1) * B_b  over its chunk  =  acc + lo * running
 template <class Cfg>
-__global__ void __launch_bounds__(128, (Cfg::Fp::N == 8 ? 3 : 1)) msm_reduce_kernel(const uint32_t* __restrict__ buckets, uint32_t B, uint32_t CH,
+__global__ void __launch_bounds__(128) msm_reduce_kernel(const uint32_t* __restrict__ buckets, uint32_t B, uint32_t CH,
                                                         uint32_t chunks_per_window, uint32_t W, uint32_t* __restrict__ partials) {
   using P = typename Cfg::Fp;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -869,8 +825,9 @@ uint32_t choose_table_c(size_t n, int bits, size_t point_bytes) {
   return best_c;
 }
 
+// `srs`: one device's part of a key (the calling thread's device); `first` is an index INSIDE that part
 template <class Cfg>
-int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, int mode, uint32_t* d_out,
+int msm_core(const SrsPart& srs, size_t first, const uint32_t* d_scalars, size_t n, int mode, uint32_t* d_out,
              const uint64_t* h_scalars = nullptr, uint32_t* h_out_xyzz = nullptr, uint32_t batch = 1) {
   // batch > 1: d_scalars holds `batch` polynomials of n / batch scalars each (zero padded to equal length); they
   // share one sort / accumulate / reduce pass, every polynomial owning its own bucket set(s), and d_out receives
@@ -1029,10 +986,7 @@ int msm_core(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, 
     KZ_LAUNCHED();
     const uint32_t ptile = kSortStage / W;                       // scalars per partition block
     const size_t psmem = (size_t)ptile * W * 8 + (2 * (size_t)ncoarse + 512) * 4;
-    if (W >= 11 && W <= 16)            // ptile <= 1024: two scalars per thread, ranks in registers
-      msm_partition_kernel<true><<<(unsigned)kz_div_up(n, ptile), 512, psmem, sst>>>(d_scalars, n, ptile, geo, doff, coarse_cur, sort_tmp);
-    else
-      msm_partition_kernel<false><<<(unsigned)kz_div_up(n, ptile), 512, psmem, sst>>>(d_scalars, n, ptile, geo, doff, coarse_cur, sort_tmp);
+    msm_partition_kernel<<<(unsigned)kz_div_up(n, ptile), 512, psmem, sst>>>(d_scalars, n, ptile, geo, doff, coarse_cur, sort_tmp);
     KZ_LAUNCHED();
     const size_t sort_blocks = (n * W) / kSortChunk + ncoarse + 1;
     msm_fine_hist_kernel<<<(unsigned)sort_blocks, 256, (4u << f), sst>>>(sort_tmp, coarse_off, blk_off, ncoarse, f, (uint32_t)nb, counts);
@@ -1169,7 +1123,7 @@ template <class P> void host_xyzz_to_canonical(const uint32_t* h, uint32_t* out_
 }
 
 template <class Cfg>
-int msm_affine(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n, uint64_t* out_xy, int* is_inf,
+int msm_affine(const SrsPart& srs, size_t first, const uint32_t* d_scalars, size_t n, uint64_t* out_xy, int* is_inf,
                const uint64_t* h_scalars = nullptr) {
   using P = typename Cfg::Fp;
   int rc;
@@ -1182,7 +1136,7 @@ int msm_affine(const Srs& srs, size_t first, const uint32_t* d_scalars, size_t n
 
 // k equal-length polynomials in one pass -> k canonical affine points
 template <class Cfg>
-int msm_affine_batch(const Srs& srs, const uint32_t* d_scalars, size_t poly_len, size_t k, uint64_t* out_xy, int* is_inf) {
+int msm_affine_batch(const SrsPart& srs, const uint32_t* d_scalars, size_t poly_len, size_t k, uint64_t* out_xy, int* is_inf) {
   using P = typename Cfg::Fp;
   int rc;
   if ((rc = g_ws.result.ensure(k * 4 * P::N * 4 + 4))) return rc;
@@ -1193,29 +1147,30 @@ int msm_affine_batch(const Srs& srs, const uint32_t* d_scalars, size_t poly_len,
   return 0;
 }
 
+// dynamic shared memory limits are per device: once per slot
 int set_smem_attrs() {
-  static bool done = false;
-  if (done) return 0;
+  static bool done[KZ_MAX_DEV] = {false};
+  if (done[kz_slot()]) return 0;
   KZ_CUDA(cudaFuncSetAttribute(msm_window_kernel<BLS381Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 4 * 12 * 4));
   KZ_CUDA(cudaFuncSetAttribute(g1_fold_kernel<BLS381Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 4 * 12 * 4));
-  KZ_CUDA(cudaFuncSetAttribute(msm_partition_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortStage * 8 + (2 * kMaxCoarse + 512) * 4));
-  KZ_CUDA(cudaFuncSetAttribute(msm_partition_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortStage * 8 + (2 * kMaxCoarse + 512) * 4));
+  KZ_CUDA(cudaFuncSetAttribute(msm_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortStage * 8 + (2 * kMaxCoarse + 512) * 4));
   KZ_CUDA(cudaFuncSetAttribute(msm_fine_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 << 13) + (512 + kSortChunk) * 4));
-  done = true;
+  done[kz_slot()] = true;
   return 0;
 }
 
-const Srs* find_srs(uint64_t handle) {
+Srs* find_srs(uint64_t handle) {
   auto it = g_srs.find(handle);
   return it == g_srs.end() ? nullptr : &it->second;
 }
 
-// allocate the key (W tables when enabled); build_tables() fills tables 1..W-1 from table 0
+// allocate one part of n points on the calling thread's device (W tables when enabled); build_tables() fills tables
+// 1..W-1 from table 0
 template <class Cfg>
-int srs_alloc(Srs& s, size_t n) {
+int part_alloc(SrsPart& s, size_t first, size_t n) {
   using P = typename Cfg::Fp;
   using R = typename Cfg::Fr;
-  s.curve = Cfg::id; s.n = n; s.d_points = nullptr;
+  s.first = first; s.n = n; s.d_points = nullptr; s.slot = kz_slot();
   const size_t pt_bytes = 2 * P::N * 4;
   s.c_tab = n ? choose_table_c(n, R::BITS, pt_bytes) : 0;
   s.W_tab = s.c_tab ? (R::BITS + 1 + s.c_tab - 1) / s.c_tab : 1;
@@ -1232,7 +1187,7 @@ int srs_alloc(Srs& s, size_t n) {
 }
 
 template <class Cfg>
-int srs_build_tables(Srs& s) {
+int part_build_tables(SrsPart& s) {
   using P = typename Cfg::Fp;
   KzgpuCtx& cx = kz_ctx();
   const size_t stride = s.n * 2 * P::N;
@@ -1249,14 +1204,15 @@ int srs_create_impl(const uint64_t* affine_xy, size_t n, uint64_t* handle) {
   using P = typename Cfg::Fp;
   KzgpuCtx& cx = kz_ctx();
   Srs s;
-  int rc0 = srs_alloc<Cfg>(s, n);
+  s.curve = Cfg::id; s.n = n;
+  int rc0 = part_alloc<Cfg>(s.full, 0, n);
   if (rc0) return rc0;
   size_t bytes = n * 2 * P::N * 4;
   if (n) {
-    KZ_CUDA(cudaMemcpyAsync(s.d_points, affine_xy, bytes, cudaMemcpyHostToDevice, cx.stream));
-    srs_to_mont_kernel<Cfg><<<(unsigned)kz_div_up(2 * n, 128), 128, 0, cx.stream>>>(s.d_points, n);
+    KZ_CUDA(cudaMemcpyAsync(s.full.d_points, affine_xy, bytes, cudaMemcpyHostToDevice, cx.stream));
+    srs_to_mont_kernel<Cfg><<<(unsigned)kz_div_up(2 * n, 128), 128, 0, cx.stream>>>(s.full.d_points, n);
     KZ_LAUNCHED();
-    int rc1 = srs_build_tables<Cfg>(s);
+    int rc1 = part_build_tables<Cfg>(s.full);
     if (rc1) return rc1;
     KZ_CUDA(cudaStreamSynchronize(cx.stream));
   }
@@ -1285,18 +1241,210 @@ int srs_generate_impl(const uint64_t* tau, size_t start, size_t n, uint64_t* han
   KZ_CUDA(cudaMalloc((void**)&d_table, table.size() * 4));
   KZ_CUDA(cudaMemcpyAsync(d_table, table.data(), table.size() * 4, cudaMemcpyHostToDevice, cx.stream));
   Srs s;
-  int rc0 = srs_alloc<Cfg>(s, n);
+  s.curve = Cfg::id; s.n = n;
+  int rc0 = part_alloc<Cfg>(s.full, 0, n);
   if (rc0) return rc0;
   if (n) {
-    srs_generate_kernel<Cfg><<<(unsigned)kz_div_up(n, 128), 128, 0, cx.stream>>>(s.d_points, start, n, fe_to_mont<R>(t), d_table);
+    srs_generate_kernel<Cfg><<<(unsigned)kz_div_up(n, 128), 128, 0, cx.stream>>>(s.full.d_points, start, n, fe_to_mont<R>(t), d_table);
     KZ_LAUNCHED();
-    int rc1 = srs_build_tables<Cfg>(s);
+    int rc1 = part_build_tables<Cfg>(s.full);
     if (rc1) return rc1;
   }
   KZ_CUDA(cudaStreamSynchronize(cx.stream));
   cudaFree(d_table);
   *handle = g_next_handle++;
   g_srs[*handle] = s;
+  return 0;
+}
+
+void srs_free(Srs& s) {
+  cudaFree(s.full.d_points);
+  for (int d = 0; d < KZ_MAX_DEV; d++) {
+    if (s.has_shards && s.shard[d].d_points) cudaFree(s.shard[d].d_points);
+    if (s.has_replicas && d > 0 && s.replica[d].d_points) cudaFree(s.replica[d].d_points);
+  }
+}
+
+// ---------------------------------------------------------------- several devices (kzgpu_init_multi)
+size_t shard_min() {
+  static size_t v = 0;
+  if (!v) {
+    const char* env = getenv("KZGPU_SHARD_MIN");
+    v = env && atoll(env) > 0 ? (size_t)atoll(env) : (size_t)1 << 20;
+  }
+  return v;
+}
+
+// Point shards: slot d owns the contiguous range d of the key.  Its plain points come from the primary device's table 0
+// by a peer copy (NVLink when peer access is on); the window tables are built locally, for the SHARD's size -- a 2^21-point
+// shard of a 2^24-point key gets c = 20 (2^19 buckets to reduce per MSM), not the key's c = 22.
+template <class Cfg>
+int ensure_shards(Srs& s) {
+  using P = typename Cfg::Fp;
+  if (s.has_shards) return 0;
+  const int nd = kz_ndev();
+  KZ_CUDA(cudaStreamSynchronize(kz_ctx_of(0).stream));
+  const int dev0 = kz_device_of(0);
+  const size_t pt_words = 2 * P::N;
+  int rc = kz_parallel([&](int slot) -> int {
+    const size_t base = s.n / nd, rem = s.n % nd;
+    const size_t first = slot * base + ((size_t)slot < rem ? slot : rem), cnt = base + ((size_t)slot < rem ? 1 : 0);
+    SrsPart& sh = s.shard[slot];
+    int r = part_alloc<Cfg>(sh, first, cnt);
+    if (r) return r;
+    if (!cnt) return 0;
+    KzgpuCtx& cx = kz_ctx();
+    KZ_CUDA(cudaMemcpyPeerAsync(sh.d_points, kz_device_of(slot), s.full.d_points + first * pt_words, dev0, cnt * pt_words * 4, cx.stream));
+    if ((r = part_build_tables<Cfg>(sh))) return r;
+    KZ_CUDA(cudaStreamSynchronize(cx.stream));
+    return 0;
+  });
+  if (rc) return rc;
+  s.has_shards = true;
+  return 0;
+}
+
+// Replicas: the whole key with its window tables on every device (whole polynomials of a batched commit run where they
+// are placed): one peer copy of the primary's tables per device.
+template <class Cfg>
+int ensure_replicas(Srs& s) {
+  using P = typename Cfg::Fp;
+  if (s.has_replicas) return 0;
+  KZ_CUDA(cudaStreamSynchronize(kz_ctx_of(0).stream));
+  const int dev0 = kz_device_of(0);
+  const size_t bytes = s.n * 2 * P::N * 4 * s.full.W_tab;
+  s.replica[0] = s.full;
+  int rc = kz_parallel([&](int slot) -> int {
+    if (slot == 0) return 0;
+    SrsPart& rp = s.replica[slot];
+    rp = s.full;
+    rp.slot = slot; rp.d_points = nullptr;
+    KZ_CUDA(cudaMalloc((void**)&rp.d_points, bytes ? bytes : 16));
+    KzgpuCtx& cx = kz_ctx();
+    KZ_CUDA(cudaMemcpyPeerAsync(rp.d_points, kz_device_of(slot), s.full.d_points, dev0, bytes, cx.stream));
+    KZ_CUDA(cudaStreamSynchronize(cx.stream));
+    return 0;
+  });
+  if (rc) return rc;
+  s.has_replicas = true;
+  return 0;
+}
+
+// One MSM over the index range [first, first + n) of the key, point-sharded over every device.  Scalars: host memory
+// (each device uploads its own slice, chunked and overlapped with its compute) or device memory of the primary device
+// (each peer pulls its slice over NVLink).  Every device leaves one XYZZ partial in the primary's gather buffer (peer
+// write); the primary folds them and the host normalises the one result.
+template <class Cfg>
+int msm_sharded(Srs& s, size_t first, size_t n, const uint64_t* h_scalars, const uint32_t* d0_scalars, uint64_t* out_xy, int* is_inf) {
+  using P = typename Cfg::Fp;
+  const int nd = kz_ndev();
+  int rc;
+  if ((rc = ensure_shards<Cfg>(s))) return rc;
+  const size_t xyzz_bytes = 4 * P::N * 4;
+  MsmWs& w0 = g_ws_slots.of(0);
+  if ((rc = w0.gather.ensure(nd * xyzz_bytes))) return rc;
+  if ((rc = w0.result.ensure((4 * P::N + 1) * 4 + 64))) return rc;
+  KzgpuCtx& cx0 = kz_ctx_of(0);
+  KZ_CUDA(cudaStreamSynchronize(cx0.stream));            // device-resident scalars may still be in flight on the primary's stream
+  const int dev0 = kz_device_of(0);
+  uint32_t* gather = (uint32_t*)w0.gather.p;
+  rc = kz_parallel([&](int slot) -> int {
+    const SrsPart& sh = s.shard[slot];
+    const size_t lo = first > sh.first ? first : sh.first;
+    const size_t hi_all = first + n, hi_sh = sh.first + sh.n;
+    const size_t hi = hi_all < hi_sh ? hi_all : hi_sh;
+    KzgpuCtx& cx = kz_ctx();
+    MsmWs& w = g_ws;
+    int r;
+    if ((r = set_smem_attrs())) return r;
+    if ((r = w.result.ensure(xyzz_bytes + 64))) return r;
+    uint32_t* d_part = (uint32_t*)w.result.p;
+    if (hi <= lo) {
+      KZ_CUDA(cudaMemsetAsync(d_part, 0, xyzz_bytes, cx.stream));          // ZZ = 0: the identity
+    } else {
+      const size_t cnt = hi - lo;
+      if ((r = w.scal.ensure(cnt * 32 + 32))) return r;
+      const uint32_t* d_sc = (const uint32_t*)w.scal.p;
+      const uint64_t* h_sc = nullptr;
+      if (h_scalars) h_sc = h_scalars + (lo - first) * 4;
+      else if (slot == 0) d_sc = d0_scalars + (lo - first) * 8;
+      else KZ_CUDA(cudaMemcpyPeerAsync(w.scal.p, kz_device_of(slot), d0_scalars + (lo - first) * 8, dev0, cnt * 32, cx.stream));
+      if ((r = msm_core<Cfg>(sh, lo - sh.first, d_sc, cnt, 0, d_part, h_sc))) return r;
+    }
+    KZ_CUDA(cudaMemcpyPeerAsync(gather + (size_t)slot * 4 * P::N, dev0, d_part, kz_device_of(slot), xyzz_bytes, cx.stream));
+    KZ_CUDA(cudaStreamSynchronize(cx.stream));
+    return 0;
+  });
+  if (rc) return rc;
+  g1_fold_kernel<Cfg><<<1, 128, 128 * 4 * P::N * 4, cx0.stream>>>(gather, (uint32_t)nd, (uint32_t*)w0.result.p);
+  KZ_LAUNCHED();
+  uint32_t h[2 * 12 + 1];
+  KZ_CUDA(cudaMemcpyAsync(h, w0.result.p, (2 * P::N + 1) * 4, cudaMemcpyDeviceToHost, cx0.stream));
+  KZ_CUDA(cudaStreamSynchronize(cx0.stream));
+  memcpy(out_xy, h, 2 * P::N * 4);
+  if (is_inf) *is_inf = (int)h[2 * P::N];
+  return 0;
+}
+
+// can the k polynomials share one pass?  (bucket sets and digit entries must fit the sort's key and index ranges)
+bool batch_fits(const SrsPart& s, int curve, size_t poly_len, size_t k) {
+  if (k < 2 || k > 64 || poly_len == 0) return false;
+  const int bits = curve == KZGPU_BN254 ? FrBN254::BITS : FrBLS381::BITS;
+  const uint32_t c = s.c_tab ? s.c_tab : choose_c(poly_len, bits);
+  const uint32_t W = (bits + 1 + c - 1) / c;
+  const size_t nb = (size_t)(s.c_tab ? 1u : W) * k << (c - 1);
+  return nb <= ((size_t)kMaxCoarse << 13) && (size_t)poly_len * k * W < 0xffffffffull && poly_len * k < 0x7fffffffull;
+}
+
+// k polynomials of poly_len scalars each, back to back on the calling thread's device, against that device's copy of the key
+int msm_batch_on_part(const SrsPart& part, int curve, const uint32_t* d_scalars, size_t poly_len, size_t k, uint64_t* out_xy, int* is_inf) {
+  const int L = kzgpu_fp_limbs64(curve);
+  int rc = set_smem_attrs();
+  if (rc) return rc;
+  if (!batch_fits(part, curve, poly_len, k)) {                 // one pass per polynomial
+    for (size_t j = 0; j < k; j++) {
+      int* fl = is_inf ? is_inf + j : nullptr;
+      rc = curve == KZGPU_BN254 ? msm_affine<BN254Cfg>(part, 0, d_scalars + j * poly_len * 8, poly_len, out_xy + j * 2 * L, fl)
+                                : msm_affine<BLS381Cfg>(part, 0, d_scalars + j * poly_len * 8, poly_len, out_xy + j * 2 * L, fl);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  if (curve == KZGPU_BN254) return msm_affine_batch<BN254Cfg>(part, d_scalars, poly_len, k, out_xy, is_inf);
+  return msm_affine_batch<BLS381Cfg>(part, d_scalars, poly_len, k, out_xy, is_inf);
+}
+
+// `count` host polynomials (ptrs / lens) of one commit() call on the calling thread's device: uploaded zero padded to a
+// common length and committed in one pass (zero scalars emit no digits); results to outs[j] / infs[j]
+int msm_batch_host_on_part(const SrsPart& part, int curve, const uint64_t* const* ptrs, const size_t* lens, size_t count,
+                           uint64_t* const* outs, int* const* infs) {
+  if (!count) return 0;
+  KzgpuCtx& cx = kz_ctx();
+  const int L = kzgpu_fp_limbs64(curve);
+  size_t maxlen = 0, total = 0;
+  for (size_t j = 0; j < count; j++) { total += lens[j]; if (lens[j] > maxlen) maxlen = lens[j]; }
+  int rc = g_ws.scal.ensure(count * maxlen * 32 + 32);
+  if (rc) return rc;
+  uint32_t* d = (uint32_t*)g_ws.scal.p;
+  if (total != count * maxlen) KZ_CUDA(cudaMemsetAsync(d, 0, count * maxlen * 32, cx.stream));
+  for (size_t j = 0; j < count; j++)
+    if (lens[j]) KZ_CUDA(cudaMemcpyAsync(d + j * maxlen * 8, ptrs[j], lens[j] * 32, cudaMemcpyHostToDevice, cx.stream));
+  std::vector<uint64_t> out(count * 2 * L);
+  std::vector<int> inf(count);
+  if ((rc = set_smem_attrs())) return rc;
+  if (maxlen == 0 || count == 1) {
+    for (size_t j = 0; j < count; j++) {
+      rc = curve == KZGPU_BN254 ? msm_affine<BN254Cfg>(part, 0, d + j * maxlen * 8, maxlen, &out[j * 2 * L], &inf[j])
+                                : msm_affine<BLS381Cfg>(part, 0, d + j * maxlen * 8, maxlen, &out[j * 2 * L], &inf[j]);
+      if (rc) return rc;
+    }
+  } else if ((rc = msm_batch_on_part(part, curve, d, maxlen, count, out.data(), inf.data()))) {
+    return rc;
+  }
+  for (size_t j = 0; j < count; j++) {
+    memcpy(outs[j], &out[j * 2 * L], 2 * L * 8);
+    if (infs[j]) *infs[j] = inf[j];
+  }
   return 0;
 }
 
@@ -1310,10 +1458,14 @@ int upload_scalars(const uint64_t* scalars, size_t n, uint32_t** d) {
 
 }  // namespace
 
+// every slot releases its own workspaces (called on the slot's own thread); slot 0 also frees the keys
 void kz_msm_release() {
-  for (auto& kv : g_srs) cudaFree(kv.second.d_points);
-  g_srs.clear();
-  KzScratch* all[] = {&g_ws.buckets, &g_ws.partials, &g_ws.winsums, &g_ws.result, &g_ws.flag, &g_ws.scal};
+  if (kz_slot() == 0) {
+    for (auto& kv : g_srs) srs_free(kv.second);
+    g_srs.clear();
+  }
+  MsmWs& ws = g_ws;
+  KzScratch* all[] = {&ws.buckets, &ws.partials, &ws.winsums, &ws.result, &ws.flag, &ws.scal, &ws.gather};
   for (auto* s : all) s->release();
   for (auto& w : g_sw) {
     KzScratch* per[] = {&w.counts, &w.offsets, &w.cursor, &w.entries, &w.blocksums, &w.ntasks, &w.task_off, &w.size_hist,
@@ -1322,17 +1474,22 @@ void kz_msm_release() {
   }
 }
 
-// used by poly.cu (open): MSM of device-resident scalars against a handle
+// used by poly.cu (open) and the MSM entry points: scalars on the primary device (or the host) against a handle.
+// With several devices an MSM of >= KZGPU_SHARD_MIN points is point-sharded over all of them.
 int kz_msm_dev_internal(uint64_t handle, size_t first, const uint32_t* d_scalars, size_t n, uint64_t* out_xy, int* is_inf,
                         const uint64_t* h_scalars) {
-  const Srs* s = find_srs(handle);
+  Srs* s = find_srs(handle);
   if (!s) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle %llu", (unsigned long long)handle);
   if (first + n > s->n)
     return kz_fail(KZGPU_ERANGE, "Polynomial degree %zu exceeds maximum allowed degree %zu", first + n - 1, s->n - 1);
   int rc = set_smem_attrs();
   if (rc) return rc;
-  if (s->curve == KZGPU_BN254) return msm_affine<BN254Cfg>(*s, first, d_scalars, n, out_xy, is_inf, h_scalars);
-  return msm_affine<BLS381Cfg>(*s, first, d_scalars, n, out_xy, is_inf, h_scalars);
+  if (kz_ndev() > 1 && n >= shard_min()) {
+    if (s->curve == KZGPU_BN254) return msm_sharded<BN254Cfg>(*s, first, n, h_scalars, d_scalars, out_xy, is_inf);
+    return msm_sharded<BLS381Cfg>(*s, first, n, h_scalars, d_scalars, out_xy, is_inf);
+  }
+  if (s->curve == KZGPU_BN254) return msm_affine<BN254Cfg>(s->full, first, d_scalars, n, out_xy, is_inf, h_scalars);
+  return msm_affine<BLS381Cfg>(s->full, first, d_scalars, n, out_xy, is_inf, h_scalars);
 }
 
 int kz_srs_curve(uint64_t handle) {
@@ -1366,7 +1523,7 @@ int kzgpu_srs_destroy(uint64_t handle) {
   KZ_REQUIRE_INIT();
   auto it = g_srs.find(handle);
   if (it == g_srs.end()) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle %llu", (unsigned long long)handle);
-  cudaFree(it->second.d_points);
+  srs_free(it->second);
   g_srs.erase(it);
   return 0;
 }
@@ -1383,9 +1540,9 @@ int kzgpu_srs_info(uint64_t handle, int* c_tab, int* w_tab, size_t* device_bytes
   KZ_REQUIRE_INIT();
   const Srs* s = find_srs(handle);
   if (!s) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle");
-  if (c_tab) *c_tab = (int)s->c_tab;
-  if (w_tab) *w_tab = (int)s->W_tab;
-  if (device_bytes) *device_bytes = s->n * (s->curve == KZGPU_BN254 ? 64 : 96) * s->W_tab;
+  if (c_tab) *c_tab = (int)s->full.c_tab;
+  if (w_tab) *w_tab = (int)s->full.W_tab;
+  if (device_bytes) *device_bytes = s->n * (s->curve == KZGPU_BN254 ? 64 : 96) * s->full.W_tab;
   return 0;
 }
 
@@ -1401,9 +1558,9 @@ int kzgpu_srs_read(uint64_t handle, size_t first, size_t count, uint64_t* affine
   uint32_t* tmp = nullptr;
   KZ_CUDA(cudaMalloc((void**)&tmp, bytes));
   if (s->curve == KZGPU_BN254)
-    srs_from_mont_kernel<BN254Cfg><<<(unsigned)kz_div_up(2 * count, 128), 128, 0, cx.stream>>>(s->d_points, first, count, tmp);
+    srs_from_mont_kernel<BN254Cfg><<<(unsigned)kz_div_up(2 * count, 128), 128, 0, cx.stream>>>(s->full.d_points, first, count, tmp);
   else
-    srs_from_mont_kernel<BLS381Cfg><<<(unsigned)kz_div_up(2 * count, 128), 128, 0, cx.stream>>>(s->d_points, first, count, tmp);
+    srs_from_mont_kernel<BLS381Cfg><<<(unsigned)kz_div_up(2 * count, 128), 128, 0, cx.stream>>>(s->full.d_points, first, count, tmp);
   KZ_LAUNCHED();
   KZ_CUDA(cudaMemcpyAsync(affine_xy, tmp, bytes, cudaMemcpyDeviceToHost, cx.stream));
   KZ_CUDA(cudaStreamSynchronize(cx.stream));
@@ -1420,20 +1577,14 @@ int kzgpu_msm_dev(uint64_t handle, size_t first, const uint64_t* d_scalars, size
 int kzgpu_msm(uint64_t handle, size_t first, const uint64_t* scalars, size_t n, uint64_t* out_affine_xy, int* is_inf) {
   KZ_REQUIRE_INIT();
   if (!out_affine_xy || (n && !scalars)) return kz_fail(KZGPU_EINVAL, "null pointer");
-  // the upload happens inside the MSM, chunked and overlapped with the compute
-  int rc = g_ws.scal.ensure(n * 32 + 32);
-  if (rc) return rc;
-  return kz_msm_dev_internal(handle, first, (const uint32_t*)g_ws.scal.p, n, out_affine_xy, is_inf, scalars);
-}
-
-// can the k polynomials share one pass?  (bucket sets and digit entries must fit the sort's key and index ranges)
-static bool batch_fits(const Srs& s, size_t poly_len, size_t k) {
-  if (k < 2 || k > 64 || poly_len == 0) return false;
-  const int bits = s.curve == KZGPU_BN254 ? FrBN254::BITS : FrBLS381::BITS;
-  const uint32_t c = s.c_tab ? s.c_tab : choose_c(poly_len, bits);
-  const uint32_t W = (bits + 1 + c - 1) / c;
-  const size_t nb = (size_t)(s.c_tab ? 1u : W) * k << (c - 1);
-  return nb <= ((size_t)kMaxCoarse << 13) && (size_t)poly_len * k * W < 0xffffffffull && poly_len * k < 0x7fffffffull;
+  // the upload happens inside the MSM, chunked and overlapped with the compute (per device when the MSM is sharded)
+  const uint32_t* d = nullptr;
+  if (!(kz_ndev() > 1 && n >= shard_min())) {
+    int rc = g_ws.scal.ensure(n * 32 + 32);
+    if (rc) return rc;
+    d = (const uint32_t*)g_ws.scal.p;
+  }
+  return kz_msm_dev_internal(handle, first, d, n, out_affine_xy, is_inf, scalars);
 }
 
 int kz_msm_batch_dev_internal(uint64_t handle, const uint32_t* d_scalars, size_t poly_len, size_t k, uint64_t* out_xy, int* is_inf) {
@@ -1441,18 +1592,7 @@ int kz_msm_batch_dev_internal(uint64_t handle, const uint32_t* d_scalars, size_t
   if (!s) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle %llu", (unsigned long long)handle);
   if (poly_len > s->n)
     return kz_fail(KZGPU_ERANGE, "Polynomial degree %zu exceeds maximum allowed degree %zu", poly_len - 1, s->n - 1);
-  const int L = kzgpu_fp_limbs64(s->curve);
-  int rc = set_smem_attrs();
-  if (rc) return rc;
-  if (!batch_fits(*s, poly_len, k)) {                 // one pass per polynomial
-    for (size_t j = 0; j < k; j++) {
-      rc = kz_msm_dev_internal(handle, 0, d_scalars + j * poly_len * 8, poly_len, out_xy + j * 2 * L, is_inf ? is_inf + j : nullptr, nullptr);
-      if (rc) return rc;
-    }
-    return 0;
-  }
-  if (s->curve == KZGPU_BN254) return msm_affine_batch<BN254Cfg>(*s, d_scalars, poly_len, k, out_xy, is_inf);
-  return msm_affine_batch<BLS381Cfg>(*s, d_scalars, poly_len, k, out_xy, is_inf);
+  return msm_batch_on_part(s->full, s->curve, d_scalars, poly_len, k, out_xy, is_inf);
 }
 
 int kzgpu_msm_batch_dev(uint64_t handle, const uint64_t* d_scalars, size_t poly_len, size_t k, uint64_t* out_affine_xy, int* is_inf) {
@@ -1462,36 +1602,71 @@ int kzgpu_msm_batch_dev(uint64_t handle, const uint64_t* d_scalars, size_t poly_
   return kz_msm_batch_dev_internal(handle, (const uint32_t*)d_scalars, poly_len, k, out_affine_xy, is_inf);
 }
 
+// One commit() call (kzg.py:102): k host polynomials, concatenated.  One device: a single pass over all of them.  Several
+// devices: polynomials of >= KZGPU_SHARD_MIN coefficients are point-sharded over every device, the others are placed
+// whole, longest first, on the least loaded device (longest-processing-time rule; each device commits its share in one
+// pass against its replica of the key).
 int kzgpu_msm_batch(uint64_t handle, const uint64_t* scalars, const size_t* lens, size_t k, uint64_t* out_affine_xy, int* is_inf) {
   KZ_REQUIRE_INIT();
   if (k && (!lens || !out_affine_xy)) return kz_fail(KZGPU_EINVAL, "null pointer");
-  const Srs* s = find_srs(handle);
+  Srs* s = find_srs(handle);
   if (!s) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle %llu", (unsigned long long)handle);
   if (!k) return 0;
-  size_t maxlen = 0, total = 0;
-  for (size_t j = 0; j < k; j++) { total += lens[j]; if (lens[j] > maxlen) maxlen = lens[j]; }
+  size_t maxlen = 0;
+  for (size_t j = 0; j < k; j++) if (lens[j] > maxlen) maxlen = lens[j];
   if (maxlen > s->n)                                   // the degree check of kzg.py:103-106, before any work
     return kz_fail(KZGPU_ERANGE, "Polynomial degree %zu exceeds maximum allowed degree %zu", maxlen - 1, s->n - 1);
-  // the k polynomials of one commit() call, zero padded to a common length, share one pass (zero scalars emit no digits)
-  KzgpuCtx& cx = kz_ctx();
-  int rc = g_ws.scal.ensure(k * maxlen * 32 + 32);
-  if (rc) return rc;
-  uint32_t* d = (uint32_t*)g_ws.scal.p;
-  if (total != k * maxlen) KZ_CUDA(cudaMemsetAsync(d, 0, k * maxlen * 32, cx.stream));
+  const int L = kzgpu_fp_limbs64(s->curve);
+  std::vector<const uint64_t*> ptr(k);
+  std::vector<uint64_t*> outp(k);
+  std::vector<int*> infp(k);
   size_t off = 0;
   for (size_t j = 0; j < k; j++) {
-    if (lens[j]) KZ_CUDA(cudaMemcpyAsync(d + j * maxlen * 8, scalars + off * 4, lens[j] * 32, cudaMemcpyHostToDevice, cx.stream));
-    off += lens[j];
+    ptr[j] = scalars + off * 4; off += lens[j];
+    outp[j] = out_affine_xy + j * 2 * L; infp[j] = is_inf ? is_inf + j : nullptr;
   }
-  if (maxlen == 0 || k == 1) {
-    const int L = kzgpu_fp_limbs64(s->curve);
-    for (size_t j = 0; j < k; j++) {
-      rc = kz_msm_dev_internal(handle, 0, d + j * maxlen * 8, maxlen, out_affine_xy + j * 2 * L, is_inf ? is_inf + j : nullptr, nullptr);
+  const int nd = kz_ndev();
+  if (nd == 1 || (k == 1 && lens[0] < shard_min())) return msm_batch_host_on_part(s->full, s->curve, ptr.data(), lens, k, outp.data(), infp.data());
+  // several devices
+  std::vector<size_t> order, owner(k, 0);
+  int rc;
+  for (size_t j = 0; j < k; j++) {
+    if (lens[j] >= shard_min()) {
+      rc = s->curve == KZGPU_BN254 ? msm_sharded<BN254Cfg>(*s, 0, lens[j], ptr[j], nullptr, outp[j], infp[j])
+                                   : msm_sharded<BLS381Cfg>(*s, 0, lens[j], ptr[j], nullptr, outp[j], infp[j]);
       if (rc) return rc;
+    } else {
+      order.push_back(j);
     }
-    return 0;
   }
-  return kz_msm_batch_dev_internal(handle, d, maxlen, k, out_affine_xy, is_inf);
+  if (order.empty()) return 0;
+  std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return lens[a] != lens[b] ? lens[a] > lens[b] : a < b; });
+  size_t load[KZ_MAX_DEV] = {0};
+  std::vector<std::vector<size_t>> mine(nd);
+  for (size_t j : order) {
+    int best = 0;
+    for (int d = 1; d < nd; d++) if (load[d] < load[best]) best = d;
+    load[best] += lens[j] + 4096;                      // + a fixed cost per polynomial
+    mine[best].push_back(j);
+  }
+  bool others = false;
+  for (int d = 1; d < nd; d++) others = others || !mine[d].empty();
+  if (others) {
+    rc = s->curve == KZGPU_BN254 ? ensure_replicas<BN254Cfg>(*s) : ensure_replicas<BLS381Cfg>(*s);
+    if (rc) return rc;
+  } else {
+    s->replica[0] = s->full;
+  }
+  return kz_parallel([&](int slot) -> int {
+    const std::vector<size_t>& js = mine[slot];
+    if (js.empty()) return 0;
+    std::vector<const uint64_t*> p;
+    std::vector<size_t> ln;
+    std::vector<uint64_t*> o;
+    std::vector<int*> f;
+    for (size_t j : js) { p.push_back(ptr[j]); ln.push_back(lens[j]); o.push_back(outp[j]); f.push_back(infp[j]); }
+    return msm_batch_host_on_part(slot == 0 ? s->full : s->replica[slot], s->curve, p.data(), ln.data(), js.size(), o.data(), f.data());
+  });
 }
 
 int kzgpu_msm_partial_dev(uint64_t handle, size_t first, const uint64_t* d_scalars, size_t n, uint64_t* d_out_xyzz) {
@@ -1502,8 +1677,8 @@ int kzgpu_msm_partial_dev(uint64_t handle, size_t first, const uint64_t* d_scala
   if (!d_out_xyzz || (n && !d_scalars)) return kz_fail(KZGPU_EINVAL, "null pointer");
   int rc = set_smem_attrs();
   if (rc) return rc;
-  if (s->curve == KZGPU_BN254) return msm_core<BN254Cfg>(*s, first, (const uint32_t*)d_scalars, n, 0, (uint32_t*)d_out_xyzz);
-  return msm_core<BLS381Cfg>(*s, first, (const uint32_t*)d_scalars, n, 0, (uint32_t*)d_out_xyzz);
+  if (s->curve == KZGPU_BN254) return msm_core<BN254Cfg>(s->full, first, (const uint32_t*)d_scalars, n, 0, (uint32_t*)d_out_xyzz);
+  return msm_core<BLS381Cfg>(s->full, first, (const uint32_t*)d_scalars, n, 0, (uint32_t*)d_out_xyzz);
 }
 
 int kzgpu_msm_partial(uint64_t handle, size_t first, const uint64_t* scalars, size_t n, uint64_t* d_out_xyzz) {
@@ -1517,8 +1692,8 @@ int kzgpu_msm_partial(uint64_t handle, size_t first, const uint64_t* scalars, si
   // host scalars of this rank's shard: uploaded inside the MSM, chunked and overlapped with the compute like kzgpu_msm
   if ((rc = g_ws.scal.ensure(n * 32 + 32))) return rc;
   const uint32_t* d = (const uint32_t*)g_ws.scal.p;
-  if (s->curve == KZGPU_BN254) return msm_core<BN254Cfg>(*s, first, d, n, 0, (uint32_t*)d_out_xyzz, scalars);
-  return msm_core<BLS381Cfg>(*s, first, d, n, 0, (uint32_t*)d_out_xyzz, scalars);
+  if (s->curve == KZGPU_BN254) return msm_core<BN254Cfg>(s->full, first, d, n, 0, (uint32_t*)d_out_xyzz, scalars);
+  return msm_core<BLS381Cfg>(s->full, first, d, n, 0, (uint32_t*)d_out_xyzz, scalars);
 }
 
 int kzgpu_g1_fold(int curve, const uint64_t* d_xyzz, size_t count, uint64_t* out_affine_xy, int* is_inf) {

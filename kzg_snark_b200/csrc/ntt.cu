@@ -502,9 +502,12 @@ struct NttPlan {
   }
 };
 
-std::list<NttPlan> g_plans;                 // most recently used first
+KzPerSlot<std::list<NttPlan>> g_plans_slots;                 // per device; most recently used first
+#define g_plans (g_plans_slots.get())
 constexpr size_t kMaxPlans = 8;
-KzScratch g_ntt_scratch[2];
+struct NttScratchPair { KzScratch s[2]; };
+KzPerSlot<NttScratchPair> g_ntt_scratch_slots;
+#define g_ntt_scratch (g_ntt_scratch_slots.get().s)
 
 template <class P> Fe<P> host_pow(Fe<P> base, uint64_t e) {
   Fe<P> r = fe_one<P>();
@@ -612,7 +615,8 @@ int run_plan(const NttPlan& pl, uint32_t* d_data, size_t batch, const NttHostIo*
   if (m >= 3 && (rc = g_ntt_scratch[1].ensure(bytes))) return rc;
   NttConsts<P> c;
   memcpy(c.w8.v, pl.consts, 32); memcpy(c.w4.v, pl.consts + 8, 32); memcpy(c.w8_3.v, pl.consts + 16, 32);
-  static bool attr_set = false;
+  static bool attr_set_slot[KZ_MAX_DEV] = {false};       // function attributes are per device
+  bool& attr_set = attr_set_slot[kz_slot()];
   if (!attr_set) {
     KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<FrBN254>, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 * 4 << kLogTile) + (32 << kMaxB)));
     KZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<FrBLS381>, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 * 4 << kLogTile) + (32 << kMaxB)));
@@ -642,7 +646,8 @@ int run_plan(const NttPlan& pl, uint32_t* d_data, size_t batch, const NttHostIo*
     const bool slab_in = io && m >= 2 && i == 0, slab_out = io && m >= 2 && i == m - 1 && pp.logK == pp.logQ;
     if (slab_in || slab_out) {
       // [R][Q] matrix, slab = tiles/kSlabs column tiles = (Q / kSlabs) columns of every row
-      static cudaEvent_t done_ev[kSlabs] = {nullptr};
+      static cudaEvent_t done_ev_slot[KZ_MAX_DEV][kSlabs] = {{nullptr}};
+      cudaEvent_t* done_ev = done_ev_slot[kz_slot()];
       if (!done_ev[0]) for (uint32_t k = 0; k < kSlabs; k++) KZ_CUDA(cudaEventCreateWithFlags(&done_ev[k], cudaEventDisableTiming));
       const size_t R = 1ull << pp.b, Q = 1ull << pp.logQ, pitch = Q * 32, width = pitch / kSlabs;
       if (slab_in)
@@ -729,7 +734,8 @@ int ntt_dispatch(int field, uint32_t* d_data, size_t n, size_t batch, const uint
   return kz_fail(KZGPU_EINVAL, "unknown field id %d", field);
 }
 
-KzScratch g_ntt_io;
+KzPerSlot<KzScratch> g_ntt_io_slots;
+#define g_ntt_io (g_ntt_io_slots.get())
 
 }  // namespace
 
@@ -752,11 +758,13 @@ int kzgpu_ntt_dev(int field, uint64_t* d_data, size_t n, const uint64_t* w, int 
   return kzgpu_ntt_batch_dev(field, d_data, n, 1, w, inverse, coset_shift);
 }
 
-int kzgpu_ntt_batch(int field, uint64_t* data, size_t n, size_t batch, const uint64_t* w, int inverse,
-                    const uint64_t* coset_shift) {
-  KZ_REQUIRE_INIT();
-  if (!data || !w) return kz_fail(KZGPU_EINVAL, "null pointer");
-  if (n == 0 || (n & (n - 1))) return kz_fail(KZGPU_EINVAL, "NTT length %zu is not a power of two (fft_ff.py:74)", n);
+// `batch` host vectors on the calling thread's device.
+//  * one long vector: transfers pipelined with the first and last pass, slab by slab (run_plan);
+//  * several long vectors: a per-vector pipeline over three streams -- vector k+1 uploads (copy stream) while vector k is
+//    transformed (main stream) and vector k-1 downloads (download stream), so the PCIe link runs full duplex;
+//  * otherwise one upload, one batched transform, one download.
+static int ntt_batch_host_on_slot(int field, uint64_t* data, size_t n, size_t batch, const uint64_t* w, int inverse,
+                                  const uint64_t* coset_shift) {
   KzgpuCtx& cx = kz_ctx();
   size_t bytes = n * batch * 32;
   if (bytes == 0) return 0;
@@ -767,12 +775,50 @@ int kzgpu_ntt_batch(int field, uint64_t* data, size_t n, size_t batch, const uin
     NttHostIo io{data, data};
     return ntt_dispatch(field, (uint32_t*)g_ntt_io.p, n, 1, w, inverse, coset_shift, &io);
   }
+  if (batch > 1 && n >= (1u << 18) && !getenv("KZGPU_NTT_NO_OVERLAP")) {
+    static cudaEvent_t ev_slot[KZ_MAX_DEV][2][4] = {{{nullptr}}};          // [slot][up | done][vector & 3]
+    cudaEvent_t (*ev)[4] = ev_slot[kz_slot()];
+    if (!ev[0][0]) for (int a = 0; a < 2; a++) for (int k = 0; k < 4; k++) KZ_CUDA(cudaEventCreateWithFlags(&ev[a][k], cudaEventDisableTiming));
+    KZ_CUDA(cudaEventRecord(cx.start_ev, cx.stream));                      // everything queued so far precedes the first upload
+    KZ_CUDA(cudaStreamWaitEvent(cx.copy_stream, cx.start_ev, 0));
+    const size_t vbytes = n * 32;
+    for (size_t v = 0; v < batch; v++) {
+      char* d = (char*)g_ntt_io.p + v * vbytes;
+      KZ_CUDA(cudaMemcpyAsync(d, (const char*)data + v * vbytes, vbytes, cudaMemcpyHostToDevice, cx.copy_stream));
+      KZ_CUDA(cudaEventRecord(ev[0][v & 3], cx.copy_stream));
+      KZ_CUDA(cudaStreamWaitEvent(cx.stream, ev[0][v & 3], 0));
+      if ((rc = ntt_dispatch(field, (uint32_t*)d, n, 1, w, inverse, coset_shift))) return rc;
+      KZ_CUDA(cudaEventRecord(ev[1][v & 3], cx.stream));
+      KZ_CUDA(cudaStreamWaitEvent(cx.d2h_stream, ev[1][v & 3], 0));
+      KZ_CUDA(cudaMemcpyAsync((char*)data + v * vbytes, d, vbytes, cudaMemcpyDeviceToHost, cx.d2h_stream));
+      if (v >= 3) KZ_CUDA(cudaEventSynchronize(ev[1][(v - 3) & 3]));        // an event slot is re-recorded only once its waiters are past it
+    }
+    KZ_CUDA(cudaStreamSynchronize(cx.d2h_stream));
+    KZ_CUDA(cudaStreamSynchronize(cx.stream));
+    return 0;
+  }
   KZ_CUDA(cudaMemcpyAsync(g_ntt_io.p, data, bytes, cudaMemcpyHostToDevice, cx.stream));
   rc = ntt_dispatch(field, (uint32_t*)g_ntt_io.p, n, batch, w, inverse, coset_shift);
   if (rc) return rc;
   KZ_CUDA(cudaMemcpyAsync(data, g_ntt_io.p, bytes, cudaMemcpyDeviceToHost, cx.stream));
   KZ_CUDA(cudaStreamSynchronize(cx.stream));
   return 0;
+}
+
+// Several devices (kzgpu_init_multi): whole vectors per device -- vector v of the batch runs on device v * ndev / batch
+// (contiguous blocks), each device running the single-device path above on its block; no exchange.
+int kzgpu_ntt_batch(int field, uint64_t* data, size_t n, size_t batch, const uint64_t* w, int inverse,
+                    const uint64_t* coset_shift) {
+  KZ_REQUIRE_INIT();
+  if (!data || !w) return kz_fail(KZGPU_EINVAL, "null pointer");
+  if (n == 0 || (n & (n - 1))) return kz_fail(KZGPU_EINVAL, "NTT length %zu is not a power of two (fft_ff.py:74)", n);
+  const int nd = kz_ndev();
+  if (nd == 1 || batch < 2 || n * batch < (1u << 16)) return ntt_batch_host_on_slot(field, data, n, batch, w, inverse, coset_shift);
+  return kz_parallel([&](int slot) -> int {
+    const size_t lo = batch * slot / nd, hi = batch * (slot + 1) / nd;
+    if (hi <= lo) return 0;
+    return ntt_batch_host_on_slot(field, data + lo * n * 4, n, hi - lo, w, inverse, coset_shift);
+  });
 }
 
 int kzgpu_ntt(int field, uint64_t* data, size_t n, const uint64_t* w, int inverse, const uint64_t* coset_shift) {

@@ -374,6 +374,7 @@ int marlin_impl(bool is_t, size_t n, size_t m, const uint32_t* d_row_or_index, c
 }  // namespace
 
 void kz_plonk_release() {
+  if (kz_slot() != 0) return;          // polynomial / prover kernels run on the primary device only
   KzScratch* all[] = {&g_ws.num, &g_ws.den, &g_ws.pre, &g_ws.levels, &g_ws.flag, &g_ws.ptrs};
   for (auto* s : all) s->release();
 }

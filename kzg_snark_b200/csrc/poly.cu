@@ -273,6 +273,7 @@ int powers_impl(uint32_t* d_out, size_t n, const uint64_t* base, const uint64_t*
 }  // namespace
 
 void kz_poly_release() {
+  if (kz_slot() != 0) return;          // polynomial / prover kernels run on the primary device only
   KzScratch* all[] = {&g_pw.polys, &g_pw.meta, &g_pw.comb, &g_pw.levels, &g_pw.t};
   for (auto* s : all) s->release();
 }

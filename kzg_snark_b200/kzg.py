@@ -146,8 +146,11 @@ class KZG:
 
     def _device_srs(self, ck):
         srs = getattr(ck, "srs", None)
-        if srs is not None and srs.handle and srs.curve == self._cid and ck._snapshot == ck:
-            return srs
+        if srs is not None and srs.handle and srs.curve == self._cid:
+            if ck._snapshot == ck:
+                return srs
+            srs.destroy()                                 # edited in place since setup(): falls through to a fresh upload
+            ck.srs = None
         key = (id(ck), self._cid)
         hit = _SRS_CACHE.get(key)
         if hit is not None and hit[1].handle and hit[0] == ck:

@@ -16,12 +16,17 @@ Semantics follow Sage where the reference relies on them:
 
 import random as _random
 
-_rng = _random.Random()
+# GF(q).random_element() draws the KZG trapdoor (kzg.py:67), the batching challenge of batch_check (kzg.py:236) and the
+# provers' blinding scalars: by default it is backed by the operating system's CSPRNG.  seed() switches to a seeded
+# Mersenne Twister for reproducible tests and golden-trace generation only (Sage's set_random_seed).
+_rng = _random.SystemRandom()
 
 
 def seed(s):
-    """Re-seed the generator behind GF(q).random_element() (set_random_seed in Sage)."""
-    _rng.seed(s)
+    """Make GF(q).random_element() deterministic (tests / fixture generation): seeded Mersenne Twister from here on.
+    seed(None) returns to the system CSPRNG."""
+    global _rng
+    _rng = _random.SystemRandom() if s is None else _random.Random(s)
 
 
 class FieldElement:

@@ -1,0 +1,60 @@
+"""Worker for tests/test_gpu_multi.py (one library context per process): runs a fixed set of hot-path calls from a PLAIN
+python process -- no torch, no launcher -- and prints the results as JSON.  With KZGPU_DEVICES=all the library spreads
+the work over every visible GPU (kzgpu_init_multi); without it everything runs on one.  Both must print the same thing."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np                                              # noqa: E402
+from kzg_snark_b200 import _ffi, device                         # noqa: E402
+from kzg_snark_b200.limbs import random_scalars, ints_to_limbs  # noqa: E402
+
+R = device.FR[0]
+TAU = 0x1D2C3B4A5F6E7D8C9BA % R
+
+
+def hx(a):
+    return np.ascontiguousarray(a).tobytes().hex()
+
+
+def main():
+    scale = int(sys.argv[1]) if len(sys.argv) > 1 else 14       # log2 of the base polynomial length
+    _ffi.init()
+    out = {"ndev": _ffi.device_count()}
+    n = 1 << scale
+    # the 11 commitments of one Marlin proof (marlin/prover.py:106,142,176), scaled: lengths n .. 12 n
+    lens = [n + 2] * 4 + [n + 4, 2 * n + 1] + [n, n - 1, n + 2] + [2 * n - 1, 12 * n - 6]
+    srs = device.Srs.generate("bn254", TAU, 12 * n)
+    polys = [random_scalars(ln, R, seed=50 + j) for j, ln in enumerate(lens)]
+    pts, infs = device.msm_batch(srs, polys)                    # KZG.commit(ck, [p_1 .. p_11]) at the buffer level
+    out["commits"] = [hx(p) for p in pts]
+    out["infs"] = [bool(f) for f in infs]
+    # one long MSM from host scalars (point-sharded when several devices), also with an offset into the key
+    big = random_scalars(8 * n, R, seed=7)
+    o, f = device.msm(srs, big)
+    out["msm"] = hx(o)
+    o, f = device.msm(srs, big[: 5 * n + 3], first=n + 1)
+    out["msm_offset"] = hx(o)
+    # the same from device-resident scalars on the primary device (peers pull their slices)
+    d = _ffi.DeviceBuffer(big.nbytes).upload(big)
+    o, f = device.msm_dev(srs, d, 8 * n)
+    out["msm_dev"] = hx(o)
+    # batched open (kzg.py:122-159): quotient on the primary device, its MSM over all devices
+    z, xi = ints_to_limbs([0x1234567], R)[0], ints_to_limbs([0x7654321], R)[0]
+    o, f = device.open_proof(srs, [polys[10], polys[5], polys[0]], z, xi)
+    out["open"] = hx(o)
+    # batched NTTs: whole vectors per device
+    m = 1 << (scale + 1)
+    w = ints_to_limbs([pow(5, (R - 1) // m, R)], R)[0]
+    vecs = random_scalars(9 * m, R, seed=3)
+    y = device.ntt("bn254", vecs.copy(), w, batch=9)
+    out["ntt"] = hx(y[::997])
+    back = device.ntt("bn254", y.copy(), w, inverse=True, batch=9)
+    out["ntt_roundtrip"] = bool((back == vecs).all())
+    out["launches"] = _ffi.launch_count()
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

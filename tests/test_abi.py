@@ -42,6 +42,17 @@ def test_library_exports_every_declared_symbol(lib):
         assert hasattr(lib, f)
 
 
+def test_microbenchmarks_live_in_their_own_library(lib):
+    """Measurement tooling is not part of the product ABI: kzgpu_microbench is exported by libkzgpu_bench.so
+    (include/kzgpu_bench.h) and by nothing else."""
+    from kzg_snark_b200 import _ffi
+    assert os.path.exists(_ffi.BENCH_LIB_PATH)
+    nm = lambda p: set(re.findall(r"\sT\s+(kzgpu_\w+)", subprocess.run(["nm", "-D", "--defined-only", p], capture_output=True, text=True).stdout))   # noqa: E731
+    assert nm(_ffi.BENCH_LIB_PATH) == {"kzgpu_microbench"}
+    assert "kzgpu_microbench" not in nm(_ffi.LIB_PATH)
+    assert "kzgpu_microbench" in open(os.path.join(ROOT, "include", "kzgpu_bench.h")).read()
+
+
 def test_library_is_sm100a_only():
     from kzg_snark_b200 import _ffi
     out = subprocess.run(["cuobjdump", "-lelf", _ffi.LIB_PATH], capture_output=True, text=True).stdout

@@ -130,9 +130,26 @@ def test_commit_key_cache_and_plain_list_ck():
     a = kzg.commit(plain, [[1, 2, 3, 4]])[0]
     b = KZG("bn254").commit(plain, [[1, 2, 3, 4]])[0]      # a second KZG instance, same list -> cached SRS
     assert aff(cv, a) == aff(cv, b) == aff(cv, kzg.commit(ck, [[1, 2, 3, 4]])[0])
-    assert id(plain) in _SRS_CACHE
+    assert (id(plain), 0) in _SRS_CACHE
     exp = cv.normalize(cv.multiply(cv.G1, poly_eval([1, 2, 3, 4], 12345, cv.r)))
     assert aff(cv, a) == exp
+    # the reference reads ck[i] afresh on every call (kzg.py:115): a key edited in place must not reuse the stale device copy
+    handle = _SRS_CACHE[(id(plain), 0)][1].handle
+    plain[1] = plain[2]                                        # ck = [G, t^2 G, t^2 G, t^3 G, ...]
+    c = kzg.commit(plain, [[1, 2, 3, 4]])[0]
+    t = 12345
+    exp2 = cv.normalize(cv.multiply(cv.G1, (1 + 2 * t ** 2 + 3 * t ** 2 + 4 * t ** 3) % cv.r))
+    assert aff(cv, c) == exp2 != exp
+    assert _SRS_CACHE[(id(plain), 0)][1].handle != handle, "stale device key reused after an in-place edit"
+    ck[1] = ck[3]                                              # the same for a CommitmentKey returned by setup()
+    d = kzg.commit(ck, [[1, 2, 3, 4]])[0]
+    assert aff(cv, d) == cv.normalize(cv.multiply(cv.G1, (1 + 2 * t ** 3 + 3 * t ** 2 + 4 * t ** 3) % cv.r))
+    # cache eviction releases device keys nobody else holds, and never one that a live CommitmentKey still uses
+    keys = [list(kzg.setup(4, tau=100 + i)[0]) for i in range(10)]
+    for k in keys:
+        kzg.commit(k, [[1, 1]])
+    assert len(_SRS_CACHE) <= 8
+    assert aff(cv, kzg.commit(ck, [[5]])[0]) == cv.normalize(cv.multiply(cv.G1, 5))
 
 
 @pytest.mark.parametrize("logn", [20])
