@@ -60,6 +60,12 @@ MADD = (6, 2, 1)          # XYZZ mixed addition: 6 products + 2 squarings + 1 du
 FULL_ADD = (12, 2)        # XYZZ + XYZZ (canonical arithmetic, bucket reduction)
 
 
+def _timeit(f):
+    t0 = time.perf_counter()
+    f()
+    return time.perf_counter() - t0
+
+
 def load_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed `ncu --set full` captures
     (profiles/r2_traffic.json, else r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
@@ -569,7 +575,7 @@ def run_gpu(args):
         }
         if "ms_e2e_pageable" in r:
             res["e2e"]["pageable"] = {"value": total_pts * K / (r["ms_e2e_pageable"] * 1e-3), "ms_per_step": r["ms_e2e_pageable"] / K,
-                                      "host_buffers": "pageable numpy array (cudaMemcpyAsync stages through the driver's bounce buffer)"}
+                                      "host_buffers": "pageable numpy array (what the Python drop-in hands over): staged through page-locked double buffers by 4 host threads inside the call (kz_upload)"}
         if strong:
             # the independent-shards variant beside it: 2^logn points per GPU
             wr = msm_case(n_total, rank * n_total, seed=args.logn * 100 + 50 + rank, want_e2e=True, want_profile=False)
@@ -633,7 +639,7 @@ def run_gpu(args):
             for _ in range(K):
                 device.ntt(curve, heap, wl)
             msp = (time.perf_counter() - t0) * 1e3
-            e2e["pageable"] = {"value": n_total * K / (msp * 1e-3), "ms_per_step": msp / K, "host_buffers": "pageable numpy array"}
+            e2e["pageable"] = {"value": n_total * K / (msp * 1e-3), "ms_per_step": msp / K, "host_buffers": "pageable numpy array, staged both ways (kz_upload / kz_download)"}
             # batched host vectors: vector k's download overlaps vector k+1's upload (full duplex)
             nb, bl = 4, args.logn - 2
             wb = ints_to_limbs([pow(GEN[curve], (r_mod - 1) >> bl, r_mod)], r_mod)[0]
@@ -743,6 +749,40 @@ def run_gpu(args):
                                 "key": key, "srs_build_s": tb, "check": bool(ok)})
             d.free(); pin.free(); srs.destroy()
         return rows
+
+    # ------------------------------------------------------------------ the Python-object boundary (SURVEY.md section 7 hard part 3)
+    def bench_python_boundary(logn=18):
+        """What the reference's callers pay at the boundary they actually use: `KZG.commit(ck, [poly])` and `fft_ff(list, w, F)`
+        with Python objects in and out (kzg.py:110,115 `poly.list()` / `int(coeff)`; fft_ff.py:3), next to the same work
+        through the C ABI with a limb array, and the marshalling alone."""
+        from kzg_snark_b200.kzg import KZG
+        from kzg_snark_b200 import fft_ff as gff
+        n = 1 << logn
+        kzg = KZG("bn254")
+        t0 = time.perf_counter()
+        ck, _ = kzg.setup(n - 1, tau=TAU)                      # device SRS + the Python list of n points the reference API returns
+        t_setup = time.perf_counter() - t0
+        F = kzg.Fq
+        vals = limbs_to_ints(random_scalars(n, R_BN254, seed=logn))
+        poly = kzg.R([F(v) for v in vals])
+        best = lambda f, reps=3: min(_timeit(f) for _ in range(reps))            # noqa: E731
+        t_marshal = best(lambda: kzg._coeff_limbs(poly))
+        limbs = kzg._coeff_limbs(poly)
+        device.msm(ck.srs, limbs)
+        t_cabi = best(lambda: device.msm(ck.srs, limbs))
+        kzg.commit(ck, [poly])
+        t_commit = best(lambda: kzg.commit(ck, [poly]))
+        w = F(pow(5, (R_BN254 - 1) // n, R_BN254))
+        xs = [F(v) for v in vals]
+        gff.fft_ff(xs, w, F)
+        t_fft = best(lambda: gff.fft_ff(xs, w, F))
+        arr = ints_to_limbs(vals, R_BN254)
+        wl = ints_to_limbs([int(w)], R_BN254)[0]
+        t_fft_cabi = best(lambda: device.ntt("bn254", arr, wl))
+        return {"coefficients": n, "setup_s": t_setup, "commit_python_objects_s": t_commit, "commit_marshalling_s": t_marshal,
+                "commit_c_abi_s": t_cabi, "fft_ff_python_objects_s": t_fft, "fft_c_abi_s": t_fft_cabi,
+                "note": "python objects = shim polynomial / list of field elements in, py_ecc-shaped point / list of elements out; "
+                        "c_abi = the same call with a (n, 4) uint64 limb array (pageable numpy memory), PCIe included"}
 
     # ------------------------------------------------------------------ PLONK prove (configs[3])
     def bench_plonk():
@@ -1011,6 +1051,7 @@ def run_gpu(args):
     plonk = None
     if world == 1 and curve == "bn254" and (args.workload == "plonk" or not args.no_secondary):
         plonk = bench_plonk()
+        plonk["python_boundary"] = bench_python_boundary()
     if args.workload == "plonk":
         if rank == 0:
             emit({"metric": "plonk_prove_s", "value": plonk["synthetic"]["prove_s"], "unit": "s", "n_gpus": 1,
@@ -1092,13 +1133,107 @@ def run_gpu(args):
     return finish()
 
 
+def run_inproc(args):
+    """Multi-GPU INSIDE the library (kzgpu_init_multi): one plain python process, no torch, no launcher.
+    One step = one 2^logn-point MSM through `kzgpu_msm` with pinned host scalars (the product entry point); beside it the same
+    MSM from scalars resident on the primary device (peers pull their slices over NVLink), one batched commit of the 11
+    Marlin-sized polynomials (placed longest-first / point-sharded) and one batched NTT of 8 host vectors."""
+    import numpy as np
+    from kzg_snark_b200 import _ffi, device
+    from kzg_snark_b200.limbs import random_scalars, ints_to_limbs
+    curve, r_mod = args.curve, FR[args.curve]
+    K, Wm = args.steps, args.warmup
+    n = 1 << args.logn
+    _ffi.init_multi(None if args.devices <= 0 else list(range(args.devices)))
+    nd = _ffi.device_count()
+    info = _ffi.device_info()
+    t0 = time.perf_counter()
+    srs = device.Srs.generate(curve, TAU, n)
+    _ffi.check(_ffi._lib.kzgpu_sync())
+    build_s = time.perf_counter() - t0
+    pinned = _ffi.PinnedArray((n, 4))
+    pinned.array[:] = random_scalars(n, r_mod, seed=args.logn * 100)
+    dsc = _ffi.DeviceBuffer(n * 32).upload(pinned.array)
+    t0 = time.perf_counter()
+    out, inf = device.msm(srs, pinned.array)                        # first call: builds the per-device shards (peer copy + tables)
+    first_s = time.perf_counter() - t0
+    ok = tau_identity(curve, out, inf, horner_dev(curve, dsc, n, TAU % r_mod))
+
+    def timed(fn, reps):
+        for _ in range(Wm):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) * 1e3 / reps
+
+    sampler = ClockSampler(0)
+    l0 = _ffi.launch_count()
+    ms_host = timed(lambda: device.msm(srs, pinned.array), K)
+    launches = (_ffi.launch_count() - l0) // (K + Wm)
+    ms_dev = timed(lambda: device.msm_dev(srs, dsc, n), K)
+    # batched commit of Marlin-sized polynomials (marlin/prover.py:106,142,176 at 2^20 constraints, scaled to the key)
+    b = n // 16
+    lens = [b + 2] * 4 + [b + 4, 2 * b + 1] + [b, b - 1, b + 2] + [2 * b - 1, 12 * b - 6]
+    polys = [random_scalars(ln, r_mod, seed=60 + j) for j, ln in enumerate(lens)]
+    ms_batch = timed(lambda: device.msm_batch(srs, polys), max(2, K // 2))
+    # 8 host vectors of 2^(logn-3) elements each through kzgpu_ntt_batch
+    m = n // 8
+    wl = ints_to_limbs([pow(GEN[curve], (r_mod - 1) // m, r_mod)], r_mod)[0]
+    vecs = pinned.array.reshape(8 * m, 4)
+    ms_ntt = timed(lambda: device.ntt(curve, vecs, wl, batch=8), max(2, K // 2))
+    # configs[4]: the device Marlin prover on a synthetic R1CS of 2^marlin_rows_logn rows, its commitments and openings over all devices
+    from kzg_snark_b200 import marlin
+    rows = 1 << args.marlin_rows_logn
+    sA, sB, sC, sx, sw = marlin.synthetic_r1cs(rows, 8, R_BN254, seed=args.marlin_rows_logn)
+    mK = 1 << (2 * rows - 1).bit_length()
+    midx = marlin.Indexer("bn254")
+    t0 = time.perf_counter()
+    sipk, _ = midx.preprocess(sA, sB, sC, max_degree=6 * mK, tau=TAU)
+    t_index = time.perf_counter() - t0
+    mpr = marlin.Prover("bn254")
+    sxs, swl, sdraws = [midx.kzg.Fq(v) for v in sx], ints_to_limbs(sw, R_BN254), random_scalars(8 + 2 * rows + 1, R_BN254, seed=4)
+    mt = []
+    for _ in range(2 + 3):
+        t0 = time.perf_counter()
+        mpr.prove(sipk, sxs, swl, draws=sdraws)
+        mt.append(time.perf_counter() - t0)
+    assert set(mpr.checks.values()) == {0}, "a Marlin linearisation identity failed"
+    marlin_res = {"rows": rows, "K": sipk["subgroups"]["m"], "prove_s": sorted(mt[2:])[1], "first_prove_s": mt[0], "index_s": t_index,
+                  "rounds_s": {k: round(v, 5) for k, v in mpr.timings.items()}}
+    clocks = sampler.stop()
+    line = {"metric": "g1_msm_points_per_s", "value": n / (ms_host * 1e-3), "unit": "points/s", "n_gpus": nd, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_host, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32x8 (256-bit modular integers, Montgomery)" if curve == "bn254" else "u32x12 / u32x8", "data": "synthetic",
+            "config": {"workload": f"{curve} G1 MSM of 2^{args.logn} points through kzgpu_msm from ONE process driving {nd} GPU(s) "
+                                   "(kzgpu_init_multi): host scalars in pinned memory, each device uploads and reduces its shard, peer-to-peer "
+                                   "partials, fold on the primary", "curve": curve, "logn": args.logn,
+                       "srs_build_s": round(build_s, 3), "first_call_s_incl_shard_build": round(first_s, 3), "tau_identity_check": bool(ok)},
+            "e2e": {"value": n / (ms_host * 1e-3), "unit": "points/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 68,
+                    "ms_per_step": ms_host, "host_buffers": "pinned (cudaHostAlloc)"},
+            "device_resident": {"ms_per_step": ms_dev, "value": n / (ms_dev * 1e-3),
+                                "note": "scalars on the primary device; the other devices pull their slices over NVLink (cudaMemcpyPeerAsync)"},
+            "batched_commit": {"polynomials": lens, "ms_per_call": ms_batch, "points_per_s": sum(lens) / (ms_batch * 1e-3),
+                               "note": "kzgpu_msm_batch from pageable host arrays: >= KZGPU_SHARD_MIN coefficients point-sharded, the rest placed "
+                                       "longest-first on the least loaded device (key replicated)"},
+            "batched_ntt": {"vectors": 8, "n": m, "ms_per_call": ms_ntt, "elements_per_s": 8 * m / (ms_ntt * 1e-3),
+                            "note": "kzgpu_ntt_batch from pinned host memory, whole vectors per device"},
+            "marlin_synthetic": marlin_res,
+            "gpu_launches": launches, "clocks": clocks, "device": info["name"], "cpu_baseline": None,
+            "roofline": None}
+    sys.stdout.write("\n" + json.dumps(line) + "\n")
+    sys.stdout.flush()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="msm", choices=["msm", "ntt", "sweep", "plonk", "marlin"])
+    ap.add_argument("--workload", default="msm", choices=["msm", "ntt", "sweep", "plonk", "marlin", "inproc"])
+    ap.add_argument("--devices", type=int, default=0, help="--workload inproc: GPUs driven from this ONE process (0 = all visible)")
     ap.add_argument("--curve", default="bn254", choices=["bn254", "bls12_381"])
     ap.add_argument("--marlin-logn", type=int, default=20, help="constraints of the Marlin kernel workload (log2)")
     ap.add_argument("--marlin-rows-logn", type=int, default=16, help="rows of the synthetic R1CS for the device Marlin prover (log2)")
@@ -1113,6 +1248,8 @@ def main():
         args.warmup = 3 if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "inproc":
+        return run_inproc(args)
     return run_gpu(args)
 
 

@@ -48,6 +48,14 @@ KzgpuCtx& kz_ctx();                        // context of the calling thread's sl
 KzgpuCtx& kz_ctx_of(int slot);
 int kz_fail(int code, const char* fmt, ...);
 
+// Host <-> device copies of caller buffers that may be PAGEABLE (the Python drop-in hands over ordinary numpy arrays).
+// Pinned memory goes straight to cudaMemcpyAsync on `stream`.  Pageable memory of >= 8 MiB is staged by a few host threads
+// through page-locked double buffers (4 MiB pieces) instead of the driver's single bounce buffer: the call returns when
+// every piece has been ISSUED on `stream` (upload) / has ARRIVED in dst (download).  context.cu.
+int kz_upload(void* d_dst, const void* h_src, size_t bytes, cudaStream_t stream);
+int kz_download(void* h_dst, const void* d_src, size_t bytes, cudaStream_t stream);
+bool kz_host_is_pinned(const void* p);
+
 // scoped CUDA-event timer around one or more launches of a profiled kernel class
 struct KzProf {
   int which;

@@ -6,6 +6,8 @@
 #include <unistd.h>
 #include <sys/syscall.h>
 #include <thread>
+#include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <condition_variable>
 
@@ -74,6 +76,129 @@ int kz_parallel(const std::function<int(int)>& fn) {
     }
   }
   return rc;
+}
+
+// ---------------------------------------------------------------- staged copies of pageable host memory
+namespace {
+constexpr size_t kPiece = 4u << 20;          // bytes per staged piece
+constexpr int kStageThreads = 4;             // host threads per copy (the caller is one of them)
+struct KzStage {                             // per slot: two page-locked pieces and their events per thread
+  char* buf[kStageThreads][2] = {{nullptr}};
+  cudaEvent_t ev[kStageThreads][2] = {{nullptr}};
+  bool ready = false;
+};
+KzStage g_stage[KZ_MAX_DEV];
+
+int stage_ready(KzStage& st) {
+  if (st.ready) return 0;
+  for (int t = 0; t < kStageThreads; t++)
+    for (int k = 0; k < 2; k++) {
+      KZ_CUDA(cudaHostAlloc((void**)&st.buf[t][k], kPiece, cudaHostAllocDefault));
+      KZ_CUDA(cudaEventCreateWithFlags(&st.ev[t][k], cudaEventDisableTiming));
+    }
+  st.ready = true;
+  return 0;
+}
+
+void stage_release(KzStage& st) {
+  if (!st.ready) return;
+  for (int t = 0; t < kStageThreads; t++)
+    for (int k = 0; k < 2; k++) { cudaFreeHost(st.buf[t][k]); cudaEventDestroy(st.ev[t][k]); st.buf[t][k] = nullptr; }
+  st.ready = false;
+}
+
+bool staging_wanted(const void* h, size_t bytes) {
+  static const bool off = getenv("KZGPU_NO_STAGING") != nullptr;
+  return !off && bytes >= (8u << 20) && !kz_host_is_pinned(h);
+}
+}  // namespace
+
+bool kz_host_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+int kz_upload(void* d_dst, const void* h_src, size_t bytes, cudaStream_t stream) {
+  if (!bytes) return 0;
+  if (!staging_wanted(h_src, bytes)) {
+    KZ_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, stream));
+    return 0;
+  }
+  KzStage& st = g_stage[kz_slot()];
+  int rc = stage_ready(st);
+  if (rc) return rc;
+  const size_t pieces = (bytes + kPiece - 1) / kPiece;
+  const int device = kz_ctx().device;
+  std::atomic<size_t> next{0};
+  std::atomic<int> err{0};
+  auto work = [&](int t) {
+    cudaSetDevice(device);
+    int k = 0;
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= pieces || err.load()) break;
+      const size_t off = i * kPiece, len = off + kPiece <= bytes ? kPiece : bytes - off;
+      cudaEventSynchronize(st.ev[t][k]);                            // this thread's previous use of the buffer has left the host
+      memcpy(st.buf[t][k], (const char*)h_src + off, len);
+      cudaError_t e = cudaMemcpyAsync((char*)d_dst + off, st.buf[t][k], len, cudaMemcpyHostToDevice, stream);
+      if (e == cudaSuccess) e = cudaEventRecord(st.ev[t][k], stream);
+      if (e != cudaSuccess) err.store((int)e);
+      k ^= 1;
+    }
+  };
+  std::thread th[kStageThreads - 1];
+  for (int t = 1; t < kStageThreads; t++) th[t - 1] = std::thread(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+  if (err.load()) return kz_fail(KZGPU_ECUDA, "staged upload failed: %s", cudaGetErrorString((cudaError_t)err.load()));
+  return 0;
+}
+
+int kz_download(void* h_dst, const void* d_src, size_t bytes, cudaStream_t stream) {
+  if (!bytes) return 0;
+  if (!staging_wanted(h_dst, bytes)) {
+    KZ_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, stream));
+    return 0;
+  }
+  KzStage& st = g_stage[kz_slot()];
+  int rc = stage_ready(st);
+  if (rc) return rc;
+  const size_t pieces = (bytes + kPiece - 1) / kPiece;
+  const int device = kz_ctx().device;
+  std::atomic<size_t> next{0};
+  std::atomic<int> err{0};
+  auto work = [&](int t) {
+    cudaSetDevice(device);
+    // two pieces in flight per thread: piece b is copied out of its buffer while piece b^1 is still arriving
+    size_t cur[2] = {(size_t)-1, (size_t)-1};
+    int k = 0;
+    auto drain = [&](int b) {
+      if (cur[b] == (size_t)-1) return;
+      cudaEventSynchronize(st.ev[t][b]);
+      const size_t off = cur[b] * kPiece, len = off + kPiece <= bytes ? kPiece : bytes - off;
+      memcpy((char*)h_dst + off, st.buf[t][b], len);
+      cur[b] = (size_t)-1;
+    };
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= pieces || err.load()) break;
+      drain(k);
+      const size_t off = i * kPiece, len = off + kPiece <= bytes ? kPiece : bytes - off;
+      cudaError_t e = cudaMemcpyAsync(st.buf[t][k], (const char*)d_src + off, len, cudaMemcpyDeviceToHost, stream);
+      if (e == cudaSuccess) e = cudaEventRecord(st.ev[t][k], stream);
+      if (e != cudaSuccess) { err.store((int)e); break; }
+      cur[k] = i;
+      k ^= 1;
+    }
+    drain(k); drain(k ^ 1);
+  };
+  std::thread th[kStageThreads - 1];
+  for (int t = 1; t < kStageThreads; t++) th[t - 1] = std::thread(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+  if (err.load()) return kz_fail(KZGPU_ECUDA, "staged download failed: %s", cudaGetErrorString((cudaError_t)err.load()));
+  return 0;
 }
 
 int kz_fail(int code, const char* fmt, ...) {
@@ -178,6 +303,7 @@ static void slot_destroy(int slot) {
   KzgpuCtx& cx = g_ctx[slot];
   if (!cx.inited) return;
   cudaStreamSynchronize(cx.stream);
+  stage_release(g_stage[slot]);
   cudaEventDestroy(cx.ev0);
   cudaEventDestroy(cx.ev1);
   cudaStreamDestroy(cx.own_stream);
@@ -310,14 +436,16 @@ int kzgpu_free(void* d_ptr) {
 
 int kzgpu_h2d(void* d_dst, const void* src, size_t bytes) {
   KZ_REQUIRE_INIT();
-  KZ_CUDA(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, kz_ctx().stream));
+  int rc = kz_upload(d_dst, src, bytes, kz_ctx().stream);
+  if (rc) return rc;
   KZ_CUDA(cudaStreamSynchronize(kz_ctx().stream));
   return 0;
 }
 
 int kzgpu_d2h(void* dst, const void* d_src, size_t bytes) {
   KZ_REQUIRE_INIT();
-  KZ_CUDA(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, kz_ctx().stream));
+  int rc = kz_download(dst, d_src, bytes, kz_ctx().stream);
+  if (rc) return rc;
   KZ_CUDA(cudaStreamSynchronize(kz_ctx().stream));
   return 0;
 }

@@ -864,13 +864,17 @@ int msm_core(const SrsPart& srs, size_t first, const uint32_t* d_scalars, size_t
   cudaStream_t sst = piped ? cx.sort_stream : st;
   size_t chunk_n = 0;                                   // largest chunk: sizes the sort scratch
   for (uint32_t k = 0; k < nchunks; k++) if (chunk_lo[k + 1] - chunk_lo[k] > chunk_n) chunk_n = chunk_lo[k + 1] - chunk_lo[k];
-  if (h_scalars && n) {
-    for (uint32_t k = 0; k < nchunks; k++) {
-      size_t lo = chunk_lo[k], cnt = chunk_lo[k + 1] - chunk_lo[k];
-      if (cnt) KZ_CUDA(cudaMemcpyAsync((void*)(d_scalars + lo * 8), h_scalars + lo * 4, cnt * 32, cudaMemcpyHostToDevice, cx.copy_stream));
-      KZ_CUDA(cudaEventRecord(cx.copy_ev[k], cx.copy_stream));
-    }
-  }
+  // chunk k of the host scalars -> device, on the copy stream (pinned memory: one asynchronous copy; pageable memory: staged
+  // through page-locked buffers by a few host threads, kz_upload).  Chunk 0 goes now, chunk k + 1 right after chunk k's
+  // kernels have been queued, so that its transfer (and, for pageable memory, its host-side staging) runs under them.
+  const uint32_t* const d_base = d_scalars;              // (d_scalars itself walks through the chunks below)
+  auto upload_chunk = [&](uint32_t k) -> int {
+    const size_t lo = chunk_lo[k], cnt = chunk_lo[k + 1] - chunk_lo[k];
+    if (cnt) { int r = kz_upload((void*)(d_base + lo * 8), h_scalars + lo * 4, cnt * 32, cx.copy_stream); if (r) return r; }
+    KZ_CUDA(cudaEventRecord(cx.copy_ev[k], cx.copy_stream));
+    return 0;
+  };
+  if (h_scalars && n) { int r = upload_chunk(0); if (r) return r; }
   const bool tabled = srs.c_tab != 0;
   const uint32_t c = tabled ? srs.c_tab : choose_c(n, R::BITS);
   const uint32_t W = (R::BITS + 1 + c - 1) / c;          // digits per scalar
@@ -1052,6 +1056,7 @@ int msm_core(const SrsPart& srs, size_t first, const uint32_t* d_scalars, size_t
   }
   prof_merge.stop(0, 0.0);
   if (piped) KZ_CUDA(cudaEventRecord(cx.acc_ev[chunk & 1], st));
+  if (h_scalars && chunk + 1 < nchunks) { int r = upload_chunk(chunk + 1); if (r) return r; }
   }  // chunks
   KzProf prof_red(3);
   msm_reduce_kernel<Cfg><<<(unsigned)kz_div_up((size_t)cpw * Wb, 128), 128, 0, st>>>((uint32_t*)g_ws.buckets.p, B, CH, cpw, Wb,
@@ -1428,7 +1433,7 @@ int msm_batch_host_on_part(const SrsPart& part, int curve, const uint64_t* const
   uint32_t* d = (uint32_t*)g_ws.scal.p;
   if (total != count * maxlen) KZ_CUDA(cudaMemsetAsync(d, 0, count * maxlen * 32, cx.stream));
   for (size_t j = 0; j < count; j++)
-    if (lens[j]) KZ_CUDA(cudaMemcpyAsync(d + j * maxlen * 8, ptrs[j], lens[j] * 32, cudaMemcpyHostToDevice, cx.stream));
+    if (lens[j]) { int r = kz_upload(d + j * maxlen * 8, ptrs[j], lens[j] * 32, cx.stream); if (r) return r; }
   std::vector<uint64_t> out(count * 2 * L);
   std::vector<int> inf(count);
   if ((rc = set_smem_attrs())) return rc;
@@ -1587,12 +1592,53 @@ int kzgpu_msm(uint64_t handle, size_t first, const uint64_t* scalars, size_t n, 
   return kz_msm_dev_internal(handle, first, d, n, out_affine_xy, is_inf, scalars);
 }
 
+// k polynomials of poly_len scalars each, back to back on the PRIMARY device.  Several devices: polynomials of
+// >= KZGPU_SHARD_MIN coefficients are point-sharded one after the other; shorter ones are dealt round-robin (they are
+// equally long) and each device pulls its polynomials from the primary over NVLink and commits them in one pass.
 int kz_msm_batch_dev_internal(uint64_t handle, const uint32_t* d_scalars, size_t poly_len, size_t k, uint64_t* out_xy, int* is_inf) {
-  const Srs* s = find_srs(handle);
+  Srs* s = find_srs(handle);
   if (!s) return kz_fail(KZGPU_EHANDLE, "unknown SRS handle %llu", (unsigned long long)handle);
   if (poly_len > s->n)
     return kz_fail(KZGPU_ERANGE, "Polynomial degree %zu exceeds maximum allowed degree %zu", poly_len - 1, s->n - 1);
-  return msm_batch_on_part(s->full, s->curve, d_scalars, poly_len, k, out_xy, is_inf);
+  const int nd = kz_ndev();
+  const int L = kzgpu_fp_limbs64(s->curve);
+  if (nd == 1 || poly_len * k < ((size_t)1 << 17)) return msm_batch_on_part(s->full, s->curve, d_scalars, poly_len, k, out_xy, is_inf);
+  int rc;
+  if (poly_len >= shard_min()) {
+    for (size_t j = 0; j < k; j++) {
+      int* fl = is_inf ? is_inf + j : nullptr;
+      rc = s->curve == KZGPU_BN254 ? msm_sharded<BN254Cfg>(*s, 0, poly_len, nullptr, d_scalars + j * poly_len * 8, out_xy + j * 2 * L, fl)
+                                   : msm_sharded<BLS381Cfg>(*s, 0, poly_len, nullptr, d_scalars + j * poly_len * 8, out_xy + j * 2 * L, fl);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  if (k > 1) {
+    rc = s->curve == KZGPU_BN254 ? ensure_replicas<BN254Cfg>(*s) : ensure_replicas<BLS381Cfg>(*s);
+    if (rc) return rc;
+  }
+  KZ_CUDA(cudaStreamSynchronize(kz_ctx_of(0).stream));            // the polynomials may still be in flight on the primary's stream
+  const int dev0 = kz_device_of(0);
+  return kz_parallel([&](int slot) -> int {
+    // polynomials slot, slot + nd, ... ; the primary works in place on contiguous runs only when nd == 1, so it copies too
+    std::vector<size_t> js;
+    for (size_t j = slot; j < k; j += nd) js.push_back(j);
+    if (js.empty()) return 0;
+    KzgpuCtx& cx = kz_ctx();
+    int r = g_ws.scal.ensure(js.size() * poly_len * 32 + 32);
+    if (r) return r;
+    uint32_t* d = (uint32_t*)g_ws.scal.p;
+    for (size_t q = 0; q < js.size(); q++)
+      KZ_CUDA(cudaMemcpyPeerAsync(d + q * poly_len * 8, kz_device_of(slot), d_scalars + js[q] * poly_len * 8, dev0, poly_len * 32, cx.stream));
+    std::vector<uint64_t> o(js.size() * 2 * L);
+    std::vector<int> f(js.size());
+    if ((r = msm_batch_on_part(slot == 0 ? s->full : s->replica[slot], s->curve, d, poly_len, js.size(), o.data(), f.data()))) return r;
+    for (size_t q = 0; q < js.size(); q++) {
+      memcpy(out_xy + js[q] * 2 * L, &o[q * 2 * L], 2 * L * 8);
+      if (is_inf) is_inf[js[q]] = f[q];
+    }
+    return 0;
+  });
 }
 
 int kzgpu_msm_batch_dev(uint64_t handle, const uint64_t* d_scalars, size_t poly_len, size_t k, uint64_t* out_affine_xy, int* is_inf) {

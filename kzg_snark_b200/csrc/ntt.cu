@@ -770,12 +770,13 @@ static int ntt_batch_host_on_slot(int field, uint64_t* data, size_t n, size_t ba
   if (bytes == 0) return 0;
   int rc = g_ntt_io.ensure(bytes);
   if (rc) return rc;
-  if (batch == 1 && n >= (1u << 20) && !getenv("KZGPU_NTT_NO_OVERLAP")) {
+  const bool pinned = kz_host_is_pinned(data);           // the pipelined paths need truly asynchronous copies
+  if (batch == 1 && n >= (1u << 20) && pinned && !getenv("KZGPU_NTT_NO_OVERLAP")) {
     // one long vector: transfers pipelined with the first and last pass (>= 2 passes at this size, >= kSlabs tiles each)
     NttHostIo io{data, data};
     return ntt_dispatch(field, (uint32_t*)g_ntt_io.p, n, 1, w, inverse, coset_shift, &io);
   }
-  if (batch > 1 && n >= (1u << 18) && !getenv("KZGPU_NTT_NO_OVERLAP")) {
+  if (batch > 1 && n >= (1u << 18) && pinned && !getenv("KZGPU_NTT_NO_OVERLAP")) {
     static cudaEvent_t ev_slot[KZ_MAX_DEV][2][4] = {{{nullptr}}};          // [slot][up | done][vector & 3]
     cudaEvent_t (*ev)[4] = ev_slot[kz_slot()];
     if (!ev[0][0]) for (int a = 0; a < 2; a++) for (int k = 0; k < 4; k++) KZ_CUDA(cudaEventCreateWithFlags(&ev[a][k], cudaEventDisableTiming));
@@ -797,10 +798,11 @@ static int ntt_batch_host_on_slot(int field, uint64_t* data, size_t n, size_t ba
     KZ_CUDA(cudaStreamSynchronize(cx.stream));
     return 0;
   }
-  KZ_CUDA(cudaMemcpyAsync(g_ntt_io.p, data, bytes, cudaMemcpyHostToDevice, cx.stream));
+  // pageable caller memory (what the Python drop-in hands over) or short vectors: staged upload, transform, staged download
+  if ((rc = kz_upload(g_ntt_io.p, data, bytes, cx.stream))) return rc;
   rc = ntt_dispatch(field, (uint32_t*)g_ntt_io.p, n, batch, w, inverse, coset_shift);
   if (rc) return rc;
-  KZ_CUDA(cudaMemcpyAsync(data, g_ntt_io.p, bytes, cudaMemcpyDeviceToHost, cx.stream));
+  if ((rc = kz_download(data, g_ntt_io.p, bytes, cx.stream))) return rc;
   KZ_CUDA(cudaStreamSynchronize(cx.stream));
   return 0;
 }

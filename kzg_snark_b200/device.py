@@ -244,6 +244,22 @@ def open_quotient(field, poly_arrays, z_limbs, xi_limbs):
     return quot[:qlen.value], ev
 
 
+def powers(field, base, n, scale=1):
+    """[scale * base^i for i < n] as (n, 4) limbs, computed on the device (kzgpu_powers_dev)."""
+    lib = _ffi.init()
+    fid = curve_id(field)
+    out = np.zeros((n, 4), dtype=np.uint64)
+    if n == 0:
+        return out
+    d = _ffi.DeviceBuffer(n * 32)
+    b = np.frombuffer((int(base) % FR[fid]).to_bytes(32, "little"), dtype="<u8").copy()
+    s = np.frombuffer((int(scale) % FR[fid]).to_bytes(32, "little"), dtype="<u8").copy()
+    check(lib.kzgpu_powers_dev(fid, d.ptr, n, ptr(b), ptr(s)))
+    d.download(out)
+    d.free()
+    return out
+
+
 # ---------------------------------------------------------------------------- diagnostics
 def field_op(curve, which, op, a, b=None):
     """Elementwise Montgomery-core check (tests): which 0=Fp 1=Fr; op 0 mul 1 add 2 sub 3 inv."""

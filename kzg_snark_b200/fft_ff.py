@@ -48,14 +48,42 @@ def _transform(values, w, F, inverse, coset=None):
     return [F(v) for v in limbs_to_ints(data)]
 
 
+def _ragged(data, w, fid, q):
+    """fft_ff.py:14-37 for a length that is NOT a power of two, on (n, 4) limb rows.  The reference never validates n
+    (only fft_ff_interpolation does, :74): its recursion halves ragged lists, lets zip-style indexing drop the last even
+    entry and leaves result[n-1] = F(0) for odd n (SURVEY.md 3.3).  The same recursion is followed here level by level;
+    every sub-list whose length IS a power of two goes through the NTT kernel, and the combining butterflies
+    (fft_ff.py:32-35: e[i] +- w^i o[i]) run as element-wise device operations.  marlin/prover.py:439 can reach this
+    (an un-padded `list(row_A)` whose top coefficient is zero)."""
+    n = data.shape[0]
+    if n == 1:
+        return data
+    if n & (n - 1) == 0:
+        out = np.ascontiguousarray(data).copy()
+        device.ntt(fid, out, int_to_limbs(w, q), inverse=False)
+        return out
+    w2 = w * w % q
+    e, o = _ragged(data[0::2], w2, fid, q), _ragged(data[1::2], w2, fid, q)
+    h = n // 2
+    tw = device.powers(fid, w, h)                                              # w^0 .. w^(h-1), computed on the device
+    t = device.field_op(fid, 1, 0, tw, np.ascontiguousarray(o[:h]))            # w^i * o[i]
+    out = np.zeros((n, 4), dtype=np.uint64)                                    # result = [F(0)] * n   (fft_ff.py:29)
+    out[:h] = device.field_op(fid, 1, 1, np.ascontiguousarray(e[:h]), t)
+    out[h:2 * h] = device.field_op(fid, 1, 2, np.ascontiguousarray(e[:h]), t)
+    return out
+
+
 def fft_ff(coeffs, w, F):
-    """out[k] = sum_j coeffs[j] * w^(j*k), natural order in and out (fft_ff.py:3-37)."""
+    """out[k] = sum_j coeffs[j] * w^(j*k), natural order in and out (fft_ff.py:3-37).  Like the reference, no check of n or
+    w: lengths that are not powers of two reproduce what its recursion returns (see _ragged)."""
     n = len(coeffs)
     if n == 1:
         return coeffs                                   # fft_ff.py:16-17: the same list object
-    if n == 0 or n & (n - 1):
-        # the reference silently mis-computes odd lengths (SURVEY.md 3.3); refuse instead
-        raise ValueError("fft_ff: length must be a power of two")
+    if n == 0:
+        raise RecursionError("maximum recursion depth exceeded")        # fft_ff.py:20-26 on an empty list never terminates
+    if n & (n - 1):
+        fid, q = _field_id(F, w)
+        return [F(v) for v in limbs_to_ints(_ragged(ints_to_limbs(coeffs, q), int(w) % q, fid, q))]
     return _transform(coeffs, w, F, inverse=False)
 
 
@@ -65,8 +93,13 @@ def ifft_ff(values, w, F):
     if n == 1:
         ninv = F(1) ** (-1)
         return [x * ninv for x in values]
-    if n == 0 or n & (n - 1):
-        raise ValueError("ifft_ff: length must be a power of two")
+    if n == 0:
+        raise RecursionError("maximum recursion depth exceeded")
+    if n & (n - 1):                                      # fft_ff.py:53-58 around the ragged recursion
+        fid, q = _field_id(F, w)
+        res = _ragged(ints_to_limbs(values, q), pow(int(w) % q, -1, q), fid, q)
+        ninv = np.ascontiguousarray(np.broadcast_to(int_to_limbs(pow(n % q, -1, q), q), (n, 4)))
+        return [F(v) for v in limbs_to_ints(device.field_op(fid, 1, 0, res, ninv))]
     return _transform(values, w, F, inverse=True)
 
 

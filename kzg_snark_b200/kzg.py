@@ -201,10 +201,8 @@ class KZG:
         z = self.Fq(z)
         xi = self.Fq(xi)
         srs = self._device_srs(ck)
-        max_degree = len(ck) - 1
-        wdeg = max((p.degree() for p in polys), default=-1) - 1
-        if wdeg > max_degree:
-            raise ValueError(f"Polynomial degree {wdeg} exceeds maximum allowed degree {max_degree}")
+        # the degree check is commit's (kzg.py:103-106 via :157): the library applies it to the quotient and reports it with the
+        # reference's message (KZGPU_ERANGE -> ValueError in device.open_proof)
         out, inf = device.open_proof(srs, [self._coeff_limbs(p) for p in polys],
                                      int_to_limbs(z, q), int_to_limbs(xi, q))
         return self._codec.from_device(out, inf)

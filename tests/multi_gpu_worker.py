@@ -52,6 +52,19 @@ def main():
     out["ntt"] = hx(y[::997])
     back = device.ntt("bn254", y.copy(), w, inverse=True, batch=9)
     out["ntt_roundtrip"] = bool((back == vecs).all())
+    # the device Marlin prover (marlin/prover.py:25-245): every round's commitments and both openings use all devices
+    from kzg_snark_b200 import marlin
+    rows = 1 << max(scale - 2, 8)
+    A, B, C, x, wit = marlin.synthetic_r1cs(rows, 8, R, seed=scale)
+    mK = 1 << (2 * rows - 1).bit_length()
+    idx = marlin.Indexer("bn254")
+    ipk, _ = idx.preprocess(A, B, C, max_degree=6 * mK, tau=TAU)
+    pr = marlin.Prover("bn254")
+    proof = pr.prove(ipk, [idx.kzg.Fq(v) for v in x], ints_to_limbs(wit, R), draws=random_scalars(8 + 2 * rows + 1, R, seed=4))
+    assert set(pr.checks.values()) == {0}
+    out["marlin"] = {"commitments": {k: [[int(c) for c in p] for p in v] for k, v in proof["commitments"].items()},
+                     "kzg_proofs": {k: [int(c) for c in v] for k, v in proof["kzg_proofs"].items()},
+                     "evaluations": {k: [int(e) for e in v] for k, v in proof["evaluations"].items()}}
     out["launches"] = _ffi.launch_count()
     print(json.dumps(out))
 

@@ -152,6 +152,47 @@ def test_commit_key_cache_and_plain_list_ck():
     assert aff(cv, kzg.commit(ck, [[5]])[0]) == cv.normalize(cv.multiply(cv.G1, 5))
 
 
+@pytest.mark.parametrize("curve", CURVE_NAMES)
+def test_fft_ff_ragged_lengths_like_the_reference(curve):
+    """fft_ff / ifft_ff never validate the length (fft_ff.py:14-37, 39-58; only fft_ff_interpolation asserts, :74): for
+    lengths that are not powers of two the recursion drops entries and leaves result[n-1] = 0.  The drop-in reproduces
+    exactly that (marlin/prover.py:439 can hand over such a list), checked against the restated recursion."""
+    from kzg_snark_b200.kzg import KZG
+    from kzg_snark_b200.fft_ff import fft_ff, ifft_ff, fft_ff_interpolation
+    from oracle.field import GFp
+    kzg = KZG(curve)
+    F = kzg.Fq
+    q = kzg.curve_order
+    Fo = GFp(q)
+    rng = random.Random(5)
+    for n in (2, 3, 5, 6, 7, 12, 24, 31, 33, 100):
+        vals = [rng.randrange(q) for _ in range(n)]
+        for w in (root_of_unity(CURVES[curve], 1 << max(n - 1, 1).bit_length()), rng.randrange(1, q)):
+            exp = [int(v) for v in off.fft_ff([Fo(v) for v in vals], Fo(w), Fo)]
+            assert [int(v) for v in fft_ff([F(v) for v in vals], F(w), F)] == exp, (n, "fft")
+            expi = [int(v) for v in off.ifft_ff([Fo(v) for v in vals], Fo(w), Fo)]
+            assert [int(v) for v in ifft_ff([F(v) for v in vals], F(w), F)] == expi, (n, "ifft")
+        if n & 1 and n > 1:
+            assert exp[-1] == 0
+    with pytest.raises(AssertionError, match="power of 2"):
+        fft_ff_interpolation([F(1)] * 3, F(root_of_unity(CURVES[curve], 4)), F)
+    with pytest.raises(RecursionError):
+        fft_ff([], F(1), F)
+    one = [F(7)]
+    assert fft_ff(one, F(1), F) is one                                  # fft_ff.py:16-17
+
+
+def test_open_degree_overflow_is_commits_error():
+    """kzg.py:157 -> :103-106: open() of a polynomial whose QUOTIENT exceeds the key raises commit's ValueError and message."""
+    from kzg_snark_b200.kzg import KZG
+    kzg = KZG("bn254")
+    ck, _ = kzg.setup(4, tau=99)
+    X = kzg.X
+    with pytest.raises(ValueError, match="Polynomial degree 5 exceeds maximum allowed degree 4"):
+        kzg.open(ck, [X ** 6 + 1], 3, 5)
+    kzg.open(ck, [X ** 5 + 1], 3, 5)                                    # quotient of degree 4 fits
+
+
 @pytest.mark.parametrize("logn", [20])
 def test_tau_identity_large(logn):
     """Full-size style check: commit(ck, p) == p(tau) * G1 at 2^20 points."""

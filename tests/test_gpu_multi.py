@@ -38,6 +38,6 @@ def test_marlin_sized_commits_on_all_gpus_match_one_gpu(scale, shard_min):
     one = _run({"KZGPU_SHARD_MIN": str(shard_min)}, scale)
     many = _run({"KZGPU_DEVICES": "all", "KZGPU_SHARD_MIN": str(shard_min)}, scale)
     assert one["ndev"] == 1 and many["ndev"] == ng
-    for k in ("commits", "infs", "msm", "msm_offset", "msm_dev", "open", "ntt", "ntt_roundtrip"):
+    for k in ("commits", "infs", "msm", "msm_offset", "msm_dev", "open", "ntt", "ntt_roundtrip", "marlin"):
         assert one[k] == many[k], k
     assert many["ntt_roundtrip"] is True and many["launches"] > one["launches"] // 2

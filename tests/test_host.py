@@ -216,3 +216,35 @@ def test_point_codec_round_trip():
     assert (int(pt[0]), int(pt[1]), int(pt[2])) == (*c.normalize(P), 1)
     z = codec.from_device(arr[1], True)
     assert int(z[2]) == 0
+
+
+def test_ints_to_limbs_fast_paths_and_edge_values():
+    """The Python-object boundary (kzg.py:110,115): plain ints, shim field elements (`.n`), arbitrary int()-able objects, and
+    values outside [0, q) -- negative, == q, > q, wider than 256 bits -- all land as canonical little-endian limbs."""
+    from kzg_snark_b200.limbs import ints_to_limbs, limbs_to_ints, int_to_limbs
+    from kzg_snark_b200.sageshim import GF
+    q = CURVES["bn254"]["r"]
+    rng = random.Random(3)
+    vals = [rng.randrange(q) for _ in range(1000)] + [0, 1, q - 1]
+    a = ints_to_limbs(vals, q)
+    assert a.shape == (1003, 4) and a.dtype == np.uint64 and a.flags["WRITEABLE"] and limbs_to_ints(a) == vals
+    F = GF(q)
+    assert (ints_to_limbs([F(v) for v in vals], q) == a).all()
+    edge = [-1, q, q + 5, q - 1, 0, 2 ** 256 - 1, 3 * q + 7, -q, 2 ** 300 + 1]
+    assert limbs_to_ints(ints_to_limbs(edge, q)) == [v % q for v in edge]
+    mixed = vals[:10] + [q + 1] + vals[10:20]
+    assert limbs_to_ints(ints_to_limbs(mixed, q)) == vals[:10] + [1] + vals[10:20]
+
+    class Odd:
+        def __init__(self, v):
+            self.v = v
+
+        def __int__(self):
+            return self.v
+
+    assert limbs_to_ints(ints_to_limbs([Odd(5), Odd(q + 2), Odd(-3)], q)) == [5, 2, q - 3]
+    assert ints_to_limbs([], q).shape == (0, 4)
+    p = CURVES["bls12_381"]["p"]
+    big = [rng.randrange(p) for _ in range(50)] + [p, p + 1]
+    assert limbs_to_ints(ints_to_limbs(big, p, 6)) == [v % p for v in big]
+    assert limbs_to_ints(int_to_limbs(q + 3, q).reshape(1, 4)) == [3]
