@@ -302,6 +302,40 @@ def reference_prover_on_gpu_dropin(name):
                     "the reference's Python polynomial algebra on the Sage stand-in, so this is dominated by host work"}
 
 
+def marlin_synthetic_prove(rows_logn, reps=3):
+    """configs[4]: kzg_snark_b200.marlin.Prover.prove (the device-resident counterpart of marlin/prover.py:25-245) on a synthetic
+    R1CS of 2^rows_logn rows, on whatever devices the library is initialised on (one, or several: its commitments and openings
+    are then point-sharded / dealt over them inside the library).  The reference prover cannot run at this size (dense Sage
+    matrices)."""
+    from kzg_snark_b200 import _ffi, marlin
+    from kzg_snark_b200.limbs import random_scalars, ints_to_limbs
+    rows = 1 << rows_logn
+    t0 = time.perf_counter()
+    sA, sB, sC, sx, sw = marlin.synthetic_r1cs(rows, 8, R_BN254, seed=rows_logn)
+    swl = ints_to_limbs(sw, R_BN254)
+    sdraws = random_scalars(8 + 2 * rows + 1, R_BN254, seed=4)
+    t_gen = time.perf_counter() - t0
+    midx = marlin.Indexer("bn254")
+    mK = 1 << (2 * rows - 1).bit_length()
+    t0 = time.perf_counter()
+    sipk, _ = midx.preprocess(sA, sB, sC, max_degree=6 * mK, tau=TAU)
+    _ffi.check(_ffi._lib.kzgpu_sync())
+    t_index = time.perf_counter() - t0
+    sxs = [midx.kzg.Fq(v) for v in sx]
+    mpr = marlin.Prover("bn254")
+    mt = []
+    for _ in range(2 + reps):
+        t0 = time.perf_counter()
+        mpr.prove(sipk, sxs, swl, draws=sdraws)
+        mt.append(time.perf_counter() - t0)
+    assert set(mpr.checks.values()) == {0}, "a Marlin linearisation identity failed"
+    warm = sorted(mt[2:])
+    return {"rows": rows, "H": sipk["subgroups"]["n"], "K": sipk["subgroups"]["m"], "gpus": _ffi.device_count(),
+            "prove_s": warm[len(warm) // 2], "first_prove_s": mt[0], "index_s": t_index, "instance_generation_s": t_gen,
+            "rounds_s": {k: round(v, 5) for k, v in mpr.timings.items()},
+            "checks": "f_1(beta_1) = f_2(beta_1) = f_3(beta_2) = 0 asserted (the verifier's polynomial identities)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -825,7 +859,7 @@ def run_gpu(args):
         wpin = _ffi.PinnedArray((3 * n - 16, 4))                      # the witness lives in page-locked host memory
         wpin.array[:] = ints_to_limbs(w[16:], R_BN254)
         wl = wpin.array
-        t_gen = time.perf_counter() - t0
+        t_gen_plonk = time.perf_counter() - t0
         t0 = time.perf_counter()
         ipk, _ = idx.preprocess(qM, qL, qR, qO, qC, perm, max_degree=n + 5, tau=TAU, k1=7, k2=13)
         _ffi.check(_ffi._lib.kzgpu_sync())
@@ -872,30 +906,8 @@ def run_gpu(args):
                  and all([int(e) for e in mproof["evaluations"][k]] == [H(q) for q in v] for k, v in dm["proof"]["evaluations"].items())
                  and all(pt2(mproof["kzg_proofs"][k]) == (H(v[0]), H(v[1])) for k, v in dm["proof"]["kzg_proofs"].items()))
         out["marlin_bundled"].update({"prove_s": mt[len(mt) // 2], "proof_equals_reference_prover": bool(msame)})
-        rows = 1 << args.marlin_rows_logn
-        t0 = time.perf_counter()
-        sA, sB, sC, sx, sw = marlin.synthetic_r1cs(rows, 8, R_BN254, seed=args.marlin_rows_logn)
-        swl = ints_to_limbs(sw, R_BN254)
-        sdraws = random_scalars(8 + 2 * rows + 1, R_BN254, seed=4)
-        t_gen = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        mK = 1 << (2 * rows - 1).bit_length()
-        sipk, _ = midx.preprocess(sA, sB, sC, max_degree=6 * mK, tau=TAU)
-        _ffi.check(_ffi._lib.kzgpu_sync())
-        t_mindex = time.perf_counter() - t0
-        sxs = [midx.kzg.Fq(v) for v in sx]
-        mt = []
-        for i in range(3 + 5):
-            t0 = time.perf_counter()
-            mpr.prove(sipk, sxs, swl, draws=sdraws)
-            mt.append(time.perf_counter() - t0)
-        assert set(mpr.checks.values()) == {0}, "a Marlin linearisation identity failed"
-        mt = sorted(mt[3:])
-        out["marlin_synthetic"] = {"rows": rows, "H": sipk["subgroups"]["n"], "K": sipk["subgroups"]["m"], "prove_s": mt[len(mt) // 2],
-                                   "index_s": t_mindex, "instance_generation_s": t_gen,
-                                   "rounds_s": {k: round(v, 5) for k, v in mpr.timings.items()},
-                                   "checks": "f_1(beta_1) = f_2(beta_1) = f_3(beta_2) = 0 asserted (the verifier's polynomial identities)"}
-        out["synthetic"] = {"gates": n, "prove_s": times[len(times) // 2], "index_s": t_index, "circuit_generation_s": t_gen,
+        out["marlin_synthetic"] = marlin_synthetic_prove(args.marlin_rows_logn)
+        out["synthetic"] = {"gates": n, "prove_s": times[len(times) // 2], "index_s": t_index, "circuit_generation_s": t_gen_plonk,
                             "h2d_bytes": int(wl.nbytes), "host_buffers": "pinned (cudaHostAlloc)", "gpu_launches_per_prove": int(launches),
                             "rounds_s": {k: round(v, 5) for k, v in prover.timings.items()},
                             "checks": "r(zeta) == 0 and deg t <= 3n+5 asserted; verifier acceptance at this construction is "
@@ -1061,6 +1073,24 @@ def run_gpu(args):
                   "plonk": plonk, "device": info["name"]})
         return finish()
 
+    # ------------------------------------------------------------------ configs[4] at N > 1: the Marlin prove on all the job's GPUs
+    marlin_multi = None
+    if world > 1 and args.workload == "msm" and not args.no_secondary:
+        # The prover is one process (its polynomials live on one device); with several devices the LIBRARY spreads each round's
+        # commitments and openings (kzgpu_init_multi).  Rank 0 therefore re-initialises the library on the job's N GPUs while the
+        # other ranks -- idle, their buffers freed -- wait on a CPU-side (gloo) barrier.
+        cpu_group = dist.new_group(backend="gloo")
+        barrier()
+        if rank == 0:
+            _ffi.shutdown()
+            _ffi.init_multi(list(range(world)))
+            try:
+                marlin_multi = marlin_synthetic_prove(args.marlin_rows_logn)
+            except Exception as exc:                                     # the primary line must survive
+                marlin_multi = {"error": repr(exc)[:300]}
+            _ffi.shutdown()
+        dist.barrier(group=cpu_group)
+
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -1117,6 +1147,10 @@ def run_gpu(args):
             line["profile_ms_per_step"] = primary["profile_ms_per_step"]
         if "weak" in primary:
             line["weak"] = primary["weak"]
+        if marlin_multi is not None:
+            line["marlin"] = {**marlin_multi, "note": f"configs[4]: device Marlin prover, synthetic R1CS, ONE process driving the job's {world} GPUs "
+                                                      "through kzgpu_init_multi (commitments / openings point-sharded or dealt over the devices inside "
+                                                      "the library); the N = 1 figure is plonk.marlin_synthetic of the 1-GPU line"}
         if plonk is not None:
             if cpu_plonk is not None:
                 plonk["bundled"]["cpu_port_hotpath_s"] = cpu_plonk
@@ -1183,24 +1217,8 @@ def run_inproc(args):
     vecs = pinned.array.reshape(8 * m, 4)
     ms_ntt = timed(lambda: device.ntt(curve, vecs, wl, batch=8), max(2, K // 2))
     # configs[4]: the device Marlin prover on a synthetic R1CS of 2^marlin_rows_logn rows, its commitments and openings over all devices
-    from kzg_snark_b200 import marlin
-    rows = 1 << args.marlin_rows_logn
-    sA, sB, sC, sx, sw = marlin.synthetic_r1cs(rows, 8, R_BN254, seed=args.marlin_rows_logn)
-    mK = 1 << (2 * rows - 1).bit_length()
-    midx = marlin.Indexer("bn254")
-    t0 = time.perf_counter()
-    sipk, _ = midx.preprocess(sA, sB, sC, max_degree=6 * mK, tau=TAU)
-    t_index = time.perf_counter() - t0
-    mpr = marlin.Prover("bn254")
-    sxs, swl, sdraws = [midx.kzg.Fq(v) for v in sx], ints_to_limbs(sw, R_BN254), random_scalars(8 + 2 * rows + 1, R_BN254, seed=4)
-    mt = []
-    for _ in range(2 + 3):
-        t0 = time.perf_counter()
-        mpr.prove(sipk, sxs, swl, draws=sdraws)
-        mt.append(time.perf_counter() - t0)
-    assert set(mpr.checks.values()) == {0}, "a Marlin linearisation identity failed"
-    marlin_res = {"rows": rows, "K": sipk["subgroups"]["m"], "prove_s": sorted(mt[2:])[1], "first_prove_s": mt[0], "index_s": t_index,
-                  "rounds_s": {k: round(v, 5) for k, v in mpr.timings.items()}}
+    pinned.free(); dsc.free(); srs.destroy()
+    marlin_res = marlin_synthetic_prove(args.marlin_rows_logn)
     clocks = sampler.stop()
     line = {"metric": "g1_msm_points_per_s", "value": n / (ms_host * 1e-3), "unit": "points/s", "n_gpus": nd, "steps": K, "warmup": Wm,
             "ms_per_step": ms_host, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -1236,7 +1254,7 @@ def main():
     ap.add_argument("--devices", type=int, default=0, help="--workload inproc: GPUs driven from this ONE process (0 = all visible)")
     ap.add_argument("--curve", default="bn254", choices=["bn254", "bls12_381"])
     ap.add_argument("--marlin-logn", type=int, default=20, help="constraints of the Marlin kernel workload (log2)")
-    ap.add_argument("--marlin-rows-logn", type=int, default=16, help="rows of the synthetic R1CS for the device Marlin prover (log2)")
+    ap.add_argument("--marlin-rows-logn", type=int, default=20, help="rows of the synthetic R1CS for the device Marlin prover (log2; configs[4] names 2^20)")
     ap.add_argument("--plonk-logn", type=int, default=20, help="gates of the synthetic PLONK circuit (log2)")
     ap.add_argument("--logn", type=int, default=24)
     ap.add_argument("--sweep-max", type=int, default=26, help="largest log2 size of --workload sweep")

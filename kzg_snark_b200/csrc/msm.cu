@@ -741,6 +741,55 @@ __global__ void __launch_bounds__(128) srs_table_kernel(const uint32_t* __restri
   for (int k = 0; k < P::N; k++) { o[k] = r.x.v[k]; o[P::N + k] = r.y.v[k]; }
 }
 
+// All window tables of a short key in ONE launch.  Thread i walks the doubling chain of point i -- T_w[i] = 2^(c w) P_i, c (W - 1)
+// doublings in XYZZ -- leaving X, Y in the table slots and ZZ, ZZZ plus the running product of the denominators ZZ * ZZZ in
+// scratch; ONE Fermat inversion per thread then normalises all W - 1 entries on the way back (Montgomery's trick: 9 products per
+// entry instead of a 380-product inversion).  The per-table kernel above pays that inversion W - 1 times per point in W - 1
+// dependent launches: 8 ms for a 22-point key (c = 7, 37 tables) against 1.5 ms here, which is what a caller that hands over
+// a fresh `ck` list pays before its first commit (kzg.py:80).  scratch: (W - 1) * n * 3N words, laid out [w][i] like the tables.
+template <class Cfg>
+__global__ void __launch_bounds__(128) srs_tables_fused_kernel(uint32_t* __restrict__ tables, size_t n, uint32_t c, uint32_t W,
+                                                              uint32_t* __restrict__ scratch) {
+  using P = typename Cfg::Fp;
+  constexpr int N = P::N;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t tstride = n * 2 * N, sstride = n * 3 * N;
+  auto st_fe = [](uint32_t* p, const Fe<P>& a) { for (int k = 0; k < N; k++) p[k] = a.v[k]; };
+  auto ld_fe = [](const uint32_t* p) { Fe<P> a; for (int k = 0; k < N; k++) a.v[k] = p[k]; return a; };
+  Affine<P> a = ld_affine<P>(tables, i);
+  if (aff_is_inf<P>(a)) {
+    for (uint32_t w = 1; w < W; w++) { st_fe(tables + w * tstride + i * 2 * N, a.x); st_fe(tables + w * tstride + i * 2 * N + N, a.y); }
+    return;
+  }
+  XYZZ<P> q = xyzz_from_affine<P>(a);
+  Fe<P> run = fe_one<P>();
+  for (uint32_t w = 1; w < W; w++) {
+    for (uint32_t k = 0; k < c; k++) q = xyzz_dbl<P>(q);
+    uint32_t* t = tables + w * tstride + i * 2 * N;
+    uint32_t* sc = scratch + (w - 1) * sstride + i * 3 * N;
+    st_fe(t, q.x); st_fe(t + N, q.y);
+    st_fe(sc, q.zz); st_fe(sc + N, q.zzz);
+    st_fe(sc + 2 * N, run);                               // product of the denominators of tables 1 .. w-1
+    Fe<P> den = fe_mul<P>(q.zz, q.zzz);
+    if (fe_is_zero<P>(den)) den = fe_one<P>();            // 2^(cw) P_i = infinity (a point outside the prime-order group): written as (0, 0) below
+    run = fe_mul<P>(run, den);
+  }
+  Fe<P> inv = fe_inv<P>(run);
+  for (uint32_t w = W - 1; w >= 1; w--) {
+    uint32_t* t = tables + w * tstride + i * 2 * N;
+    const uint32_t* sc = scratch + (w - 1) * sstride + i * 3 * N;
+    Fe<P> zz = ld_fe(sc), zzz = ld_fe(sc + N), pre = ld_fe(sc + 2 * N);
+    Fe<P> den = fe_mul<P>(zz, zzz);
+    if (fe_is_zero<P>(den)) { st_fe(t, fe_zero<P>()); st_fe(t + N, fe_zero<P>()); continue; }
+    Fe<P> dinv = fe_mul<P>(inv, pre);                     // 1 / (zz * zzz) = Z^-5
+    inv = fe_mul<P>(inv, den);
+    Fe<P> x = fe_mul<P>(ld_fe(t), fe_mul<P>(dinv, zzz));  // X / ZZ
+    Fe<P> y = fe_mul<P>(ld_fe(t + N), fe_mul<P>(dinv, zz));   // Y / ZZZ
+    st_fe(t, x); st_fe(t + N, y);
+  }
+}
+
 // SRS generation (kzg.py:69-72): point i = tau^i * G1.  dbl_table[j] = 2^j * G1 (affine, Montgomery).
 template <class Cfg>
 __global__ void __launch_bounds__(128) srs_generate_kernel(uint32_t* pts, size_t start, size_t n, Fe<typename Cfg::Fr> tau_mont,
@@ -1196,6 +1245,19 @@ int part_build_tables(SrsPart& s) {
   using P = typename Cfg::Fp;
   KzgpuCtx& cx = kz_ctx();
   const size_t stride = s.n * 2 * P::N;
+  if (s.c_tab && s.W_tab > 1 && s.n <= ((size_t)1 << 18) && !getenv("KZGPU_SRS_TABLES_PER_WINDOW")) {
+    // short keys: every table in one launch, one inversion per point (srs_tables_fused_kernel)
+    uint32_t* scratch = nullptr;
+    const size_t sbytes = (size_t)(s.W_tab - 1) * s.n * 3 * P::N * 4;
+    if (cudaMalloc((void**)&scratch, sbytes) == cudaSuccess) {
+      srs_tables_fused_kernel<Cfg><<<(unsigned)kz_div_up(s.n, 128), 128, 0, cx.stream>>>(s.d_points, s.n, s.c_tab, s.W_tab, scratch);
+      KZ_LAUNCHED();
+      KZ_CUDA(cudaStreamSynchronize(cx.stream));
+      cudaFree(scratch);
+      return 0;
+    }
+    cudaGetLastError();                                   // no room for the scratch: table by table
+  }
   for (uint32_t w = 1; w < s.W_tab && s.c_tab; w++) {
     srs_table_kernel<Cfg><<<(unsigned)kz_div_up(s.n, 128), 128, 0, cx.stream>>>(s.d_points + (w - 1) * stride, s.d_points + w * stride,
                                                                               s.n, s.c_tab);
