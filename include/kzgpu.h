@@ -121,7 +121,10 @@ int kzgpu_msm_batch(uint64_t handle, const uint64_t* scalars, const size_t* lens
 int kzgpu_msm_batch_dev(uint64_t handle, const uint64_t* d_scalars, size_t poly_len, size_t k,
                         uint64_t* out_affine_xy, int* is_inf);
 /* Partial sum for point-sharded multi-GPU MSM: result left un-normalised as XYZZ in
- * Montgomery form (4 * fp_limbs64 limbs), to be all-gathered and folded by kzgpu_g1_fold. */
+ * Montgomery form (4 * fp_limbs64 limbs), to be all-gathered and folded by kzgpu_g1_fold.
+ * Both forms return with the work QUEUED on the library's stream (no host synchronisation: the caller's exchange is
+ * queued right behind the partial); a non-canonical scalar (KZGPU_ERANGE) is then reported by the call that
+ * synchronises next -- kzgpu_g1_fold, kzgpu_sync, or the next MSM. */
 int kzgpu_msm_partial_dev(uint64_t handle, size_t first, const uint64_t* d_scalars, size_t n,
                           uint64_t* d_out_xyzz);
 /* same with this rank's slice of the scalars in host memory (the multi-GPU form of kzgpu_msm: kzg.py:112-116 over an

@@ -11,6 +11,7 @@
 #include <mutex>
 #include <condition_variable>
 
+int kz_msm_pending_check();
 void kz_ntt_release();
 void kz_msm_release();
 void kz_poly_release();
@@ -464,6 +465,8 @@ int kzgpu_memset(void* d_dst, int byte, size_t bytes) {
 
 int kzgpu_sync(void) {
   KZ_REQUIRE_INIT();
+  int rc = kz_msm_pending_check();             // a kzgpu_msm_partial* that returned before its flag was read
+  if (rc) return rc;
   KZ_CUDA(cudaStreamSynchronize(kz_ctx().stream));
   return 0;
 }

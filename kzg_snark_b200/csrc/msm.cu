@@ -40,8 +40,11 @@ struct Srs {
   size_t n;
   SrsPart full;                      // the whole key on the primary device (slot 0)
   // multi-device layouts, built on first use from `full` (peer copy of the plain points, local table build):
-  bool has_shards = false, has_replicas = false;
-  SrsPart shard[KZ_MAX_DEV];         // slot d owns the contiguous range d of the key, tables sized for the SHARD
+  bool has_replicas = false;
+  // shard sets by length class E (a power of two, or the key's length): slot d owns [d E / N, (d + 1) E / N) of the key with
+  // tables sized for THAT range, so a 2^20-coefficient polynomial committed against a 12 M-point key is spread over all
+  // devices (not just the ones owning the head of the key) and each runs the window a 2^17-point MSM wants
+  std::map<size_t, std::vector<SrsPart>>* shard_sets = nullptr;
   SrsPart replica[KZ_MAX_DEV];       // the whole key, tables included, on every slot (replica[0] aliases full)
 };
 
@@ -874,10 +877,36 @@ uint32_t choose_table_c(size_t n, int bits, size_t point_bytes) {
   return best_c;
 }
 
+// The "scalar not canonical" flag of an MSM whose caller did not wait for it (msm_core with defer = true: the partial sum stays
+// on the device and the next thing queued behind it is an exchange, so a host synchronisation here would only open a gap):
+// collected by whoever synchronises the stream next -- the fold of the partials, kzgpu_sync, or the next MSM.
+bool g_flag_pending[KZ_MAX_DEV] = {false};
+int msm_flag_collect(uint32_t* host_word) {             // queue the read behind everything on the stream (no-op if nothing is pending)
+  *host_word = 0;
+  if (!g_flag_pending[kz_slot()]) return 0;
+  KZ_CUDA(cudaMemcpyAsync(host_word, g_ws.flag.p, 4, cudaMemcpyDeviceToHost, kz_ctx().stream));
+  return 0;
+}
+int msm_flag_result(uint32_t host_word) {               // after the stream has been synchronised
+  if (!g_flag_pending[kz_slot()]) return 0;
+  g_flag_pending[kz_slot()] = false;
+  if (host_word) return kz_fail(KZGPU_ERANGE, "a scalar of the preceding MSM is not a canonical residue");
+  return 0;
+}
+int msm_flag_wait() {
+  if (!g_flag_pending[kz_slot()]) return 0;
+  uint32_t h = 0;
+  int rc = msm_flag_collect(&h);
+  if (rc) return rc;
+  KZ_CUDA(cudaStreamSynchronize(kz_ctx().stream));
+  return msm_flag_result(h);
+}
+
 // `srs`: one device's part of a key (the calling thread's device); `first` is an index INSIDE that part
 template <class Cfg>
 int msm_core(const SrsPart& srs, size_t first, const uint32_t* d_scalars, size_t n, int mode, uint32_t* d_out,
-             const uint64_t* h_scalars = nullptr, uint32_t* h_out_xyzz = nullptr, uint32_t batch = 1) {
+             const uint64_t* h_scalars = nullptr, uint32_t* h_out_xyzz = nullptr, uint32_t batch = 1, bool defer = false) {
+  { int rcp = msm_flag_wait(); if (rcp) return rcp; }
   // batch > 1: d_scalars holds `batch` polynomials of n / batch scalars each (zero padded to equal length); they
   // share one sort / accumulate / reduce pass, every polynomial owning its own bucket set(s), and d_out receives
   // `batch` XYZZ results (mode 0 / 2 only)
@@ -896,13 +925,22 @@ int msm_core(const SrsPart& srs, size_t first, const uint32_t* d_scalars, size_t
   // loses about what the overlap wins, plus the second chunk's bucket fix-up -- so it stays off by default.
   static const bool pipe_ok = !getenv("KZGPU_MSM_NO_PIPE");
   uint32_t nchunks = 1;
-  if (batch == 1 && h_scalars && n >= (1u << 20)) nchunks = 4;
+  bool host_two = false;
+  if (batch == 1 && h_scalars && n >= (1u << 20)) {
+    // every chunk pays the fixed cost of a sort / task / accumulate round (~0.2 ms) and a bucket load + store per task, so short
+    // MSMs -- the shards of a point-sharded MSM -- upload in two chunks (1/4, 3/4), long ones in four
+    static const int forced = getenv("KZGPU_MSM_NCHUNKS") ? atoi(getenv("KZGPU_MSM_NCHUNKS")) : 0;
+    nchunks = forced == 1 || forced == 2 || forced == 4 ? (uint32_t)forced : (n >= (1u << 23) ? 4u : 2u);
+    host_two = nchunks == 2;
+  }
   else if (batch == 1 && !h_scalars && n >= (1u << 22) && pipe_ok && getenv("KZGPU_MSM_DEV_SPLIT")) nchunks = 2;
   size_t chunk_lo[5] = {0, n, n, n, n};
   if (nchunks == 4) {
     const char* env = getenv("KZGPU_MSM_CHUNKS");      // "uniform": four equal chunks (A/B measurements)
     if (env && env[0] == 'u') { chunk_lo[1] = n / 4; chunk_lo[2] = n / 2; chunk_lo[3] = 3 * (n / 4); }
     else { chunk_lo[1] = n / 16; chunk_lo[2] = n / 4; chunk_lo[3] = n / 2; }
+  } else if (host_two) {
+    chunk_lo[1] = n / 4;
   } else if (nchunks == 2) {
     static const char* env = getenv("KZGPU_MSM_DEV_SPLIT");     // first chunk = n / split (A/B measurements)
     const size_t split = env && atoi(env) >= 2 ? (size_t)atoi(env) : 8;
@@ -1127,6 +1165,7 @@ int msm_core(const SrsPart& srs, size_t first, const uint32_t* d_scalars, size_t
   msm_final_kernel<Cfg><<<batch, 32, 0, st>>>(lvl_in, Wp, c, mode == 2 ? 0 : mode, d_out);
   KZ_LAUNCHED();
   prof_red.stop(1, (double)nb);
+  if (defer && mode == 0 && !cx.profile) { g_flag_pending[kz_slot()] = true; return 0; }
   uint32_t hflag = 0;
   KZ_CUDA(cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, st));
   if (mode == 2 && h_out_xyzz) KZ_CUDA(cudaMemcpyAsync(h_out_xyzz, d_out, (size_t)batch * 4 * P::N * 4, cudaMemcpyDeviceToHost, st));
@@ -1326,10 +1365,14 @@ int srs_generate_impl(const uint64_t* tau, size_t start, size_t n, uint64_t* han
 
 void srs_free(Srs& s) {
   cudaFree(s.full.d_points);
-  for (int d = 0; d < KZ_MAX_DEV; d++) {
-    if (s.has_shards && s.shard[d].d_points) cudaFree(s.shard[d].d_points);
-    if (s.has_replicas && d > 0 && s.replica[d].d_points) cudaFree(s.replica[d].d_points);
+  if (s.shard_sets) {
+    for (auto& kv : *s.shard_sets)
+      for (auto& part : kv.second) if (part.d_points) cudaFree(part.d_points);
+    delete s.shard_sets;
+    s.shard_sets = nullptr;
   }
+  for (int d = 1; d < KZ_MAX_DEV; d++)
+    if (s.has_replicas && s.replica[d].d_points) cudaFree(s.replica[d].d_points);
 }
 
 // ---------------------------------------------------------------- several devices (kzgpu_init_multi)
@@ -1342,21 +1385,28 @@ size_t shard_min() {
   return v;
 }
 
-// Point shards: slot d owns the contiguous range d of the key.  Its plain points come from the primary device's table 0
-// by a peer copy (NVLink when peer access is on); the window tables are built locally, for the SHARD's size -- a 2^21-point
-// shard of a 2^24-point key gets c = 20 (2^19 buckets to reduce per MSM), not the key's c = 22.
+// Point shards of the length class E (the index range [0, E) of the key): slot d owns [d E / N, (d + 1) E / N).  Its plain
+// points come from the primary device's table 0 by a peer copy (NVLink when peer access is on); the window tables are built
+// locally, for the SHARD's size -- a 2^21-point shard of a 2^24-point key gets c = 20 (2^19 buckets to reduce per MSM), not
+// the key's c = 22.  Returns the set through *out.
 template <class Cfg>
-int ensure_shards(Srs& s) {
+int ensure_shards(Srs& s, size_t end, std::vector<SrsPart>** out) {
   using P = typename Cfg::Fp;
-  if (s.has_shards) return 0;
+  size_t E = 1;
+  while (E < end) E <<= 1;
+  if (E > s.n) E = s.n;
+  if (!s.shard_sets) s.shard_sets = new std::map<size_t, std::vector<SrsPart>>();
+  auto it = s.shard_sets->find(E);
+  if (it != s.shard_sets->end()) { *out = &it->second; return 0; }
   const int nd = kz_ndev();
+  std::vector<SrsPart> parts(nd);
   KZ_CUDA(cudaStreamSynchronize(kz_ctx_of(0).stream));
   const int dev0 = kz_device_of(0);
   const size_t pt_words = 2 * P::N;
   int rc = kz_parallel([&](int slot) -> int {
-    const size_t base = s.n / nd, rem = s.n % nd;
+    const size_t base = E / nd, rem = E % nd;
     const size_t first = slot * base + ((size_t)slot < rem ? slot : rem), cnt = base + ((size_t)slot < rem ? 1 : 0);
-    SrsPart& sh = s.shard[slot];
+    SrsPart& sh = parts[slot];
     int r = part_alloc<Cfg>(sh, first, cnt);
     if (r) return r;
     if (!cnt) return 0;
@@ -1366,8 +1416,12 @@ int ensure_shards(Srs& s) {
     KZ_CUDA(cudaStreamSynchronize(cx.stream));
     return 0;
   });
-  if (rc) return rc;
-  s.has_shards = true;
+  if (rc) {
+    for (auto& part : parts) if (part.d_points) cudaFree(part.d_points);
+    return rc;
+  }
+  *out = &(*s.shard_sets)[E];
+  **out = parts;
   return 0;
 }
 
@@ -1406,7 +1460,8 @@ int msm_sharded(Srs& s, size_t first, size_t n, const uint64_t* h_scalars, const
   using P = typename Cfg::Fp;
   const int nd = kz_ndev();
   int rc;
-  if ((rc = ensure_shards<Cfg>(s))) return rc;
+  std::vector<SrsPart>* shards = nullptr;
+  if ((rc = ensure_shards<Cfg>(s, first + n, &shards))) return rc;
   const size_t xyzz_bytes = 4 * P::N * 4;
   MsmWs& w0 = g_ws_slots.of(0);
   if ((rc = w0.gather.ensure(nd * xyzz_bytes))) return rc;
@@ -1416,7 +1471,7 @@ int msm_sharded(Srs& s, size_t first, size_t n, const uint64_t* h_scalars, const
   const int dev0 = kz_device_of(0);
   uint32_t* gather = (uint32_t*)w0.gather.p;
   rc = kz_parallel([&](int slot) -> int {
-    const SrsPart& sh = s.shard[slot];
+    const SrsPart& sh = (*shards)[slot];
     const size_t lo = first > sh.first ? first : sh.first;
     const size_t hi_all = first + n, hi_sh = sh.first + sh.n;
     const size_t hi = hi_all < hi_sh ? hi_all : hi_sh;
@@ -1436,11 +1491,13 @@ int msm_sharded(Srs& s, size_t first, size_t n, const uint64_t* h_scalars, const
       if (h_scalars) h_sc = h_scalars + (lo - first) * 4;
       else if (slot == 0) d_sc = d0_scalars + (lo - first) * 8;
       else KZ_CUDA(cudaMemcpyPeerAsync(w.scal.p, kz_device_of(slot), d0_scalars + (lo - first) * 8, dev0, cnt * 32, cx.stream));
-      if ((r = msm_core<Cfg>(sh, lo - sh.first, d_sc, cnt, 0, d_part, h_sc))) return r;
+      if ((r = msm_core<Cfg>(sh, lo - sh.first, d_sc, cnt, 0, d_part, h_sc, nullptr, 1, true))) return r;
     }
     KZ_CUDA(cudaMemcpyPeerAsync(gather + (size_t)slot * 4 * P::N, dev0, d_part, kz_device_of(slot), xyzz_bytes, cx.stream));
+    uint32_t hflag = 0;
+    if ((r = msm_flag_collect(&hflag))) return r;
     KZ_CUDA(cudaStreamSynchronize(cx.stream));
-    return 0;
+    return msm_flag_result(hflag);
   });
   if (rc) return rc;
   g1_fold_kernel<Cfg><<<1, 128, 128 * 4 * P::N * 4, cx0.stream>>>(gather, (uint32_t)nd, (uint32_t*)w0.result.p);
@@ -1558,6 +1615,9 @@ int kz_msm_dev_internal(uint64_t handle, size_t first, const uint32_t* d_scalars
   if (s->curve == KZGPU_BN254) return msm_affine<BN254Cfg>(s->full, first, d_scalars, n, out_xy, is_inf, h_scalars);
   return msm_affine<BLS381Cfg>(s->full, first, d_scalars, n, out_xy, is_inf, h_scalars);
 }
+
+// kzgpu_sync: a deferred MSM flag is collected here too
+int kz_msm_pending_check() { return msm_flag_wait(); }
 
 int kz_srs_curve(uint64_t handle) {
   const Srs* s = find_srs(handle);
@@ -1785,8 +1845,10 @@ int kzgpu_msm_partial_dev(uint64_t handle, size_t first, const uint64_t* d_scala
   if (!d_out_xyzz || (n && !d_scalars)) return kz_fail(KZGPU_EINVAL, "null pointer");
   int rc = set_smem_attrs();
   if (rc) return rc;
-  if (s->curve == KZGPU_BN254) return msm_core<BN254Cfg>(s->full, first, (const uint32_t*)d_scalars, n, 0, (uint32_t*)d_out_xyzz);
-  return msm_core<BLS381Cfg>(s->full, first, (const uint32_t*)d_scalars, n, 0, (uint32_t*)d_out_xyzz);
+  // returns with the work queued: the partial stays on the device and the caller's exchange is queued right behind it; a
+  // non-canonical scalar is reported by the kzgpu_g1_fold / kzgpu_sync / MSM call that synchronises next
+  if (s->curve == KZGPU_BN254) return msm_core<BN254Cfg>(s->full, first, (const uint32_t*)d_scalars, n, 0, (uint32_t*)d_out_xyzz, nullptr, nullptr, 1, true);
+  return msm_core<BLS381Cfg>(s->full, first, (const uint32_t*)d_scalars, n, 0, (uint32_t*)d_out_xyzz, nullptr, nullptr, 1, true);
 }
 
 int kzgpu_msm_partial(uint64_t handle, size_t first, const uint64_t* scalars, size_t n, uint64_t* d_out_xyzz) {
@@ -1800,8 +1862,8 @@ int kzgpu_msm_partial(uint64_t handle, size_t first, const uint64_t* scalars, si
   // host scalars of this rank's shard: uploaded inside the MSM, chunked and overlapped with the compute like kzgpu_msm
   if ((rc = g_ws.scal.ensure(n * 32 + 32))) return rc;
   const uint32_t* d = (const uint32_t*)g_ws.scal.p;
-  if (s->curve == KZGPU_BN254) return msm_core<BN254Cfg>(s->full, first, d, n, 0, (uint32_t*)d_out_xyzz, scalars);
-  return msm_core<BLS381Cfg>(s->full, first, d, n, 0, (uint32_t*)d_out_xyzz, scalars);
+  if (s->curve == KZGPU_BN254) return msm_core<BN254Cfg>(s->full, first, d, n, 0, (uint32_t*)d_out_xyzz, scalars, nullptr, 1, true);
+  return msm_core<BLS381Cfg>(s->full, first, d, n, 0, (uint32_t*)d_out_xyzz, scalars, nullptr, 1, true);
 }
 
 int kzgpu_g1_fold(int curve, const uint64_t* d_xyzz, size_t count, uint64_t* out_affine_xy, int* is_inf) {
@@ -1820,7 +1882,10 @@ int kzgpu_g1_fold(int curve, const uint64_t* d_xyzz, size_t count, uint64_t* out
   KZ_LAUNCHED();
   uint32_t h[2 * 12 + 1];
   KZ_CUDA(cudaMemcpyAsync(h, g_ws.result.p, (2 * N + 1) * 4, cudaMemcpyDeviceToHost, cx.stream));
+  uint32_t hflag = 0;
+  if ((rc = msm_flag_collect(&hflag))) return rc;
   KZ_CUDA(cudaStreamSynchronize(cx.stream));
+  if ((rc = msm_flag_result(hflag))) return rc;
   memcpy(out_affine_xy, h, 2 * N * 4);
   if (is_inf) *is_inf = (int)h[2 * N];
   return 0;
