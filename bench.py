@@ -1209,15 +1209,41 @@ def run_inproc(args):
     # batched commit of Marlin-sized polynomials (marlin/prover.py:106,142,176 at 2^20 constraints, scaled to the key)
     b = n // 16
     lens = [b + 2] * 4 + [b + 4, 2 * b + 1] + [b, b - 1, b + 2] + [2 * b - 1, 12 * b - 6]
-    polys = [random_scalars(ln, r_mod, seed=60 + j) for j, ln in enumerate(lens)]
-    ms_batch = timed(lambda: device.msm_batch(srs, polys), max(2, K // 2))
+    packed = _ffi.PinnedArray((sum(lens), 4))
+    off = 0
+    for j, ln in enumerate(lens):
+        packed.array[off:off + ln] = random_scalars(ln, r_mod, seed=60 + j)
+        off += ln
+    ms_batch = timed(lambda: device.msm_batch_packed(srs, packed.array, lens), max(2, K // 2))
     # 8 host vectors of 2^(logn-3) elements each through kzgpu_ntt_batch
     m = n // 8
     wl = ints_to_limbs([pow(GEN[curve], (r_mod - 1) // m, r_mod)], r_mod)[0]
     vecs = pinned.array.reshape(8 * m, 4)
     ms_ntt = timed(lambda: device.ntt(curve, vecs, wl, batch=8), max(2, K // 2))
+    pinned.free(); dsc.free(); srs.destroy(); packed.free()
+    # configs[2] across devices: one MSM of 2^k points through kzgpu_msm_dev / kzgpu_msm on all the devices, k = 16 .. sweep_max
+    # (below KZGPU_SHARD_MIN = 2^20 the library keeps the MSM on the primary device); tau-identity at every size
+    sweep = []
+    for lg in range(16, min(args.sweep_max, 26) + 1, 2):
+        nn = 1 << lg
+        t0 = time.perf_counter()
+        s2 = device.Srs.generate(curve, TAU, nn)
+        _ffi.check(_ffi._lib.kzgpu_sync())
+        tb = time.perf_counter() - t0
+        pin2 = _ffi.PinnedArray((nn, 4))
+        pin2.array[:] = random_scalars(nn, r_mod, seed=300 + lg)
+        d2 = _ffi.DeviceBuffer(nn * 32).upload(pin2.array)
+        t0 = time.perf_counter()
+        o2, f2 = device.msm_dev(s2, d2, nn)
+        t_first = time.perf_counter() - t0
+        ok2 = tau_identity(curve, o2, f2, horner_dev(curve, d2, nn, TAU % r_mod))
+        reps = 5 if lg <= 24 else 3
+        sweep.append({"logn": lg, "device_ms": timed(lambda: device.msm_dev(s2, d2, nn), reps),
+                      "host_buffer_ms": timed(lambda: device.msm(s2, pin2.array), reps), "srs_build_s": tb,
+                      "first_call_s": t_first, "check": bool(ok2)})
+        sweep[-1]["points_per_s"] = nn / (sweep[-1]["device_ms"] * 1e-3)
+        d2.free(); pin2.free(); s2.destroy()
     # configs[4]: the device Marlin prover on a synthetic R1CS of 2^marlin_rows_logn rows, its commitments and openings over all devices
-    pinned.free(); dsc.free(); srs.destroy()
     marlin_res = marlin_synthetic_prove(args.marlin_rows_logn)
     clocks = sampler.stop()
     line = {"metric": "g1_msm_points_per_s", "value": n / (ms_host * 1e-3), "unit": "points/s", "n_gpus": nd, "steps": K, "warmup": Wm,
@@ -1232,10 +1258,11 @@ def run_inproc(args):
             "device_resident": {"ms_per_step": ms_dev, "value": n / (ms_dev * 1e-3),
                                 "note": "scalars on the primary device; the other devices pull their slices over NVLink (cudaMemcpyPeerAsync)"},
             "batched_commit": {"polynomials": lens, "ms_per_call": ms_batch, "points_per_s": sum(lens) / (ms_batch * 1e-3),
-                               "note": "kzgpu_msm_batch from pageable host arrays: >= KZGPU_SHARD_MIN coefficients point-sharded, the rest placed "
-                                       "longest-first on the least loaded device (key replicated)"},
+                               "note": "kzgpu_msm_batch from one pinned host buffer: >= KZGPU_SHARD_MIN coefficients point-sharded over all devices "
+                                       "(shard tables sized for the polynomial's length class), the rest placed longest-first (key replicated)"},
             "batched_ntt": {"vectors": 8, "n": m, "ms_per_call": ms_ntt, "elements_per_s": 8 * m / (ms_ntt * 1e-3),
                             "note": "kzgpu_ntt_batch from pinned host memory, whole vectors per device"},
+            "msm_sweep": sweep,
             "marlin_synthetic": marlin_res,
             "gpu_launches": launches, "clocks": clocks, "device": info["name"], "cpu_baseline": None,
             "roofline": None}

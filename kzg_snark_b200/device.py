@@ -161,6 +161,22 @@ def msm_batch(srs, scalar_arrays):
     return out, [bool(x) for x in inf]
 
 
+def msm_batch_packed(srs, packed, lens):
+    """The same call with the k polynomials already concatenated in one (sum(lens), 4) uint64 array (e.g. page-locked memory):
+    no Python-side copy between the caller's buffer and kzgpu_msm_batch."""
+    lib = _ffi.init()
+    k = len(lens)
+    a = _scalars(packed)
+    assert a.shape[0] == sum(lens)
+    out = np.zeros((k, 2 * FP_LIMBS[srs.curve]), dtype=np.uint64)
+    inf = (ctypes.c_int * k)()
+    rc = lib.kzgpu_msm_batch(srs.handle, ptr(a), (ctypes.c_size_t * k)(*lens), k, ptr(out), inf)
+    if rc == _ffi.E_RANGE:
+        raise ValueError(_ffi.last_error())
+    check(rc)
+    return out, [bool(x) for x in inf]
+
+
 def msm_batch_dev(srs, dbuf, poly_len, k):
     """k polynomials of `poly_len` scalars each, back to back on the device (zero padded), in one
     sort / accumulate / reduce pass -> ((k, 2*L) affine limbs, [is_inf])."""
