@@ -1425,6 +1425,20 @@ int ensure_shards(Srs& s, size_t end, std::vector<SrsPart>** out) {
   return 0;
 }
 
+// One device: a polynomial much shorter than the key (Marlin at 2^20 rows commits 1-2 M coefficients against a 12.6 M-point key)
+// would inherit the KEY's window -- c = 22, 2^21 buckets to reduce for ~7 entries per bucket.  The same length-class mechanism
+// gives it a table set of its own: the head [0, E) of the key with the window an E-point MSM wants (built once per class,
+// at most twice the key's tables in total).  Returns the key itself when the polynomial is not at least 4x shorter.
+template <class Cfg>
+const SrsPart* part_for_length(Srs& s, size_t end, int* rc) {
+  *rc = 0;
+  static const bool off = getenv("KZGPU_NO_CLASS_TABLES") != nullptr;
+  if (off || kz_ndev() != 1 || !s.full.c_tab || end < ((size_t)1 << 14) || end * 4 > s.n) return &s.full;
+  std::vector<SrsPart>* set = nullptr;
+  if ((*rc = ensure_shards<Cfg>(s, end, &set))) return nullptr;
+  return (*set)[0].c_tab ? &(*set)[0] : &s.full;
+}
+
 // Replicas: the whole key with its window tables on every device (whole polynomials of a batched commit run where they
 // are placed): one peer copy of the primary's tables per device.
 template <class Cfg>
@@ -1612,8 +1626,12 @@ int kz_msm_dev_internal(uint64_t handle, size_t first, const uint32_t* d_scalars
     if (s->curve == KZGPU_BN254) return msm_sharded<BN254Cfg>(*s, first, n, h_scalars, d_scalars, out_xy, is_inf);
     return msm_sharded<BLS381Cfg>(*s, first, n, h_scalars, d_scalars, out_xy, is_inf);
   }
-  if (s->curve == KZGPU_BN254) return msm_affine<BN254Cfg>(s->full, first, d_scalars, n, out_xy, is_inf, h_scalars);
-  return msm_affine<BLS381Cfg>(s->full, first, d_scalars, n, out_xy, is_inf, h_scalars);
+  if (s->curve == KZGPU_BN254) {
+    const SrsPart* part = part_for_length<BN254Cfg>(*s, first + n, &rc);
+    return part ? msm_affine<BN254Cfg>(*part, first, d_scalars, n, out_xy, is_inf, h_scalars) : rc;
+  }
+  const SrsPart* part = part_for_length<BLS381Cfg>(*s, first + n, &rc);
+  return part ? msm_affine<BLS381Cfg>(*part, first, d_scalars, n, out_xy, is_inf, h_scalars) : rc;
 }
 
 // kzgpu_sync: a deferred MSM flag is collected here too
@@ -1724,8 +1742,12 @@ int kz_msm_batch_dev_internal(uint64_t handle, const uint32_t* d_scalars, size_t
     return kz_fail(KZGPU_ERANGE, "Polynomial degree %zu exceeds maximum allowed degree %zu", poly_len - 1, s->n - 1);
   const int nd = kz_ndev();
   const int L = kzgpu_fp_limbs64(s->curve);
-  if (nd == 1 || poly_len * k < ((size_t)1 << 17)) return msm_batch_on_part(s->full, s->curve, d_scalars, poly_len, k, out_xy, is_inf);
   int rc;
+  if (nd == 1) {
+    const SrsPart* part = s->curve == KZGPU_BN254 ? part_for_length<BN254Cfg>(*s, poly_len, &rc) : part_for_length<BLS381Cfg>(*s, poly_len, &rc);
+    return part ? msm_batch_on_part(*part, s->curve, d_scalars, poly_len, k, out_xy, is_inf) : rc;
+  }
+  if (poly_len * k < ((size_t)1 << 17)) return msm_batch_on_part(s->full, s->curve, d_scalars, poly_len, k, out_xy, is_inf);
   if (poly_len >= shard_min()) {
     for (size_t j = 0; j < k; j++) {
       int* fl = is_inf ? is_inf + j : nullptr;
@@ -1794,7 +1816,12 @@ int kzgpu_msm_batch(uint64_t handle, const uint64_t* scalars, const size_t* lens
     outp[j] = out_affine_xy + j * 2 * L; infp[j] = is_inf ? is_inf + j : nullptr;
   }
   const int nd = kz_ndev();
-  if (nd == 1 || (k == 1 && lens[0] < shard_min())) return msm_batch_host_on_part(s->full, s->curve, ptr.data(), lens, k, outp.data(), infp.data());
+  if (nd == 1) {
+    int rcp;
+    const SrsPart* part = s->curve == KZGPU_BN254 ? part_for_length<BN254Cfg>(*s, maxlen, &rcp) : part_for_length<BLS381Cfg>(*s, maxlen, &rcp);
+    return part ? msm_batch_host_on_part(*part, s->curve, ptr.data(), lens, k, outp.data(), infp.data()) : rcp;
+  }
+  if (k == 1 && lens[0] < shard_min()) return msm_batch_host_on_part(s->full, s->curve, ptr.data(), lens, k, outp.data(), infp.data());
   // several devices
   std::vector<size_t> order, owner(k, 0);
   int rc;
