@@ -815,6 +815,72 @@ __global__ void __launch_bounds__(128) srs_generate_kernel(uint32_t* pts, size_t
   for (int k = 0; k < P::N; k++) { o[k] = a.x.v[k]; o[P::N + k] = a.y.v[k]; }
 }
 
+// ---- tiny MSMs (n * W <= kTinyEntries digit entries: the 22-point key of the bundled PLONK instance, the 201-point key of
+// the bundled Marlin instance) -- no sort, no buckets, two launches.  With window tables every term of the sum is
+// digit * T_w[i] with |digit| <= 2^(c-1) and c <= 10 for such keys: thread (i, w) forms that small multiple by double-and-add
+// (<= c doublings, a ~50 us chain), the block tree-sums its 256 terms, and msm_tiny_fold_kernel sums the block partials of
+// each polynomial.  The bucket path spends ~0.4 ms of fixed cost (21 launches) on the same work.
+constexpr uint32_t kTinyEntries = 16384;
+constexpr uint32_t kTinyThreads = 256;
+
+template <class Cfg>
+__global__ void __launch_bounds__(kTinyThreads) msm_tiny_kernel(const uint32_t* __restrict__ points, const uint32_t* __restrict__ scalars,
+                                                              uint32_t poly_len, uint32_t first, uint32_t n_srs, uint32_t c, uint32_t W,
+                                                              uint32_t top_bits, DigitOffset off, uint32_t* __restrict__ flag,
+                                                              uint32_t* __restrict__ partials) {
+  using P = typename Cfg::Fp;
+  extern __shared__ uint32_t shw[];
+  const uint32_t e = blockIdx.x * kTinyThreads + threadIdx.x;      // entry = (point i, window w) of polynomial blockIdx.y
+  XYZZ<P> acc = xyzz_inf<P>();
+  if (e < poly_len * W) {
+    const uint32_t i = e / W, w = e - i * W;
+    const size_t gi = (size_t)blockIdx.y * poly_len + i;
+    uint32_t s[8];
+    load_scalar_plus_offset(scalars, gi, off, s);
+    if (w == 0 && top_bits < 32) {
+      const uint32_t top = __ldg(reinterpret_cast<const uint4*>(scalars + gi * 8) + 1).w;
+      if (top >> top_bits) atomicOr(flag, 1u);
+    }
+    const int d = signed_digit(s, w, c, W);
+    if (d != 0) {
+      Affine<P> pt = ld_affine<P>(points, (size_t)w * n_srs + first + i);
+      if (!aff_is_inf<P>(pt)) {
+        if (d < 0) pt.y = fe_neg<P>(pt.y);
+        acc = xyzz_mul_u32<P>(xyzz_from_affine<P>(pt), (uint32_t)(d < 0 ? -d : d));
+      }
+    }
+  }
+  st_xyzz<P>(shw, threadIdx.x, acc);
+  __syncthreads();
+  for (uint32_t o = kTinyThreads / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      XYZZ<P> a = ld_xyzz<P>(shw, threadIdx.x), b = ld_xyzz<P>(shw, threadIdx.x + o);
+      st_xyzz<P>(shw, threadIdx.x, xyzz_add<P>(a, b));
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) st_xyzz<P>(partials, (size_t)blockIdx.y * gridDim.x + blockIdx.x, ld_xyzz<P>(shw, 0));
+}
+
+// block j: sum of the `count` block partials of polynomial j -> out[j] (XYZZ)
+template <class Cfg>
+__global__ void __launch_bounds__(64) msm_tiny_fold_kernel(const uint32_t* __restrict__ partials, uint32_t count, uint32_t* __restrict__ out) {
+  using P = typename Cfg::Fp;
+  extern __shared__ uint32_t shw[];
+  XYZZ<P> acc = xyzz_inf<P>();
+  for (uint32_t k = threadIdx.x; k < count; k += blockDim.x) acc = xyzz_add<P>(acc, ld_xyzz<P>(partials, (size_t)blockIdx.x * count + k));
+  st_xyzz<P>(shw, threadIdx.x, acc);
+  __syncthreads();
+  for (uint32_t o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      XYZZ<P> a = ld_xyzz<P>(shw, threadIdx.x), b = ld_xyzz<P>(shw, threadIdx.x + o);
+      st_xyzz<P>(shw, threadIdx.x, xyzz_add<P>(a, b));
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) st_xyzz<P>(out, blockIdx.x, ld_xyzz<P>(shw, 0));
+}
+
 // ---------------------------------------------------------------- host side
 uint32_t choose_c(size_t n, int bits) {
   const char* env = getenv("KZGPU_MSM_C");
@@ -1036,6 +1102,33 @@ int msm_core(const SrsPart& srs, size_t first, const uint32_t* d_scalars, size_t
     uint32_t bit = w * c + (c - 1);
     if (bit < 256) doff.w[bit >> 5] |= 1u << (bit & 31);
   }
+  static const bool tiny_off = getenv("KZGPU_MSM_NO_TINY") != nullptr;
+  if (!tiny_off && tabled && nchunks == 1 && n && (n / batch) * (size_t)W <= kTinyEntries && !cx.profile) {
+    // tiny MSM: every (point, window) term by double-and-add, two launches (see msm_tiny_kernel)
+    const uint32_t poly_len = (uint32_t)(n / batch);
+    const uint32_t blocks = (uint32_t)kz_div_up((size_t)poly_len * W, kTinyThreads);
+    if ((rc = g_ws.partials.ensure((size_t)blocks * batch * 4 * P::N * 4))) return rc;
+    if ((rc = g_ws.winsums.ensure((size_t)batch * 4 * P::N * 4))) return rc;
+    if (h_scalars) KZ_CUDA(cudaStreamWaitEvent(st, cx.copy_ev[0], 0));
+    msm_tiny_kernel<Cfg><<<dim3(blocks, batch), kTinyThreads, kTinyThreads * 4 * P::N * 4, st>>>(
+        srs.d_points, d_scalars, poly_len, (uint32_t)first, (uint32_t)srs.n, c, W, geo.top_bits, doff, flag, (uint32_t*)g_ws.partials.p);
+    KZ_LAUNCHED();
+    msm_tiny_fold_kernel<Cfg><<<batch, 64, 64 * 4 * P::N * 4, st>>>((uint32_t*)g_ws.partials.p, blocks, (uint32_t*)g_ws.winsums.p);
+    KZ_LAUNCHED();
+    if (mode == 1) {                                       // affine on the device (rare): the window fold kernel with one window
+      msm_final_kernel<Cfg><<<batch, 32, 0, st>>>((uint32_t*)g_ws.winsums.p, 1, c, 1, d_out);
+      KZ_LAUNCHED();
+    } else {
+      KZ_CUDA(cudaMemcpyAsync(d_out, g_ws.winsums.p, (size_t)batch * 4 * P::N * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    if (defer && mode == 0) { g_flag_pending[kz_slot()] = true; return 0; }
+    uint32_t hflag = 0;
+    KZ_CUDA(cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, st));
+    if (mode == 2 && h_out_xyzz) KZ_CUDA(cudaMemcpyAsync(h_out_xyzz, g_ws.winsums.p, (size_t)batch * 4 * P::N * 4, cudaMemcpyDeviceToHost, st));
+    KZ_CUDA(cudaStreamSynchronize(st));
+    if (hflag) return kz_fail(KZGPU_ERANGE, "a scalar is not a canonical residue (>= 2^%d)", R::BITS);
+    return 0;
+  }
   const uint32_t* d_scalars_all = d_scalars;
   const size_t n_all = n, first_all = first;
   (void)n_all;
@@ -1241,6 +1334,7 @@ int set_smem_attrs() {
   if (done[kz_slot()]) return 0;
   KZ_CUDA(cudaFuncSetAttribute(msm_window_kernel<BLS381Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 4 * 12 * 4));
   KZ_CUDA(cudaFuncSetAttribute(g1_fold_kernel<BLS381Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 4 * 12 * 4));
+  KZ_CUDA(cudaFuncSetAttribute(msm_tiny_kernel<BLS381Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTinyThreads * 4 * 12 * 4));
   KZ_CUDA(cudaFuncSetAttribute(msm_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortStage * 8 + (2 * kMaxCoarse + 512) * 4));
   KZ_CUDA(cudaFuncSetAttribute(msm_fine_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 << 13) + (512 + kSortChunk) * 4));
   done[kz_slot()] = true;

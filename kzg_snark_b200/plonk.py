@@ -23,6 +23,7 @@ There is no CPU path: everything below goes through libkzgpu.so.
 """
 
 import ctypes
+import os
 import hashlib
 import random
 import struct
@@ -74,14 +75,20 @@ class Transcript:
 
 
 _POOL = {}          # capacity in bytes -> idle DeviceBuffers (cudaMalloc / cudaFree stay out of the prove loop)
+_POOL_BYTES = 0     # bytes parked in the pool
+# Idle buffers above this many bytes go back to the driver instead of being parked: a long-lived process that proves circuits of
+# many different sizes must not grow monotonically.  Default 8 GiB (a 2^20-gate prove parks ~3 GiB); KZGPU_POOL_GIB overrides.
+_POOL_CAP = int(float(os.environ.get("KZGPU_POOL_GIB", "8")) * (1 << 30))
 
 
 def release_pool():
     """Return every pooled device buffer to the driver."""
+    global _POOL_BYTES
     for bufs in _POOL.values():
         for b in bufs:
             b.free()
     _POOL.clear()
+    _POOL_BYTES = 0
 
 
 class DVec:
@@ -92,8 +99,13 @@ class DVec:
     def __init__(self, n, zero=False):
         self.n = int(n)
         cap = max(self.n, 1) * 32
+        global _POOL_BYTES
         idle = _POOL.get(cap)
-        self.buf = idle.pop() if idle else _ffi.DeviceBuffer(cap)
+        if idle:
+            self.buf = idle.pop()
+            _POOL_BYTES -= cap
+        else:
+            self.buf = _ffi.DeviceBuffer(cap)
         if zero:
             check(_ffi._lib.kzgpu_memset(self.buf.ptr, 0, self.n * 32))
 
@@ -130,8 +142,13 @@ class DVec:
         check(_ffi._lib.kzgpu_d2d(self.at(dst_off), src.at(src_off), count * 32))
 
     def free(self):
+        global _POOL_BYTES
         if self.buf is not None:
-            _POOL.setdefault(self.buf.nbytes, []).append(self.buf)
+            if _POOL_BYTES + self.buf.nbytes > _POOL_CAP:
+                self.buf.free()                                   # the pool is full: back to the driver
+            else:
+                _POOL.setdefault(self.buf.nbytes, []).append(self.buf)
+                _POOL_BYTES += self.buf.nbytes
             self.buf = None
 
     def __del__(self):

@@ -57,7 +57,7 @@ def test_reference_main_demos_on_the_gpu_dropin():
         launches = _ffi.launch_count() - l0
         calls = [c["fn"] for c in rr.trace]
     assert text.count("PASS") == 3 and "FAIL" not in text, text
-    assert launches > 100, "the demos did not reach the GPU"
+    assert launches > 30, "the demos did not reach the GPU"      # tiny keys: 2 - 3 launches per MSM (msm_tiny_kernel), ~90 in all
     assert calls.count("commit") >= 1 + 4 + 4 and calls.count("open") >= 1 + 2 + 2 and "fft_ff_interpolation" in calls
 
 
