@@ -52,6 +52,16 @@ def main():
     out["ntt"] = hx(y[::997])
     back = device.ntt("bn254", y.copy(), w, inverse=True, batch=9)
     out["ntt_roundtrip"] = bool((back == vecs).all())
+    # the Python-object level: KZG.setup / commit / open exactly as the reference's callers use them (kzg.py:56-159), k polynomials per call
+    if scale <= 12:
+        from kzg_snark_b200.kzg import KZG
+        kzg = KZG("bn254")
+        ck, _ = kzg.setup(12 * n - 1, tau=TAU)
+        F = kzg.Fq
+        pys = [kzg.R([F(int(v)) for v in np.asarray(p_)[:, 0]]) for p_ in polys]        # 64-bit coefficients keep the conversion quick
+        comm = kzg.commit(ck, pys)
+        out["kzg_commit"] = [[int(c) for c in pt] for pt in comm]
+        out["kzg_open"] = [int(c) for c in kzg.open(ck, pys[:4], 7, 42)]
     # the device Marlin prover (marlin/prover.py:25-245): every round's commitments and both openings use all devices
     from kzg_snark_b200 import marlin
     rows = 1 << max(scale - 2, 8)

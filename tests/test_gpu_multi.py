@@ -40,4 +40,6 @@ def test_marlin_sized_commits_on_all_gpus_match_one_gpu(scale, shard_min):
     assert one["ndev"] == 1 and many["ndev"] == ng
     for k in ("commits", "infs", "msm", "msm_offset", "msm_dev", "open", "ntt", "ntt_roundtrip", "marlin"):
         assert one[k] == many[k], k
+    if scale <= 12:                                   # KZG.commit / KZG.open with Python objects, all GPUs against one
+        assert one["kzg_commit"] == many["kzg_commit"] and len(many["kzg_commit"]) == 11 and one["kzg_open"] == many["kzg_open"]
     assert many["ntt_roundtrip"] is True and many["launches"] > one["launches"] // 2

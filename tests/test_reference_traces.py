@@ -160,3 +160,26 @@ def test_product_transcript_agrees_with_reference_transcript():
         if ref is not None:
             ref.append_message(label, data)
             assert int(ref.get_challenge(label + "-c")) == c1
+
+
+def test_reference_is_staged_byte_for_byte_and_its_main_runs():
+    """`__graft_entry__.build()` stages the reference under the git-ignored baseline/_ref/ (oracle/refstage.py) so that it
+    travels to the GPU box: every staged file must equal the mounted original, and the reference's own main.py -- imported
+    unmodified, its Sage pickles decoded through the stock pickle.load (oracle/sagepickle.py) -- must print PASS three times
+    on the CPU stand-ins.  (The same three demos on top of the GPU drop-in: tests/test_gpu_reference.py.)"""
+    import contextlib
+    import io
+    from oracle import refrun, refstage
+    if not refrun.available():
+        pytest.skip("no reference tree here")
+    if os.path.isdir(refstage.SOURCE):
+        assert refstage.stage() == refstage.STAGED and refstage.verify_staged() is True
+    with refrun.ReferenceRun(seed=3, record=False) as rr:
+        main = rr.main()
+        assert main.__file__.startswith(refrun.REFERENCE_ROOT) and main.KZG.__module__ == "kzg"
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            main.demo_kzg()
+            main.demo_plonk()
+            main.demo_marlin()
+    assert buf.getvalue().count("PASS") == 3 and "FAIL" not in buf.getvalue()
