@@ -1,4 +1,8 @@
-"""Multi-GPU layout (one process per GPU, torch.distributed for the plumbing only).
+"""Multi-GPU layout, harness flavour: one process per GPU, torch.distributed for the plumbing only.
+
+(The PRODUCT path needs none of this: `KZGPU_DEVICES=all` / `_ffi.init_multi([...])` initialises libkzgpu.so on several devices
+of one plain process and the library shards MSMs, places batched commits and deals batched NTTs itself -- `kzgpu_init_multi`,
+DESIGN.md section 6.  This module serves `bench.py --gpus N` under torchrun, which is how the driver launches the benchmark.)
 
 The reference is single-process and has no parallelism (SURVEY.md sections 0, 8e); this layout
 is new.  The path shards in exactly two ways:
