@@ -1082,13 +1082,16 @@ def run_gpu(args):
         cpu_group = dist.new_group(backend="gloo")
         barrier()
         if rank == 0:
-            _ffi.shutdown()
-            _ffi.init_multi(list(range(world)))
             try:
+                _ffi.shutdown()
+                _ffi.init_multi(list(range(world)))
                 marlin_multi = marlin_synthetic_prove(args.marlin_rows_logn)
             except Exception as exc:                                     # the primary line must survive
                 marlin_multi = {"error": repr(exc)[:300]}
-            _ffi.shutdown()
+            try:
+                _ffi.shutdown()
+            except Exception:
+                pass
         dist.barrier(group=cpu_group)
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
