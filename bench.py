@@ -1079,9 +1079,12 @@ def run_gpu(args):
         # The prover is one process (its polynomials live on one device); with several devices the LIBRARY spreads each round's
         # commitments and openings (kzgpu_init_multi).  Rank 0 therefore re-initialises the library on the job's N GPUs while the
         # other ranks -- idle, their buffers freed -- wait on a CPU-side (gloo) barrier.
-        cpu_group = dist.new_group(backend="gloo")
+        try:
+            cpu_group = dist.new_group(backend="gloo")
+        except Exception:                                                # no gloo: every rank skips this leg alike
+            cpu_group = None
         barrier()
-        if rank == 0:
+        if rank == 0 and cpu_group is not None:
             try:
                 _ffi.shutdown()
                 _ffi.init_multi(list(range(world)))
@@ -1092,7 +1095,8 @@ def run_gpu(args):
                 _ffi.shutdown()
             except Exception:
                 pass
-        dist.barrier(group=cpu_group)
+        if cpu_group is not None:
+            dist.barrier(group=cpu_group)
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
     cpu = None
