@@ -1008,15 +1008,21 @@ def run_gpu(args):
     dtype = "u32x8 (256-bit modular integers, Montgomery)" if curve == "bn254" else \
         "u32x12 base field / u32x8 scalars (384 / 256-bit modular integers, Montgomery)"
 
+    pending = []
+
     def finish():
+        # the communicator is torn down FIRST, so that with NCCL_DEBUG=INFO its chatter precedes the result line, which is
+        # the last thing this process prints (rank 0 only)
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
+        for text in pending:
+            sys.stdout.write("\n" + text + "\n")
+        sys.stdout.flush()
         return 0
 
     def emit(line):
-        sys.stdout.write("\n" + json.dumps(line) + "\n")
-        sys.stdout.flush()
+        pending.append(json.dumps(line))
 
     if args.workload == "marlin":
         res = bench_marlin()
