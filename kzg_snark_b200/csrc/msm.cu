@@ -1040,10 +1040,16 @@ int msm_core(const SrsPart& srs, size_t first, const uint32_t* d_scalars, size_t
   const size_t max_entries = (size_t)chunk_n * W;
   if (max_entries >= 0xffffffffull) return kz_fail(KZGPU_EINVAL, "MSM of %zu points x %u digits exceeds 2^32 entries", n, W);
   const size_t nblk = kz_div_up(nb, 1024);
-  // tasks: heavy buckets are split into <= T-point tasks, T from the chunk's mean bucket load
+  // tasks: heavy buckets are split into <= T-point tasks, T from the chunk's mean bucket load -- and from the load of the TOP
+  // window's buckets: that window holds only BITS - c (W - 1) bits, so its 2^top buckets receive every point (128 per bucket for
+  // a 2^21-point shard at c = 20, against a mean of 53).  A T just below that load split half of them in two and left ~8,000
+  // two-task buckets for msm_merge_kernel (140 us of a 5.2 ms MSM); T covers it now whenever it fits the 1024 cap.
+  const uint32_t top_window_bits = (uint32_t)R::BITS - c * (W - 1);
   auto task_T = [&](size_t cn) {
     uint32_t mean = (uint32_t)((((size_t)cn / batch) * (tabled ? W : 1u)) / B) + 1, t = 32;
     while (t < 2 * mean && t < 1024) t <<= 1;
+    const size_t top_load = top_window_bits < 31 ? (((size_t)cn / batch) >> top_window_bits) : 0;
+    while ((size_t)t < top_load + top_load / 4 + 8 && t < 1024) t <<= 1;
     return t;
   };
   size_t max_tasks = 0, max_multi = 0;
@@ -1082,7 +1088,10 @@ int msm_core(const SrsPart& srs, size_t first, const uint32_t* d_scalars, size_t
   if (CH > B) CH = B;
   const uint32_t cpw = (B + CH - 1) / CH;
   if ((rc = g_ws.partials.ensure((size_t)cpw * Wb * 4 * P::N * 4))) return rc;
-  const size_t lvl1 = kz_div_up(cpw, 1024);
+  // tree sum of the per-chunk partials: kTreeSpan partials per block and level (128 threads: span / 128 serial additions, then 7
+  // tree levels); 256 keeps the serial part at 2 additions -- the phase is latency-bound
+  constexpr uint32_t kTreeSpan = 256;
+  const size_t lvl1 = kz_div_up(cpw, kTreeSpan);
   if ((rc = g_ws.winsums.ensure(2 * (size_t)Wb * (lvl1 + 1) * 4 * P::N * 4))) return rc;
 
   uint32_t* flag = (uint32_t*)g_ws.flag.p;
@@ -1237,14 +1246,13 @@ int msm_core(const SrsPart& srs, size_t first, const uint32_t* d_scalars, size_t
   msm_reduce_kernel<Cfg><<<(unsigned)kz_div_up((size_t)cpw * Wb, 128), 128, 0, st>>>((uint32_t*)g_ws.buckets.p, B, CH, cpw, Wb,
                                                                                     (uint32_t*)g_ws.partials.p);
   KZ_LAUNCHED();
-  // tree sum of the chunk partials of each window, 1024 per block and level
   const uint32_t* lvl_in = (const uint32_t*)g_ws.partials.p;
   uint32_t count = cpw, lvl_launches = 0;
   uint32_t* pong[2] = {(uint32_t*)g_ws.winsums.p, (uint32_t*)g_ws.winsums.p + (size_t)Wb * (lvl1 + 1) * 4 * P::N};
   while (count > 1) {
-    uint32_t blocks = (count + 1023) / 1024;
+    uint32_t blocks = (count + kTreeSpan - 1) / kTreeSpan;
     uint32_t* lvl_out = pong[lvl_launches & 1];
-    msm_window_kernel<Cfg><<<dim3(blocks, Wb), 128, 128 * 4 * P::N * 4, st>>>(lvl_in, count, 1024, lvl_out);
+    msm_window_kernel<Cfg><<<dim3(blocks, Wb), 128, 128 * 4 * P::N * 4, st>>>(lvl_in, count, kTreeSpan, lvl_out);
     KZ_LAUNCHED();
     lvl_in = lvl_out; count = blocks; lvl_launches++;
   }
