@@ -95,6 +95,16 @@ template <class P> void curve_op(const std::string& op, std::istringstream& in) 
     r = xyzz_add<P>(t, u);               // 2a + 2b
     xyzz_madd<P>(r, aff_neg<P>(a));      // a + 2b
     xyzz_madd<P>(r, aff_neg<P>(b));      // a + b
+  } else if (op == "lzadd3") {     // the same through the semi-reduced full addition, incl. the doubling and cancellation branches
+    in >> x2 >> y2;
+    Affine<P> b; b.x = M<P>(x2); b.y = M<P>(y2);
+    XYZZ<P> t = xyzz_dbl_affine<P>(a);   // 2a
+    XYZZ<P> u = xyzz_dbl_affine<P>(b);   // 2b
+    r = xyzz_add_lz<P>(t, u);            // 2a + 2b   (a == b: doubling branch; a == -b: infinity)
+    r = xyzz_add_lz<P>(r, xyzz_from_affine<P>(aff_neg<P>(a)));   // a + 2b
+    r = xyzz_add_lz<P>(r, xyzz_add_lz<P>(xyzz_from_affine<P>(aff_neg<P>(b)), xyzz_inf<P>()));   // a + b
+    r = xyzz_add_lz<P>(xyzz_inf<P>(), r);
+    r = xyzz_reduce_lz<P>(r);
   } else if (op == "dbl") {
     r = xyzz_dbl<P>(xyzz_dbl_affine<P>(a));   // 4a
   } else if (op == "smul") {

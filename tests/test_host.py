@@ -138,6 +138,7 @@ def test_csrc_semi_reduced_arithmetic_on_host(host_arith):
                 lines.append(f"{tag} lzmadd {A[0]:x} {A[1]:x} {B[0]:x} {B[1]:x}"); expect.append("%x %x" % e)
                 if A != (0, 0) and B != (0, 0):
                     lines.append(f"{tag} lzchain {A[0]:x} {A[1]:x} {B[0]:x} {B[1]:x}"); expect.append("%x %x" % e)
+                    lines.append(f"{tag} lzadd3 {A[0]:x} {A[1]:x} {B[0]:x} {B[1]:x}"); expect.append("%x %x" % e)
     out = subprocess.run([host_arith], input="\n".join(lines) + "\n", capture_output=True, text=True).stdout.split("\n")
     for i, (l, e, o) in enumerate(zip(lines, expect, out)):
         if i >= n_field:
