@@ -39,13 +39,19 @@ def _field_id(F, sample=None):
     return _FIELD_BY_ORDER[q], q
 
 
+def _elements(F, ints):
+    """canonical residues -> the caller's element type (bulk constructor of the shim field when it has one)."""
+    bulk = getattr(F, "from_canonical_ints", None)
+    return bulk(ints) if bulk is not None else [F(v) for v in ints]
+
+
 def _transform(values, w, F, inverse, coset=None):
     fid, q = _field_id(F, w)
     data = ints_to_limbs(values, q)
     wl = int_to_limbs(w, q)
     cl = None if coset is None else int_to_limbs(coset, q)
     device.ntt(fid, data, wl, inverse=inverse, coset_limbs=cl)
-    return [F(v) for v in limbs_to_ints(data)]
+    return _elements(F, limbs_to_ints(data))
 
 
 def _ragged(data, w, fid, q):
@@ -83,7 +89,7 @@ def fft_ff(coeffs, w, F):
         raise RecursionError("maximum recursion depth exceeded")        # fft_ff.py:20-26 on an empty list never terminates
     if n & (n - 1):
         fid, q = _field_id(F, w)
-        return [F(v) for v in limbs_to_ints(_ragged(ints_to_limbs(coeffs, q), int(w) % q, fid, q))]
+        return _elements(F, limbs_to_ints(_ragged(ints_to_limbs(coeffs, q), int(w) % q, fid, q)))
     return _transform(coeffs, w, F, inverse=False)
 
 
@@ -99,7 +105,7 @@ def ifft_ff(values, w, F):
         fid, q = _field_id(F, w)
         res = _ragged(ints_to_limbs(values, q), pow(int(w) % q, -1, q), fid, q)
         ninv = np.ascontiguousarray(np.broadcast_to(int_to_limbs(pow(n % q, -1, q), q), (n, 4)))
-        return [F(v) for v in limbs_to_ints(device.field_op(fid, 1, 0, res, ninv))]
+        return _elements(F, limbs_to_ints(device.field_op(fid, 1, 0, res, ninv)))
     return _transform(values, w, F, inverse=True)
 
 

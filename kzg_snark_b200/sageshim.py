@@ -167,6 +167,18 @@ class GFShim:
             return self(x.to_poly())
         return FieldElement(int(x), self)
 
+    def from_canonical_ints(self, ints):
+        """list of elements from residues already in [0, q) -- the results of a device call -- without the per-element
+        coercion and reduction of __call__ (the Python-object boundary of fft_ff at 2^18 elements is otherwise mostly this)."""
+        new, cls, out = object.__new__, FieldElement, []
+        append = out.append
+        for v in ints:
+            e = new(cls)
+            e.n = v
+            e.F = self
+            append(e)
+        return out
+
     def order(self):
         return self.q
 
