@@ -822,7 +822,7 @@ __global__ void __launch_bounds__(128) srs_generate_kernel(uint32_t* pts, size_t
 // digit * T_w[i] with |digit| <= 2^(c-1) and c <= 10 for such keys: thread (i, w) forms that small multiple by double-and-add
 // (<= c doublings, a ~50 us chain), the block tree-sums its 256 terms, and msm_tiny_fold_kernel sums the block partials of
 // each polynomial.  The bucket path spends ~0.4 ms of fixed cost (21 launches) on the same work.
-constexpr uint32_t kTinyEntries = 16384;
+constexpr uint32_t kTinyEntries = 98304;      // up to ~4,000 points: above that the bucket method does less work
 constexpr uint32_t kTinyThreads = 256;
 
 template <class Cfg>
