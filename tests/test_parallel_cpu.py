@@ -102,3 +102,23 @@ def test_point_sharded_commit_over_gloo(n_total):
         assert p.exitcode == 0
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] and r[2] for r in res), res
+
+
+def test_strong_scaling_check_formula():
+    """bench.py's correctness check of a point-sharded MSM at N ranks: rank k evaluates its slice p_k at tau on the device and the
+    ranks' values are combined as sum_k p_k(tau) * tau^(start_k) = p(tau), the scalar of the tau-identity commit == p(tau) * G1
+    (kzg.py:108).  Checked here on plain integers for every split bench.py uses."""
+    from kzg_snark_b200.parallel import shard_range
+    cv = get_curve("bn254")
+    rng = random.Random(5)
+    n = 1 << 10
+    tau = rng.randrange(1, cv.r)
+    p = [rng.randrange(cv.r) for _ in range(n)]
+    whole = poly_eval(p, tau, cv.r)
+    for world in (1, 2, 4, 8):
+        parts = []
+        for rank in range(world):
+            start, cnt = shard_range(n, world, rank)
+            assert (start, cnt) == (rank * (n // world), n // world)          # bench.py: start = rank * n, n = n_total // world
+            parts.append(poly_eval(p[start:start + cnt], tau, cv.r) * pow(tau, start, cv.r) % cv.r)
+        assert sum(parts) % cv.r == whole
